@@ -1,0 +1,241 @@
+"""CPU oracle for the motion-compensation hot path -- TEST INFRASTRUCTURE, NOT PRODUCT.
+
+Only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s ``cpu_baseline`` /
+``--impl reference`` legs may import this module. The product path (the CUDA
+extension behind ``include/diffcodec_b200.h``) never does, and fails loudly when
+its shared library is missing instead of falling back to anything here.
+
+What is restated, and from where (paths relative to the upstream repository):
+
+* ``splat_fwd / splat_ingrad / splat_flowgrad`` -> ``liboracle.so``
+  (``softsplat_oracle.c``): the three kernels of ``controlnet/softsplat.py:284-335,
+  368-423, 439-512`` in sequential canonical order.
+* ``OracleSplatFunc``  -> ``softsplat_func`` (``controlnet/softsplat.py:277-528``).
+* ``softsplat``        -> the mode wrapper ``controlnet/softsplat.py:232-274``.
+* ``compute_mask / feature_warper / resize_and_normalize_flow_batched``
+                       -> ``controlnet/control_utils.py:11-17, 49-72, 74-97``.
+* ``residual_recipe``  -> ``controlnet/residual_utils.py:151-199`` and
+                          ``controlnet/dataset.py:224-265``.
+* ``backwarp``         -> ``cmp/models/modules/warp.py:9-25`` (calls torch's own CPU
+                          ``grid_sample``, the reference's actual callee).
+
+Parity pin: the reference has no tests or golden vectors for this path. The
+restatement is pinned against the reference's *own kernel text*, templated by its
+own ``cuda_kernel()`` and executed sequentially on the CPU, see
+``oracle/ref_emulation.py`` and ``tests/golden/ref_emu_*.npz``.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+
+def build(force: bool = False) -> str:
+    """Compile liboracle.so with the committed Makefile (gcc only)."""
+    so = os.path.join(_HERE, "liboracle.so")
+    src = os.path.join(_HERE, "softsplat_oracle.c")
+    if force or not os.path.exists(so) or os.path.getmtime(so) < os.path.getmtime(src):
+        subprocess.check_call(["make", "-s", "-C", _HERE, "liboracle.so"] + (["-B"] if force else []))
+    return so
+
+
+def lib() -> ctypes.CDLL:
+    global _LIB
+    if _LIB is None:
+        _LIB = ctypes.CDLL(build())
+        _LIB.orc_max_threads.restype = ctypes.c_int
+    return _LIB
+
+
+def _ptr(a: np.ndarray):
+    return a.ctypes.data_as(ctypes.c_void_p)
+
+
+def _suffix(dtype) -> str:
+    if dtype == np.float32:
+        return "f32"
+    if dtype == np.float64:
+        return "f64"
+    raise TypeError(f"oracle supports float32/float64, got {dtype}")
+
+
+def _prep(*arrays):
+    dt = arrays[0].dtype
+    return [np.ascontiguousarray(a, dtype=dt) for a in arrays]
+
+
+def splat_fwd(tin: np.ndarray, flow: np.ndarray) -> np.ndarray:
+    """Sum-splat of ``tin [N,C,H,W]`` by ``flow [N,2,H,W]`` (softsplat.py:290-335)."""
+    tin, flow = _prep(tin, flow)
+    n, c, h, w = tin.shape
+    assert flow.shape == (n, 2, h, w)
+    out = np.zeros_like(tin)
+    getattr(lib(), "orc_splat_fwd_" + _suffix(tin.dtype))(_ptr(tin), _ptr(flow), _ptr(out), n, c, h, w)
+    return out
+
+
+def splat_fwd_mt(tin: np.ndarray, flow: np.ndarray, threads: int = 0) -> np.ndarray:
+    """Frame-parallel float32 forward for the CPU baseline (bit-identical to splat_fwd)."""
+    tin, flow = _prep(tin.astype(np.float32, copy=False), flow.astype(np.float32, copy=False))
+    n, c, h, w = tin.shape
+    out = np.zeros_like(tin)
+    lib().orc_splat_fwd_f32_mt(_ptr(tin), _ptr(flow), _ptr(out), n, c, h, w, int(threads))
+    return out
+
+
+def max_threads() -> int:
+    return int(lib().orc_max_threads())
+
+
+def splat_ingrad(flow: np.ndarray, outgrad: np.ndarray) -> np.ndarray:
+    """softsplat.py:376-423."""
+    outgrad, flow = _prep(outgrad, flow)
+    n, c, h, w = outgrad.shape
+    ingrad = np.zeros_like(outgrad)
+    getattr(lib(), "orc_splat_ingrad_" + _suffix(outgrad.dtype))(_ptr(flow), _ptr(outgrad), _ptr(ingrad), n, c, h, w)
+    return ingrad
+
+
+def splat_flowgrad(tin: np.ndarray, flow: np.ndarray, outgrad: np.ndarray) -> np.ndarray:
+    """softsplat.py:447-512."""
+    tin, flow, outgrad = _prep(tin, flow, outgrad)
+    n, c, h, w = tin.shape
+    flowgrad = np.zeros_like(flow)
+    getattr(lib(), "orc_splat_flowgrad_" + _suffix(tin.dtype))(
+        _ptr(tin), _ptr(flow), _ptr(outgrad), _ptr(flowgrad), n, c, h, w)
+    return flowgrad
+
+
+class OracleSplatFunc(torch.autograd.Function):
+    """CPU stand-in for ``softsplat_func`` (controlnet/softsplat.py:277-528)."""
+
+    @staticmethod
+    def forward(ctx, tenIn, tenFlow):
+        out = torch.from_numpy(splat_fwd(tenIn.detach().numpy(), tenFlow.detach().numpy()))
+        ctx.save_for_backward(tenIn, tenFlow)
+        return out
+
+    @staticmethod
+    def backward(ctx, tenOutgrad):
+        tenIn, tenFlow = ctx.saved_tensors
+        g = tenOutgrad.contiguous().numpy()
+        gi = gf = None
+        if ctx.needs_input_grad[0]:
+            gi = torch.from_numpy(splat_ingrad(tenFlow.detach().numpy(), g))
+        if ctx.needs_input_grad[1]:
+            gf = torch.from_numpy(splat_flowgrad(tenIn.detach().numpy(), tenFlow.detach().numpy(), g))
+        return gi, gf
+
+
+def softsplat(tenIn, tenFlow, tenMetric, strMode: str):
+    """Mode wrapper, restating controlnet/softsplat.py:232-274 on CPU tensors."""
+    base = strMode.split("-")[0]
+    assert base in ("sum", "avg", "linear", "soft")
+    if strMode in ("sum", "avg"):
+        assert tenMetric is None
+    if base in ("linear", "soft"):
+        assert tenMetric is not None
+
+    if strMode == "avg":
+        ones = tenIn.new_ones([tenIn.shape[0], 1, tenIn.shape[2], tenIn.shape[3]])
+        tenIn = torch.cat([tenIn, ones], 1)
+    elif base == "linear":
+        tenIn = torch.cat([tenIn * tenMetric, tenMetric], 1)
+    elif base == "soft":
+        tenIn = torch.cat([tenIn * tenMetric.exp(), tenMetric.exp()], 1)
+
+    tenOut = OracleSplatFunc.apply(tenIn, tenFlow)
+
+    if base in ("avg", "linear", "soft"):
+        norm = tenOut[:, -1:, :, :]
+        parts = strMode.split("-")
+        if len(parts) == 1 or parts[1] == "addeps":
+            norm = norm + 0.0000001
+        elif parts[1] == "zeroeps":
+            norm = torch.where(norm == 0.0, torch.ones_like(norm), norm)  # values of :263, no aliasing
+        elif parts[1] == "clipeps":
+            norm = norm.clip(0.0000001, None)
+        tenOut = tenOut[:, :-1, :, :] / norm
+    return tenOut
+
+
+def compute_mask(flow_a, flow_b):
+    """controlnet/control_utils.py:11-17 -- first argument is splatted by the second."""
+    metric = torch.ones_like(flow_b[:, :1])
+    warped = softsplat(flow_a, flow_b, metric, "soft")
+    diff = flow_b + warped
+    return (torch.norm(diff, p=2, dim=1, keepdim=True) > 0.3).float()
+
+
+def feature_warper(feat, flow, metric=None, mask=None):
+    """controlnet/control_utils.py:49-72 with the metric supplied by the caller."""
+    if metric is None:
+        metric = torch.ones_like(flow[:, :1])
+    warped = softsplat(feat, flow, metric, "soft")
+    if mask is not None:
+        warped = warped * (1 - mask)
+    return warped, metric
+
+
+def resize_and_normalize_flow_batched(flow, target_h: int, target_w: int):
+    """controlnet/control_utils.py:74-97."""
+    resized = torch.nn.functional.interpolate(flow, size=(target_h, target_w), mode="bilinear", align_corners=False)
+    u = resized[:, 0] / ((target_w - 1) / 2.0)
+    v = resized[:, 1] / ((target_h - 1) / 2.0)
+    return torch.stack([u, v], dim=1)
+
+
+def fuse(warped_a, warped_b, conf_a, conf_b, occ_a=None, occ_b=None):
+    """Confidence fusion (+ double-hole fill), extractors.py:298-310 / residual_utils.py:181-193."""
+    conf = torch.clamp(torch.cat([conf_a, conf_b], dim=1), min=0)
+    w = conf / (conf.sum(dim=1, keepdim=True) + 1e-6)
+    fused = w[:, :1] * warped_a + w[:, 1:] * warped_b
+    if occ_a is not None:
+        holes = (occ_a + occ_b) > 1.5
+        if holes.any():
+            fused = torch.where(holes.expand_as(fused), 0.5 * (warped_a + warped_b), fused)
+    return fused
+
+
+def residual_recipe(image1, flow1, flow2, gt, variant: str):
+    """Conditioning builder.
+
+    variant "dataset": controlnet/dataset.py:233-265 (occlusion masks are the fusion weights,
+    no hole branch). variant "wrapper": controlnet/residual_utils.py:159-199 (ones metrics
+    are the weights, double-hole average fill). Both splat image1 by flow1 twice (Appendix
+    B-6 of SURVEY.md) -- restated as the reference computes it, not as it was intended.
+    Returns (fused, residual, occ_fwd, occ_bwd).
+    """
+    metric = torch.ones_like(flow1[:, :1])
+    warped1 = softsplat(image1, flow1, metric, "soft")
+    warped2 = softsplat(image1, flow1, metric, "soft")
+    occ_fwd = compute_mask(flow1, flow2)
+    occ_bwd = compute_mask(flow2, flow1)
+    if variant == "dataset":
+        fused = fuse(warped1, warped2, occ_fwd, occ_bwd)
+    elif variant == "wrapper":
+        fused = fuse(warped1, warped2, metric, metric, occ_fwd, occ_bwd)
+    else:
+        raise ValueError(variant)
+    return fused, gt - fused, occ_fwd, occ_bwd
+
+
+def backwarp(image, flow, align_corners=None):
+    """cmp/models/modules/warp.py:9-25 on CPU tensors (torch's own grid_sample)."""
+    fg = torch.zeros_like(flow)
+    fg[:, 0] = flow[:, 0] / ((flow.size(3) - 1.0) / 2.0)
+    fg[:, 1] = flow[:, 1] / ((flow.size(2) - 1.0) / 2.0)
+    n, _, h, w = image.shape
+    hor = torch.linspace(-1.0, 1.0, w, dtype=image.dtype).view(1, 1, 1, w).expand(n, 1, h, w)
+    ver = torch.linspace(-1.0, 1.0, h, dtype=image.dtype).view(1, 1, h, 1).expand(n, 1, h, w)
+    grid = (torch.cat([hor, ver], 1) + fg).permute(0, 2, 3, 1)
+    if align_corners is None:
+        return torch.nn.functional.grid_sample(image, grid)  # as executed: default False
+    return torch.nn.functional.grid_sample(image, grid, align_corners=bool(align_corners))

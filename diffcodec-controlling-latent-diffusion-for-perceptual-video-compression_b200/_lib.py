@@ -1,0 +1,154 @@
+"""ctypes binding of libdiffcodec_b200.so (the C ABI in include/diffcodec_b200.h).
+
+PyTorch is used here only for device memory, streams and autograd plumbing: every
+arithmetic operation of the hot path happens inside the shared library. There is
+no fallback: if the library is missing or a call fails, we raise.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import subprocess
+import threading
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libdiffcodec_b200.so")
+
+DCB_F32, DCB_BF16, DCB_F64 = 0, 1, 2
+MODE_SUM, MODE_AVG, MODE_LINEAR, MODE_SOFT = 0, 1, 2, 3
+EPS_ADD, EPS_ZERO, EPS_CLIP = 0, 1, 2
+FLAG_DETERMINISTIC, FLAG_WS_CLEAN = 1, 2
+RECIPE_DATASET, RECIPE_WRAPPER = 0, 1
+
+E_NULL, E_SHAPE, E_DTYPE, E_MODE, E_WORKSPACE, E_LIMIT, E_ALIGN = -1, -2, -3, -4, -5, -6, -7
+
+_DTYPES = {torch.float32: DCB_F32, torch.bfloat16: DCB_BF16, torch.float64: DCB_F64}
+
+
+class DcbTensor(ctypes.Structure):
+    _fields_ = [
+        ("ptr", ctypes.c_void_p),
+        ("dtype", ctypes.c_int32),
+        ("reserved", ctypes.c_int32),
+        ("size", ctypes.c_int64 * 4),
+        ("stride", ctypes.c_int64 * 4),
+    ]
+
+
+_P = ctypes.POINTER(DcbTensor)
+_lib = None
+_lock = threading.Lock()
+
+# name -> (restype, argtypes); exactly the symbols include/diffcodec_b200.h declares
+SYMBOLS = {
+    "dcb_version": (ctypes.c_int, []),
+    "dcb_last_error": (ctypes.c_char_p, []),
+    "dcb_build_info": (ctypes.c_char_p, []),
+    "dcb_launch_count": (ctypes.c_int64, []),
+    "dcb_splat_workspace_bytes": (ctypes.c_int64, [ctypes.c_int64] * 4 + [ctypes.c_int32] * 3),
+    "dcb_splat_fwd": (ctypes.c_int, [_P] * 6 + [ctypes.c_void_p, ctypes.c_int64] + [ctypes.c_int32] * 3 + [ctypes.c_void_p]),
+    "dcb_splat_bwd": (ctypes.c_int, [_P] * 10 + [ctypes.c_void_p, ctypes.c_int64] + [ctypes.c_int32] * 3 + [ctypes.c_void_p]),
+    "dcb_backwarp_fwd": (ctypes.c_int, [_P] * 5 + [ctypes.c_int32, ctypes.c_void_p]),
+    "dcb_backwarp_bwd_workspace_bytes": (ctypes.c_int64, [ctypes.c_int64] * 4 + [ctypes.c_int32]),
+    "dcb_backwarp_bwd": (ctypes.c_int, [_P] * 5 + [ctypes.c_int32, ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p]),
+    "dcb_occlusion_mask_workspace_bytes": (ctypes.c_int64, [ctypes.c_int64] * 3),
+    "dcb_occlusion_mask": (ctypes.c_int, [_P] * 3 + [ctypes.c_void_p, ctypes.c_int64, ctypes.c_int32, ctypes.c_void_p]),
+    "dcb_residual_workspace_bytes": (ctypes.c_int64, [ctypes.c_int64] * 4),
+    "dcb_residual_fused": (ctypes.c_int, [_P] * 8 + [ctypes.c_void_p, ctypes.c_int64, ctypes.c_int32, ctypes.c_int32, ctypes.c_void_p]),
+}
+
+
+def build(verbose: bool = False) -> str:
+    """Compile the library in-tree for sm_100a with the committed Makefile (nvcc cross-compiles without a GPU)."""
+    out = subprocess.run(["make", "-C", os.path.join(_HERE, "csrc"), "-j8"], capture_output=True, text=True)
+    if out.returncode != 0:
+        raise RuntimeError("building libdiffcodec_b200.so failed:\n" + out.stdout[-4000:] + out.stderr[-4000:])
+    if verbose:
+        print(out.stdout[-2000:])
+    return LIB_PATH
+
+
+def lib() -> ctypes.CDLL:
+    """Load the library (once). Raises if it is absent -- there is no other implementation."""
+    global _lib
+    if _lib is None:
+        with _lock:
+            if _lib is None:
+                if not os.path.exists(LIB_PATH):
+                    raise RuntimeError(
+                        f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                        "(or `make -C <package>/csrc`). diffcodec_b200 has no CPU or PyTorch fallback.")
+                handle = ctypes.CDLL(LIB_PATH)
+                for name, (res, args) in SYMBOLS.items():
+                    fn = getattr(handle, name)
+                    fn.restype, fn.argtypes = res, args
+                _lib = handle
+    return _lib
+
+
+class DcbError(RuntimeError):
+    pass
+
+
+def check(rc: int, what: str) -> None:
+    """Map ABI return codes to the exceptions the reference would raise."""
+    if rc == 0:
+        return
+    msg = lib().dcb_last_error().decode("utf-8", "replace")
+    if rc in (E_SHAPE, E_MODE, E_NULL):
+        raise AssertionError(f"{what}: {msg}")          # the reference uses assert for these
+    if rc in (E_DTYPE, E_LIMIT, E_ALIGN, E_WORKSPACE):
+        raise ValueError(f"{what}: {msg}")
+    raise DcbError(f"{what}: CUDA error {rc}: {msg}")
+
+
+def desc(t: torch.Tensor | None):
+    """DcbTensor* for a 4-d CUDA tensor (or NULL)."""
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise AssertionError("diffcodec_b200 runs on CUDA tensors only (the reference asserts the same, softsplat.py:347-348)")
+    if t.dim() != 4:
+        raise AssertionError(f"expected a 4-d NCHW tensor, got {tuple(t.shape)}")
+    if t.dtype not in _DTYPES:
+        raise ValueError(f"unsupported dtype {t.dtype}: float32, bfloat16 and float64 are implemented")
+    d = DcbTensor()
+    d.ptr = t.data_ptr()
+    d.dtype = _DTYPES[t.dtype]
+    d.size[:] = list(t.shape)
+    d.stride[:] = list(t.stride())
+    return ctypes.byref(d)
+
+
+def stream_ptr(device) -> int:
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+# -------------------------------------------------------------------------------------------------
+# per-(device, stream) workspace caches. Two kinds:
+#   "acc"     accumulators; kept all-zero BETWEEN calls (the epilogue kernels re-zero what they
+#             read), so DCB_FLAG_WS_CLEAN can be passed and no memset is launched;
+#   "scratch" anything else (backward scalars, deterministic-mode keys); contents arbitrary.
+# A workspace is only ever used on the stream it was created for.
+# -------------------------------------------------------------------------------------------------
+_workspaces: dict = {}
+
+
+def workspace(device: torch.device, nbytes: int, kind: str) -> torch.Tensor:
+    key = (kind, device.index, stream_ptr(device))
+    buf = _workspaces.get(key)
+    if buf is None or buf.numel() < nbytes:
+        buf = torch.zeros(max(int(nbytes), 1 << 20), dtype=torch.uint8, device=device)
+        _workspaces[key] = buf
+    return buf
+
+
+def invalidate_acc(device: torch.device) -> None:
+    """Forget the clean accumulator buffer (after a failed call it may hold partial sums)."""
+    _workspaces.pop(("acc", device.index, stream_ptr(device)), None)
+
+
+def release_workspaces() -> None:
+    _workspaces.clear()

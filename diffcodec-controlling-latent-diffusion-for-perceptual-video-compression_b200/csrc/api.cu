@@ -1,0 +1,324 @@
+// api.cu -- the C ABI of libdiffcodec_b200.so (include/diffcodec_b200.h): argument validation,
+// error reporting, launch accounting. No allocation, no synchronisation, no stream creation.
+#include "dcb_common.cuh"
+
+#include <string.h>
+
+namespace dcb {
+
+std::atomic<long long> g_launches{0};
+static thread_local char t_error[512] = "";
+
+int set_error(int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(t_error, sizeof(t_error), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+int device_sm_count() {
+    static int sms = 0;
+    if (sms == 0) {
+        int dev = 0, n = 0;
+        if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && n > 0)
+            sms = n;
+        else
+            sms = 148;
+    }
+    return sms;
+}
+
+// implemented in the kernel translation units
+long long splat_fwd_workspace(long long N, long long C, long long H, long long W, int dtype, int mode);
+long long splat_bwd_workspace(long long N, long long H, long long W, int dtype, int mode);
+long long det_workspace(long long N, long long C, long long H, long long W, int dtype, int mode);
+int splat_fwd_impl(const DcbTensor*, const DcbTensor*, const DcbTensor*, const DcbTensor*, const DcbTensor*,
+                   const DcbTensor*, void*, long long, int, int, int, cudaStream_t);
+int splat_fwd_det_impl(const DcbTensor*, const DcbTensor*, const DcbTensor*, const DcbTensor*, const DcbTensor*,
+                       const DcbTensor*, void*, long long, int, int, int, cudaStream_t);
+int splat_bwd_impl(const DcbTensor*, const DcbTensor*, const DcbTensor*, const DcbTensor*, const DcbTensor*,
+                   const DcbTensor*, const DcbTensor*, const DcbTensor*, const DcbTensor*, const DcbTensor*, void*,
+                   long long, int, int, cudaStream_t);
+int backwarp_fwd_impl(const DcbTensor*, const DcbTensor*, const DcbTensor*, const DcbTensor*, const DcbTensor*, int,
+                      cudaStream_t);
+long long backwarp_bwd_workspace(long long N, long long C, long long H, long long W, int dtype);
+int backwarp_bwd_impl(const DcbTensor*, const DcbTensor*, const DcbTensor*, const DcbTensor*, const DcbTensor*, int,
+                      void*, long long, cudaStream_t);
+long long mask_workspace(long long N, long long H, long long W);
+long long recipe_workspace(long long N, long long H, long long W);
+int occlusion_mask_impl(const DcbTensor*, const DcbTensor*, const DcbTensor*, void*, long long, int, cudaStream_t);
+int residual_fused_impl(const DcbTensor*, const DcbTensor*, const DcbTensor*, const DcbTensor*, const DcbTensor*,
+                        const DcbTensor*, const DcbTensor*, const DcbTensor*, void*, long long, int, int, cudaStream_t);
+
+// ---------------------------------------------------------------------------------------------
+// validation helpers
+// ---------------------------------------------------------------------------------------------
+static int check_tensor(const char* fn, const char* name, const DcbTensor* t, bool required) {
+    if (!t) return required ? set_error(DCB_E_NULL, "%s: %s is required", fn, name) : DCB_OK;
+    if (t->dtype != DCB_F32 && t->dtype != DCB_BF16 && t->dtype != DCB_F64)
+        return set_error(DCB_E_DTYPE, "%s: %s has unsupported dtype %d", fn, name, t->dtype);
+    long long numel = 1;
+    for (int d = 0; d < 4; ++d) {
+        if (t->size[d] < 0) return set_error(DCB_E_SHAPE, "%s: %s has a negative size", fn, name);
+        numel *= t->size[d];
+    }
+    if (numel > 0 && !t->ptr) return set_error(DCB_E_NULL, "%s: %s has a null data pointer", fn, name);
+    if ((uintptr_t)t->ptr % (uintptr_t)elem_size(t->dtype))
+        return set_error(DCB_E_ALIGN, "%s: %s is not aligned to its element size", fn, name);
+    return DCB_OK;
+}
+
+static int check_shape(const char* fn, const char* name, const DcbTensor* t, long long N, long long C, long long H,
+                       long long W) {
+    if (!t) return DCB_OK;
+    if (t->size[0] != N || t->size[1] != C || t->size[2] != H || t->size[3] != W)
+        return set_error(DCB_E_SHAPE, "%s: %s is [%lld,%lld,%lld,%lld], expected [%lld,%lld,%lld,%lld]", fn, name,
+                         (long long)t->size[0], (long long)t->size[1], (long long)t->size[2], (long long)t->size[3], N,
+                         C, H, W);
+    return DCB_OK;
+}
+
+static int check_out(const char* fn, const char* name, const DcbTensor* t, int dtype, int align) {
+    if (!t) return DCB_OK;
+    if (t->dtype != dtype) return set_error(DCB_E_DTYPE, "%s: %s has dtype %d, expected %d", fn, name, t->dtype, dtype);
+    if (!is_contig(t)) return set_error(DCB_E_SHAPE, "%s: %s must be NCHW-contiguous", fn, name);
+    if ((uintptr_t)t->ptr % (uintptr_t)align) return set_error(DCB_E_ALIGN, "%s: %s must be %d-byte aligned", fn, name, align);
+    return DCB_OK;
+}
+
+static int check_limits(const char* fn, const DcbTensor* t) {
+    const long long N = t->size[0], C = t->size[1], H = t->size[2], W = t->size[3];
+    if (H * W >= (1ll << 31) || N * H * W >= (1ll << 31) || C >= (1ll << 24) || H >= (1 << 24) || W >= (1 << 24))
+        return set_error(DCB_E_LIMIT, "%s: sizes [%lld,%lld,%lld,%lld] exceed kernel index limits (N*H*W < 2^31)", fn, N, C, H, W);
+    return DCB_OK;
+}
+
+static int flow_dtype_ok(const char* fn, const DcbTensor* in, const DcbTensor* flow) {
+    if (flow->dtype == in->dtype) return DCB_OK;
+    if (in->dtype == DCB_BF16 && flow->dtype == DCB_F32) return DCB_OK;
+    return set_error(DCB_E_DTYPE, "%s: flow dtype %d does not go with tensor dtype %d", fn, flow->dtype, in->dtype);
+}
+
+#define TRY(expr)                  \
+    do {                           \
+        int rc__ = (expr);         \
+        if (rc__ != DCB_OK) return rc__; \
+    } while (0)
+
+static int acc_dtype(int dtype) { return dtype == DCB_F64 ? DCB_F64 : DCB_F32; }
+
+}  // namespace dcb
+
+using namespace dcb;
+
+extern "C" {
+
+int dcb_version(void) { return DCB_VERSION; }
+const char* dcb_last_error(void) { return t_error; }
+int64_t dcb_launch_count(void) { return (int64_t)g_launches.load(); }
+
+const char* dcb_build_info(void) {
+    return "libdiffcodec_b200 " __DATE__ " nvcc " DCB_STR(__CUDACC_VER_MAJOR__) "." DCB_STR(__CUDACC_VER_MINOR__)
+           " target sm_100a; kernels: k_scatter_planar k_scatter_vec4 k_normalize k_bwd_target k_bwd_source "
+           "k_backwarp_fwd k_backwarp_bwd k_mask_scatter k_mask_epilogue k_recipe_scatter k_recipe_epilogue "
+           "k_det_count k_det_scan k_det_fill k_det_reduce";
+}
+
+int64_t dcb_splat_workspace_bytes(int64_t N, int64_t C, int64_t H, int64_t W, int32_t dtype, int32_t mode, int32_t flags) {
+    if (N < 0 || C < 0 || H < 0 || W < 0) return 0;
+    long long f = splat_fwd_workspace(N, C, H, W, dtype, mode);
+    long long b = splat_bwd_workspace(N, H, W, dtype, mode);
+    long long need = f > b ? f : b;
+    if (flags & DCB_FLAG_DETERMINISTIC) {
+        long long d = det_workspace(N, C, H, W, dtype, mode);
+        if (d > need) need = d;
+    }
+    return (int64_t)need;
+}
+
+int dcb_splat_fwd(const DcbTensor* in, const DcbTensor* flow, const DcbTensor* metric, const DcbTensor* out,
+                  const DcbTensor* norm, const DcbTensor* mask, void* ws, int64_t ws_bytes, int32_t mode, int32_t eps,
+                  int32_t flags, void* stream) {
+    const char* fn = "dcb_splat_fwd";
+    TRY(check_tensor(fn, "in", in, true));
+    TRY(check_tensor(fn, "flow", flow, true));
+    TRY(check_tensor(fn, "metric", metric, false));
+    TRY(check_tensor(fn, "out", out, true));
+    TRY(check_tensor(fn, "norm", norm, false));
+    TRY(check_tensor(fn, "mask", mask, false));
+    if (mode < DCB_MODE_SUM || mode > DCB_MODE_SOFT) return set_error(DCB_E_MODE, "%s: unknown mode %d", fn, mode);
+    if (eps < DCB_EPS_ADD || eps > DCB_EPS_CLIP) return set_error(DCB_E_MODE, "%s: unknown eps rule %d", fn, eps);
+    if (flags & ~(DCB_FLAG_DETERMINISTIC | DCB_FLAG_WS_CLEAN)) return set_error(DCB_E_MODE, "%s: unknown flags 0x%x", fn, flags);
+    // softsplat.py:235-238
+    if ((mode == DCB_MODE_SUM || mode == DCB_MODE_AVG) && metric) return set_error(DCB_E_MODE, "%s: metric must be NULL for sum/avg", fn);
+    if ((mode == DCB_MODE_LINEAR || mode == DCB_MODE_SOFT) && !metric) return set_error(DCB_E_MODE, "%s: metric is required for linear/soft", fn);
+    if (mode == DCB_MODE_SUM && (mask || norm)) return set_error(DCB_E_MODE, "%s: mask/norm need a normalised mode", fn);
+    const long long N = in->size[0], C = in->size[1], H = in->size[2], W = in->size[3];
+    TRY(check_limits(fn, in));
+    TRY(check_shape(fn, "flow", flow, N, 2, H, W));       // softsplat.py:296
+    TRY(check_shape(fn, "metric", metric, N, 1, H, W));
+    TRY(check_shape(fn, "out", out, N, C, H, W));
+    TRY(check_shape(fn, "norm", norm, N, 1, H, W));
+    TRY(check_shape(fn, "mask", mask, N, 1, H, W));
+    TRY(flow_dtype_ok(fn, in, flow));
+    if (metric && metric->dtype != in->dtype) return set_error(DCB_E_DTYPE, "%s: metric dtype differs from in", fn);
+    if (mask && mask->dtype != in->dtype) return set_error(DCB_E_DTYPE, "%s: mask dtype differs from in", fn);
+    TRY(check_out(fn, "out", out, in->dtype, elem_size(in->dtype)));
+    TRY(check_out(fn, "norm", norm, acc_dtype(in->dtype), elem_size(acc_dtype(in->dtype))));
+    if (flags & DCB_FLAG_DETERMINISTIC)
+        return splat_fwd_det_impl(in, flow, metric, out, norm, mask, ws, ws_bytes, mode, eps, flags, (cudaStream_t)stream);
+    return splat_fwd_impl(in, flow, metric, out, norm, mask, ws, ws_bytes, mode, eps, flags, (cudaStream_t)stream);
+}
+
+int dcb_splat_bwd(const DcbTensor* gout, const DcbTensor* in, const DcbTensor* flow, const DcbTensor* metric,
+                  const DcbTensor* out, const DcbTensor* norm, const DcbTensor* mask, const DcbTensor* gin,
+                  const DcbTensor* gflow, const DcbTensor* gmetric, void* ws, int64_t ws_bytes, int32_t mode,
+                  int32_t eps, int32_t flags, void* stream) {
+    const char* fn = "dcb_splat_bwd";
+    (void)flags;
+    TRY(check_tensor(fn, "grad_out", gout, true));
+    TRY(check_tensor(fn, "in", in, true));
+    TRY(check_tensor(fn, "flow", flow, true));
+    TRY(check_tensor(fn, "metric", metric, false));
+    TRY(check_tensor(fn, "out", out, false));
+    TRY(check_tensor(fn, "norm", norm, false));
+    TRY(check_tensor(fn, "mask", mask, false));
+    TRY(check_tensor(fn, "grad_in", gin, false));
+    TRY(check_tensor(fn, "grad_flow", gflow, false));
+    TRY(check_tensor(fn, "grad_metric", gmetric, false));
+    if (mode < DCB_MODE_SUM || mode > DCB_MODE_SOFT) return set_error(DCB_E_MODE, "%s: unknown mode %d", fn, mode);
+    if (eps < DCB_EPS_ADD || eps > DCB_EPS_CLIP) return set_error(DCB_E_MODE, "%s: unknown eps rule %d", fn, eps);
+    if ((mode == DCB_MODE_LINEAR || mode == DCB_MODE_SOFT) && !metric) return set_error(DCB_E_MODE, "%s: metric is required for linear/soft", fn);
+    if ((mode == DCB_MODE_SUM || mode == DCB_MODE_AVG) && (metric || gmetric)) return set_error(DCB_E_MODE, "%s: no metric in sum/avg", fn);
+    if (mode != DCB_MODE_SUM && (!out || !norm)) return set_error(DCB_E_NULL, "%s: out and norm of the forward are required", fn);
+    if (mode == DCB_MODE_SUM && mask) return set_error(DCB_E_MODE, "%s: mask needs a normalised mode", fn);
+    const long long N = in->size[0], C = in->size[1], H = in->size[2], W = in->size[3];
+    TRY(check_limits(fn, in));
+    TRY(check_shape(fn, "grad_out", gout, N, C, H, W));
+    TRY(check_shape(fn, "flow", flow, N, 2, H, W));
+    TRY(check_shape(fn, "metric", metric, N, 1, H, W));
+    TRY(check_shape(fn, "out", out, N, C, H, W));
+    TRY(check_shape(fn, "norm", norm, N, 1, H, W));
+    TRY(check_shape(fn, "mask", mask, N, 1, H, W));
+    TRY(check_shape(fn, "grad_in", gin, N, C, H, W));
+    TRY(check_shape(fn, "grad_flow", gflow, N, 2, H, W));
+    TRY(check_shape(fn, "grad_metric", gmetric, N, 1, H, W));
+    TRY(flow_dtype_ok(fn, in, flow));
+    if (gout->dtype != in->dtype) return set_error(DCB_E_DTYPE, "%s: grad_out dtype differs from in", fn);
+    if (metric && metric->dtype != in->dtype) return set_error(DCB_E_DTYPE, "%s: metric dtype differs from in", fn);
+    if (mask && mask->dtype != in->dtype) return set_error(DCB_E_DTYPE, "%s: mask dtype differs from in", fn);
+    TRY(check_out(fn, "out", out, in->dtype, elem_size(in->dtype)));
+    TRY(check_out(fn, "norm", norm, acc_dtype(in->dtype), elem_size(acc_dtype(in->dtype))));
+    TRY(check_out(fn, "grad_in", gin, in->dtype, elem_size(in->dtype)));
+    TRY(check_out(fn, "grad_flow", gflow, flow->dtype, elem_size(flow->dtype)));
+    TRY(check_out(fn, "grad_metric", gmetric, in->dtype, elem_size(in->dtype)));
+    return splat_bwd_impl(gout, in, flow, metric, out, norm, mask, gin, gflow, gmetric, ws, ws_bytes, mode, eps,
+                          (cudaStream_t)stream);
+}
+
+int dcb_backwarp_fwd(const DcbTensor* image, const DcbTensor* flow, const DcbTensor* gt, const DcbTensor* warped,
+                     const DcbTensor* residual, int32_t align_corners, void* stream) {
+    const char* fn = "dcb_backwarp_fwd";
+    TRY(check_tensor(fn, "image", image, true));
+    TRY(check_tensor(fn, "flow", flow, true));
+    TRY(check_tensor(fn, "gt", gt, false));
+    TRY(check_tensor(fn, "warped", warped, true));
+    TRY(check_tensor(fn, "residual", residual, false));
+    if ((gt == nullptr) != (residual == nullptr)) return set_error(DCB_E_NULL, "%s: gt and residual go together", fn);
+    const long long N = image->size[0], C = image->size[1], H = image->size[2], W = image->size[3];
+    TRY(check_limits(fn, image));
+    TRY(check_shape(fn, "flow", flow, N, 2, H, W));
+    TRY(check_shape(fn, "gt", gt, N, C, H, W));
+    TRY(check_shape(fn, "warped", warped, N, C, H, W));
+    TRY(check_shape(fn, "residual", residual, N, C, H, W));
+    TRY(flow_dtype_ok(fn, image, flow));
+    if (gt && gt->dtype != image->dtype) return set_error(DCB_E_DTYPE, "%s: gt dtype differs from image", fn);
+    TRY(check_out(fn, "warped", warped, image->dtype, elem_size(image->dtype)));
+    TRY(check_out(fn, "residual", residual, image->dtype, elem_size(image->dtype)));
+    return backwarp_fwd_impl(image, flow, gt, warped, residual, align_corners ? 1 : 0, (cudaStream_t)stream);
+}
+
+int64_t dcb_backwarp_bwd_workspace_bytes(int64_t N, int64_t C, int64_t H, int64_t W, int32_t dtype) {
+    return (int64_t)backwarp_bwd_workspace(N, C, H, W, dtype);
+}
+
+int dcb_backwarp_bwd(const DcbTensor* gout, const DcbTensor* image, const DcbTensor* flow, const DcbTensor* gimage,
+                     const DcbTensor* gflow, int32_t align_corners, void* ws, int64_t ws_bytes, void* stream) {
+    const char* fn = "dcb_backwarp_bwd";
+    TRY(check_tensor(fn, "grad_warped", gout, true));
+    TRY(check_tensor(fn, "image", image, true));
+    TRY(check_tensor(fn, "flow", flow, true));
+    TRY(check_tensor(fn, "grad_image", gimage, false));
+    TRY(check_tensor(fn, "grad_flow", gflow, false));
+    const long long N = image->size[0], C = image->size[1], H = image->size[2], W = image->size[3];
+    TRY(check_limits(fn, image));
+    TRY(check_shape(fn, "grad_warped", gout, N, C, H, W));
+    TRY(check_shape(fn, "flow", flow, N, 2, H, W));
+    TRY(check_shape(fn, "grad_image", gimage, N, C, H, W));
+    TRY(check_shape(fn, "grad_flow", gflow, N, 2, H, W));
+    TRY(flow_dtype_ok(fn, image, flow));
+    if (gout->dtype != image->dtype) return set_error(DCB_E_DTYPE, "%s: grad_warped dtype differs from image", fn);
+    TRY(check_out(fn, "grad_image", gimage, image->dtype, elem_size(image->dtype)));
+    TRY(check_out(fn, "grad_flow", gflow, flow->dtype, elem_size(flow->dtype)));
+    return backwarp_bwd_impl(gout, image, flow, gimage, gflow, align_corners ? 1 : 0, ws, ws_bytes, (cudaStream_t)stream);
+}
+
+int64_t dcb_occlusion_mask_workspace_bytes(int64_t N, int64_t H, int64_t W) { return (int64_t)mask_workspace(N, H, W); }
+
+int dcb_occlusion_mask(const DcbTensor* flow_a, const DcbTensor* flow_b, const DcbTensor* mask, void* ws, int64_t ws_bytes,
+                       int32_t flags, void* stream) {
+    const char* fn = "dcb_occlusion_mask";
+    TRY(check_tensor(fn, "flow_a", flow_a, true));
+    TRY(check_tensor(fn, "flow_b", flow_b, true));
+    TRY(check_tensor(fn, "mask", mask, true));
+    const long long N = flow_a->size[0], H = flow_a->size[2], W = flow_a->size[3];
+    TRY(check_limits(fn, flow_a));
+    TRY(check_shape(fn, "flow_a", flow_a, N, 2, H, W));
+    TRY(check_shape(fn, "flow_b", flow_b, N, 2, H, W));
+    TRY(check_shape(fn, "mask", mask, N, 1, H, W));
+    if (flow_b->dtype != flow_a->dtype) return set_error(DCB_E_DTYPE, "%s: flow dtypes differ", fn);
+    TRY(check_out(fn, "mask", mask, flow_a->dtype, elem_size(flow_a->dtype)));
+    return occlusion_mask_impl(flow_a, flow_b, mask, ws, ws_bytes, flags, (cudaStream_t)stream);
+}
+
+int64_t dcb_residual_workspace_bytes(int64_t N, int64_t C, int64_t H, int64_t W) {
+    (void)C;
+    return (int64_t)recipe_workspace(N, H, W);
+}
+
+int dcb_residual_fused(const DcbTensor* image1, const DcbTensor* flow1, const DcbTensor* flow2, const DcbTensor* gt,
+                       const DcbTensor* fused, const DcbTensor* residual, const DcbTensor* occ_fwd,
+                       const DcbTensor* occ_bwd, void* ws, int64_t ws_bytes, int32_t variant, int32_t flags,
+                       void* stream) {
+    const char* fn = "dcb_residual_fused";
+    TRY(check_tensor(fn, "image1", image1, true));
+    TRY(check_tensor(fn, "flow1", flow1, true));
+    TRY(check_tensor(fn, "flow2", flow2, true));
+    TRY(check_tensor(fn, "gt", gt, true));
+    TRY(check_tensor(fn, "fused", fused, true));
+    TRY(check_tensor(fn, "residual", residual, true));
+    TRY(check_tensor(fn, "occ_fwd", occ_fwd, false));
+    TRY(check_tensor(fn, "occ_bwd", occ_bwd, false));
+    if (variant != DCB_RECIPE_DATASET && variant != DCB_RECIPE_WRAPPER) return set_error(DCB_E_MODE, "%s: unknown variant %d", fn, variant);
+    const long long N = image1->size[0], C = image1->size[1], H = image1->size[2], W = image1->size[3];
+    TRY(check_limits(fn, image1));
+    if (C < 1 || C > 3) return set_error(DCB_E_LIMIT, "%s: fused recipe handles 1..3 image channels, got %lld", fn, C);
+    TRY(check_shape(fn, "flow1", flow1, N, 2, H, W));
+    TRY(check_shape(fn, "flow2", flow2, N, 2, H, W));
+    TRY(check_shape(fn, "gt", gt, N, C, H, W));
+    TRY(check_shape(fn, "fused", fused, N, C, H, W));
+    TRY(check_shape(fn, "residual", residual, N, C, H, W));
+    TRY(check_shape(fn, "occ_fwd", occ_fwd, N, 1, H, W));
+    TRY(check_shape(fn, "occ_bwd", occ_bwd, N, 1, H, W));
+    const int dt = image1->dtype;
+    if (flow1->dtype != dt || flow2->dtype != dt || gt->dtype != dt) return set_error(DCB_E_DTYPE, "%s: all tensors must share one dtype", fn);
+    TRY(check_out(fn, "fused", fused, dt, elem_size(dt)));
+    TRY(check_out(fn, "residual", residual, dt, elem_size(dt)));
+    TRY(check_out(fn, "occ_fwd", occ_fwd, dt, elem_size(dt)));
+    TRY(check_out(fn, "occ_bwd", occ_bwd, dt, elem_size(dt)));
+    return residual_fused_impl(image1, flow1, flow2, gt, fused, residual, occ_fwd, occ_bwd, ws, ws_bytes, variant, flags,
+                               (cudaStream_t)stream);
+}
+
+}  // extern "C"

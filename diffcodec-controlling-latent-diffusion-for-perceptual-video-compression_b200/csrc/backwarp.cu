@@ -1,0 +1,225 @@
+// backwarp.cu -- bilinear backward warp (+ fused residual) and its backward (K4 / K4b), sm_100a.
+//
+// Replaces WarpingLayerBWFlow.forward, cmp/models/modules/warp.py:9-25: the reference allocates
+// zeros_like(flow), two linspace grids, a cat, an H2D copy, an add and a permute (five extra
+// full-tensor passes) and then calls torch's grid_sample. Here the normalised grid value is
+// formed in registers with the same fp32 operation sequence, so no grid tensor exists:
+//     t    = flow_x / ((W-1)/2)                                     warp.py:11
+//     lin  = linspace(-1, 1, W)[x]   (torch: fma(step, i, -1) below W/2, fma(-step, W-1-i, 1) above)
+//     g    = lin + t                                                warp.py:24
+//     sx   = ((g + 1) * W - 1) / 2          align_corners = 0   (grid_sample default, as executed)
+//     sx   = ((g + 1) / 2) * (W - 1)        align_corners = 1
+// followed by grid_sample's bilinear footprint with zeros padding. The optional residual
+// (gt - warped, controlnet/residual_utils.py:199) is fused into the same pass.
+#include "dcb_common.cuh"
+
+namespace dcb {
+
+struct WarpArgs {
+    View image, flow, gt, gout;
+    void* warped;        // [N,C,H,W] contiguous
+    void* residual;      // [N,C,H,W] contiguous or null
+    void* gimage;        // [N,C,H,W] contiguous (zeroed before the launch) or null
+    void* gflow;         // [N,2,H,W] contiguous or null
+    unsigned total, HW;
+    int N, C, H, W;
+    int align;
+};
+
+template <class A> struct Tap {
+    int x0, y0;
+    A wnw, wne, wsw, wse;
+    A ex, ey, dx, dy;    // (x1 - sx), (y1 - sy), (sx - x0), (sy - y0)
+    bool b[4];
+};
+
+template <class A> __device__ __forceinline__ A linspace_pm1(int i, int n) {
+    if (n == 1) return (A)-1;
+    const A step = (A)2 / (A)(n - 1);
+    return i < n / 2 ? fma_rn(step, (A)i, (A)-1) : fma_rn(-step, (A)(n - 1 - i), (A)1);
+}
+
+template <class A> __device__ __forceinline__ A unnormalize(A g, int size, int align) {
+    if (align) return ((g + (A)1) / (A)2) * (A)(size - 1);
+    return fma_rn(g + (A)1, (A)size, (A)-1) / (A)2;
+}
+
+template <class A>
+__device__ __forceinline__ Tap<A> make_tap(int x, int y, A flow_x, A flow_y, int W, int H, int align) {
+    Tap<A> t;
+    const A gx = linspace_pm1<A>(x, W) + flow_x / (A)((W - 1.0) / 2.0);
+    const A gy = linspace_pm1<A>(y, H) + flow_y / (A)((H - 1.0) / 2.0);
+    const A sx = unnormalize<A>(gx, W, align), sy = unnormalize<A>(gy, H, align);
+    const A x0f = floor_t(sx), y0f = floor_t(sy);
+    t.x0 = to_int_sat(x0f);
+    t.y0 = to_int_sat(y0f);
+    t.ex = (x0f + (A)1) - sx; t.ey = (y0f + (A)1) - sy;
+    t.dx = sx - x0f; t.dy = sy - y0f;
+    t.wnw = mul_rn(t.ex, t.ey); t.wne = mul_rn(t.dx, t.ey);
+    t.wsw = mul_rn(t.ex, t.dy); t.wse = mul_rn(t.dx, t.dy);
+    const bool fin = finite_t(sx) && finite_t(sy);
+    const int x1 = (int)((unsigned)t.x0 + 1u), y1 = (int)((unsigned)t.y0 + 1u);
+    const bool vx0 = fin && (unsigned)t.x0 < (unsigned)W, vx1 = fin && (unsigned)x1 < (unsigned)W;
+    const bool vy0 = (unsigned)t.y0 < (unsigned)H, vy1 = (unsigned)y1 < (unsigned)H;
+    t.b[0] = vx0 && vy0; t.b[1] = vx1 && vy0; t.b[2] = vx0 && vy1; t.b[3] = vx1 && vy1;
+    return t;
+}
+
+// K4: one thread per OUTPUT pixel, loop over channels (gather, coalesced for smooth flow).
+template <class T, class TF>
+__global__ void __launch_bounds__(256) k_backwarp_fwd(const WarpArgs a) {
+    using A = typename Acc<T>::type;
+    const unsigned p = blockIdx.x * 256 + threadIdx.x;
+    if (p >= a.total) return;
+    const unsigned n = p / a.HW, r = p - n * a.HW;
+    const int y = (int)(r / (unsigned)a.W), x = (int)(r - (unsigned)y * (unsigned)a.W);
+    const TF* fp = (const TF*)a.flow.p + n * a.flow.sN + y * a.flow.sH + x * a.flow.sW;
+    const Tap<A> t = make_tap<A>(x, y, ld<A>(fp), ld<A>(fp + a.flow.sC), a.W, a.H, a.align);
+
+    const T* im = (const T*)a.image.p + n * a.image.sN + (long long)t.y0 * a.image.sH + (long long)t.x0 * a.image.sW;
+    const long long o1 = a.image.sW, o2 = a.image.sH, o3 = a.image.sH + a.image.sW;
+    const T* gt = a.gt.p ? (const T*)a.gt.p + n * a.gt.sN + y * a.gt.sH + x * a.gt.sW : nullptr;
+    T* wp = (T*)a.warped + (long long)n * a.C * a.HW + r;
+    T* rp = a.residual ? (T*)a.residual + (long long)n * a.C * a.HW + r : nullptr;
+    for (int c = 0; c < a.C; ++c, im += a.image.sC) {
+        A acc = (A)0;
+        if (t.b[0]) acc = fma_rn(ld<A>(im), t.wnw, acc);
+        if (t.b[1]) acc = fma_rn(ld<A>(im + o1), t.wne, acc);
+        if (t.b[2]) acc = fma_rn(ld<A>(im + o2), t.wsw, acc);
+        if (t.b[3]) acc = fma_rn(ld<A>(im + o3), t.wse, acc);
+        st<T, A>(wp + (long long)c * a.HW, acc);
+        if (rp) {
+            // residual of the value as stored (rounded to T), like `gt - warped` on the stored tensor
+            const A stored = ld<A>(wp + (long long)c * a.HW);
+            st<T, A>(rp + (long long)c * a.HW, sub_rn(ld<A>(gt + c * a.gt.sC), stored));
+        }
+    }
+}
+
+// K4b: gradImage by scatter (reds into the zeroed planar buffer), gradFlow by gather.
+template <class T, class TF>
+__global__ void __launch_bounds__(256) k_backwarp_bwd(const WarpArgs a, typename Acc<T>::type* gimage_acc) {
+    using A = typename Acc<T>::type;
+    const unsigned p = blockIdx.x * 256 + threadIdx.x;
+    if (p >= a.total) return;
+    const unsigned n = p / a.HW, r = p - n * a.HW;
+    const int y = (int)(r / (unsigned)a.W), x = (int)(r - (unsigned)y * (unsigned)a.W);
+    const TF* fp = (const TF*)a.flow.p + n * a.flow.sN + y * a.flow.sH + x * a.flow.sW;
+    const Tap<A> t = make_tap<A>(x, y, ld<A>(fp), ld<A>(fp + a.flow.sC), a.W, a.H, a.align);
+
+    const T* im = (const T*)a.image.p + n * a.image.sN + (long long)t.y0 * a.image.sH + (long long)t.x0 * a.image.sW;
+    const long long o1 = a.image.sW, o2 = a.image.sH, o3 = a.image.sH + a.image.sW;
+    const T* gp = (const T*)a.gout.p + n * a.gout.sN + y * a.gout.sH + x * a.gout.sW;
+    A* gi = gimage_acc ? gimage_acc + (long long)n * a.C * a.HW + (long long)t.y0 * a.W + t.x0 : nullptr;
+    A gx = (A)0, gy = (A)0;
+    for (int c = 0; c < a.C; ++c, im += a.image.sC) {
+        const A g = ld<A>(gp + c * a.gout.sC);
+        if (gi) {
+            A* q = gi + (long long)c * a.HW;
+            if (t.b[0]) red_add(q, mul_rn(g, t.wnw));
+            if (t.b[1]) red_add(q + 1, mul_rn(g, t.wne));
+            if (t.b[2]) red_add(q + a.W, mul_rn(g, t.wsw));
+            if (t.b[3]) red_add(q + a.W + 1, mul_rn(g, t.wse));
+        }
+        if (a.gflow) {
+            const A vnw = t.b[0] ? ld<A>(im) : (A)0, vne = t.b[1] ? ld<A>(im + o1) : (A)0;
+            const A vsw = t.b[2] ? ld<A>(im + o2) : (A)0, vse = t.b[3] ? ld<A>(im + o3) : (A)0;
+            gx += g * ((vne - vnw) * t.ey + (vse - vsw) * t.dy);
+            gy += g * ((vsw - vnw) * t.ex + (vse - vne) * t.dx);
+        }
+    }
+    if (a.gflow) {
+        // chain through the un-normalisation (W/2 or (W-1)/2) and warp.py:11-12 (1 / ((W-1)/2))
+        const A kx = a.align ? (A)1 : (A)a.W / (A)(a.W - 1);
+        const A ky = a.align ? (A)1 : (A)a.H / (A)(a.H - 1);
+        TF* gf = (TF*)a.gflow + (long long)n * 2 * a.HW + r;
+        st<TF, A>(gf, gx * kx);
+        st<TF, A>(gf + a.HW, gy * ky);
+    }
+}
+
+// cast an accumulator-typed planar buffer to T (only needed for bf16 gradImage)
+__global__ void __launch_bounds__(256) k_cast_f32_bf16(const float* src, __nv_bfloat16* dst, long long n) {
+    const long long i = (long long)blockIdx.x * 256 + threadIdx.x;
+    if (i < n) dst[i] = __float2bfloat16_rn(src[i]);
+}
+
+static void fill(WarpArgs& a, const DcbTensor* image) {
+    a.N = (int)image->size[0]; a.C = (int)image->size[1]; a.H = (int)image->size[2]; a.W = (int)image->size[3];
+    a.HW = (unsigned)(image->size[2] * image->size[3]);
+    a.total = (unsigned)(image->size[0] * image->size[2] * image->size[3]);
+}
+
+template <class T, class TF> static int launch_warp_fwd(const WarpArgs& a, cudaStream_t st) {
+    k_backwarp_fwd<T, TF><<<(a.total + 255) / 256, 256, 0, st>>>(a);
+    DCB_CHECK_LAUNCH("k_backwarp_fwd");
+    return DCB_OK;
+}
+
+int backwarp_fwd_impl(const DcbTensor* image, const DcbTensor* flow, const DcbTensor* gt, const DcbTensor* warped,
+                      const DcbTensor* residual, int align, cudaStream_t st) {
+    WarpArgs a{};
+    a.image = make_view(image); a.flow = make_view(flow); a.gt = make_view(gt);
+    a.warped = warped->ptr; a.residual = residual ? residual->ptr : nullptr;
+    a.align = align;
+    fill(a, image);
+    if (a.total == 0 || a.C == 0) return DCB_OK;
+    const bool ff = flow->dtype == DCB_F32;
+    switch (image->dtype) {
+        case DCB_F32: return launch_warp_fwd<float, float>(a, st);
+        case DCB_F64: return launch_warp_fwd<double, double>(a, st);
+        case DCB_BF16: return ff ? launch_warp_fwd<__nv_bfloat16, float>(a, st) : launch_warp_fwd<__nv_bfloat16, __nv_bfloat16>(a, st);
+    }
+    return set_error(DCB_E_DTYPE, "backwarp_fwd: unsupported dtype %d", image->dtype);
+}
+
+template <class T, class TF> static int launch_warp_bwd(const WarpArgs& a, void* acc, cudaStream_t st) {
+    using A = typename Acc<T>::type;
+    k_backwarp_bwd<T, TF><<<(a.total + 255) / 256, 256, 0, st>>>(a, (A*)acc);
+    DCB_CHECK_LAUNCH("k_backwarp_bwd");
+    return DCB_OK;
+}
+
+long long backwarp_bwd_workspace(long long N, long long C, long long H, long long W, int dtype) {
+    return dtype == DCB_BF16 ? align_up(N * C * H * W * 4, 256) : 0;
+}
+
+int backwarp_bwd_impl(const DcbTensor* gout, const DcbTensor* image, const DcbTensor* flow, const DcbTensor* gimage,
+                      const DcbTensor* gflow, int align, void* ws, long long ws_bytes, cudaStream_t st) {
+    WarpArgs a{};
+    a.image = make_view(image); a.flow = make_view(flow); a.gout = make_view(gout);
+    a.gimage = gimage ? gimage->ptr : nullptr;
+    a.gflow = gflow ? gflow->ptr : nullptr;
+    a.align = align;
+    fill(a, image);
+    if (a.total == 0 || a.C == 0 || (!a.gimage && !a.gflow)) return DCB_OK;
+    const long long nelem = (long long)a.total * a.C;
+    void* acc = a.gimage;
+    if (a.gimage) {
+        if (image->dtype == DCB_BF16) {
+            const long long need = backwarp_bwd_workspace(a.N, a.C, a.H, a.W, DCB_BF16);
+            if (!ws || ws_bytes < need || ((uintptr_t)ws & 255))
+                return set_error(DCB_E_WORKSPACE, "backwarp_bwd: workspace of %lld bytes required, got %lld", need, ws_bytes);
+            acc = ws;
+        }
+        DCB_CHECK_CUDA(cudaMemsetAsync(acc, 0, (size_t)nelem * (image->dtype == DCB_F64 ? 8 : 4), st));
+    }
+    const bool ff = flow->dtype == DCB_F32;
+    int rc;
+    switch (image->dtype) {
+        case DCB_F32: rc = launch_warp_bwd<float, float>(a, acc, st); break;
+        case DCB_F64: rc = launch_warp_bwd<double, double>(a, acc, st); break;
+        case DCB_BF16:
+            rc = ff ? launch_warp_bwd<__nv_bfloat16, float>(a, acc, st) : launch_warp_bwd<__nv_bfloat16, __nv_bfloat16>(a, acc, st);
+            break;
+        default: return set_error(DCB_E_DTYPE, "backwarp_bwd: unsupported dtype %d", image->dtype);
+    }
+    if (rc != DCB_OK) return rc;
+    if (a.gimage && image->dtype == DCB_BF16) {
+        k_cast_f32_bf16<<<(unsigned)((nelem + 255) / 256), 256, 0, st>>>((const float*)acc, (__nv_bfloat16*)a.gimage, nelem);
+        DCB_CHECK_LAUNCH("k_cast_f32_bf16");
+    }
+    return DCB_OK;
+}
+
+}  // namespace dcb

@@ -1,0 +1,144 @@
+// dcb_common.cuh -- shared device/host helpers for libdiffcodec_b200.so (sm_100a only).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdarg.h>
+#include <atomic>
+
+#include "diffcodec_b200.h"
+
+#if defined(__CUDA_ARCH__) && (__CUDA_ARCH__ < 1000)
+#error "libdiffcodec_b200 is written for sm_100a (B200) only"
+#endif
+
+#define DCB_STR_(x) #x
+#define DCB_STR(x) DCB_STR_(x)
+
+namespace dcb {
+
+// ------------------------------------------------------------------------------------------------
+// host side: errors, launch accounting
+// ------------------------------------------------------------------------------------------------
+int set_error(int code, const char* fmt, ...);
+extern std::atomic<long long> g_launches;
+inline void count_launch(int n = 1) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+// After a <<<>>> launch: convert a launch error into the ABI's positive cudaError_t code.
+#define DCB_CHECK_LAUNCH(what)                                                        \
+    do {                                                                              \
+        cudaError_t e__ = cudaGetLastError();                                         \
+        if (e__ != cudaSuccess)                                                       \
+            return dcb::set_error((int)e__, "%s: %s", what, cudaGetErrorString(e__)); \
+        dcb::count_launch();                                                          \
+    } while (0)
+
+#define DCB_CHECK_CUDA(expr)                                                           \
+    do {                                                                               \
+        cudaError_t e__ = (expr);                                                      \
+        if (e__ != cudaSuccess)                                                        \
+            return dcb::set_error((int)e__, "%s: %s", #expr, cudaGetErrorString(e__)); \
+    } while (0)
+
+// Strided 4-d view handed to kernels by value (strides in elements).
+struct View {
+    const void* p;
+    long long sN, sC, sH, sW;
+};
+
+inline View make_view(const DcbTensor* t) {
+    View v;
+    v.p = t ? t->ptr : nullptr;
+    v.sN = t ? t->stride[0] : 0;
+    v.sC = t ? t->stride[1] : 0;
+    v.sH = t ? t->stride[2] : 0;
+    v.sW = t ? t->stride[3] : 0;
+    return v;
+}
+
+inline bool is_contig(const DcbTensor* t) {
+    long long e = 1;
+    for (int d = 3; d >= 0; --d) {
+        if (t->size[d] != 1 && t->stride[d] != e) return false;
+        e *= t->size[d];
+    }
+    return true;
+}
+
+inline int elem_size(int dtype) { return dtype == DCB_F64 ? 8 : (dtype == DCB_BF16 ? 2 : 4); }
+
+inline long long align_up(long long v, long long a) { return (v + a - 1) / a * a; }
+
+int device_sm_count();
+
+// ------------------------------------------------------------------------------------------------
+// device side
+// ------------------------------------------------------------------------------------------------
+template <class T> struct Acc { using type = float; };
+template <> struct Acc<double> { using type = double; };
+
+template <class A, class T> __device__ __forceinline__ A ld(const T* p) { return (A)(*p); }
+template <> __device__ __forceinline__ float ld<float, __nv_bfloat16>(const __nv_bfloat16* p) { return __bfloat162float(*p); }
+
+template <class T, class A> __device__ __forceinline__ void st(T* p, A v) { *p = (T)v; }
+template <> __device__ __forceinline__ void st<__nv_bfloat16, float>(__nv_bfloat16* p, float v) { *p = __float2bfloat16_rn(v); }
+
+// rounded (non-contracted) arithmetic: the reference rounds every product before the atomic add
+__device__ __forceinline__ float mul_rn(float a, float b) { return __fmul_rn(a, b); }
+__device__ __forceinline__ double mul_rn(double a, double b) { return __dmul_rn(a, b); }
+__device__ __forceinline__ float sub_rn(float a, float b) { return __fsub_rn(a, b); }
+__device__ __forceinline__ double sub_rn(double a, double b) { return __dsub_rn(a, b); }
+__device__ __forceinline__ float add_rn(float a, float b) { return __fadd_rn(a, b); }
+__device__ __forceinline__ double add_rn(double a, double b) { return __dadd_rn(a, b); }
+__device__ __forceinline__ float fma_rn(float a, float b, float c) { return __fmaf_rn(a, b, c); }
+__device__ __forceinline__ double fma_rn(double a, double b, double c) { return __fma_rn(a, b, c); }
+
+__device__ __forceinline__ float floor_t(float v) { return floorf(v); }
+__device__ __forceinline__ double floor_t(double v) { return floor(v); }
+__device__ __forceinline__ float exp_t(float v) { return expf(v); }
+__device__ __forceinline__ double exp_t(double v) { return exp(v); }
+__device__ __forceinline__ int to_int_sat(float v) { return __float2int_rz(v); }   // cvt.rzi.s32.f32 saturates
+__device__ __forceinline__ int to_int_sat(double v) { return __double2int_rz(v); }
+__device__ __forceinline__ bool finite_t(float v) { return isfinite(v); }
+__device__ __forceinline__ bool finite_t(double v) { return isfinite(v); }
+
+// no-return reductions (REDG); the float4 form is one 16-byte L2 transaction per lane (sm_90+)
+__device__ __forceinline__ void red_add(float* p, float v) { atomicAdd(p, v); }
+__device__ __forceinline__ void red_add(double* p, double v) { atomicAdd(p, v); }
+__device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, float d) {
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+__device__ __forceinline__ void red_add_v2(float* p, float a, float b) {
+    asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(p), "f"(a), "f"(b) : "memory");
+}
+
+// Bilinear footprint of one source pixel: softsplat.py:298-318 (and :386-404, :457-470).
+template <class A> struct Foot {
+    A fx, fy;        // landing position
+    int x0, y0;      // north-west corner
+    A wnw, wne, wsw, wse;
+    bool finite;
+};
+
+template <class A> __device__ __forceinline__ Foot<A> make_foot(int x, int y, A flow_x, A flow_y) {
+    Foot<A> f;
+    f.fx = add_rn((A)x, flow_x);
+    f.fy = add_rn((A)y, flow_y);
+    f.finite = finite_t(f.fx) && finite_t(f.fy);
+    f.x0 = to_int_sat(floor_t(f.fx));
+    f.y0 = to_int_sat(floor_t(f.fy));
+    // `x0 + 1` wraps on the device exactly like the reference's int arithmetic
+    const A x0f = (A)f.x0, y0f = (A)f.y0;
+    const A x1f = (A)(int)((unsigned)f.x0 + 1u), y1f = (A)(int)((unsigned)f.y0 + 1u);
+    const A ex = sub_rn(x1f, f.fx), ey = sub_rn(y1f, f.fy);   // (SE - f)
+    const A dx = sub_rn(f.fx, x0f), dy = sub_rn(f.fy, y0f);   // (f - NW)
+    f.wnw = mul_rn(ex, ey);
+    f.wne = mul_rn(dx, ey);
+    f.wsw = mul_rn(ex, dy);
+    f.wse = mul_rn(dx, dy);
+    return f;
+}
+
+}  // namespace dcb

@@ -1,0 +1,248 @@
+// splat_bwd.cu -- backward of the forward splat (K3) for sm_100a.
+//
+// Replaces softsplat_func.backward (kernels `softsplat_ingrad` controlnet/softsplat.py:368-435 and
+// `softsplat_flowgrad` :439-524) AND the autograd of the eager ops around it (exp, mul, cat,
+// slice, eps, div -- softsplat.py:240-270; (1 - mask) product -- control_utils.py:69-70).
+//
+// Closed form, with G the upstream gradient, D the saved normaliser,
+// out the saved output, g(m) in {1, m, exp(m)}:
+//   target side (K3a, one thread per target pixel):
+//       a = (1 - mask) / D              T = -(sum_c G_c * out_c) / D
+//   source side (K3b, gather; no atomics), corners k = NW, NE, SW, SE with bilinear weights w_k:
+//       A_k      = sum_c G_c(k) * in_c
+//       gradIn_c = g * sum_k w_k a_k G_c(k)
+//       B_k      = a_k A_k + T_k                     (B_k = A_k for 'sum')
+//       gradMetric = g'(m) * sum_k w_k B_k           (g' = exp(m) | 1)
+//       gradFlow_x = g * [(B_NE - B_NW)(y1 - fy) + (B_SE - B_SW)(fy - y0)]
+//       gradFlow_y = g * [(B_SW - B_NW)(x1 - fx) + (B_SE - B_NE)(fx - x0)]
+// The reference reads every gradOut corner 1 + 2*C' times per pixel (ingrad thread + two flowgrad
+// threads); here each corner is read once per channel and feeds all three gradients.
+//
+// Thread layout: blockDim = (PX, CS): PX source pixels, CS channel slices per pixel. CS > 1 is
+// chosen when there are too few pixels to fill the machine (8x8 .. 64x64 ControlNet pyramids with
+// hundreds of channels); the A_k partials are then reduced through shared memory.
+#include "dcb_common.cuh"
+
+namespace dcb {
+
+struct BwdArgs {
+    View gout, in, flow, metric, mask;
+    const void* out;     // [N,C,H,W] contiguous (forward output)
+    const void* norm;    // [N,1,H,W] accumulator-typed (forward normaliser)
+    void* tscal;         // workspace: [N*H*W][2] accumulator-typed (a, T)
+    void* gin;           // [N,C,H,W] contiguous or null
+    void* gflow;         // [N,2,H,W] contiguous or null
+    void* gmetric;       // [N,1,H,W] contiguous or null
+    unsigned total, HW;
+    int N, C, H, W;
+    int mode, eps;
+    int px, cs;          // block shape
+};
+
+// K3a -- target-side scalars.
+template <class T>
+__global__ void __launch_bounds__(256) k_bwd_target(const BwdArgs a) {
+    using A = typename Acc<T>::type;
+    const unsigned p = blockIdx.x * 256 + threadIdx.x;
+    if (p >= a.total) return;
+    const unsigned n = p / a.HW, r = p - n * a.HW;
+    const int y = (int)(r / (unsigned)a.W), x = (int)(r - (unsigned)y * (unsigned)a.W);
+    const A d = ((const A*)a.norm)[p];
+    const T* gp = (const T*)a.gout.p + n * a.gout.sN + y * a.gout.sH + x * a.gout.sW;
+    const T* op = (const T*)a.out + (long long)n * a.C * a.HW + r;
+    A dot = (A)0;
+    for (int c = 0; c < a.C; ++c) dot += ld<A>(gp + c * a.gout.sC) * ld<A>(op + (long long)c * a.HW);
+    A keep = (A)1;
+    if (a.mask.p) {
+        const T* mp = (const T*)a.mask.p + n * a.mask.sN + y * a.mask.sH + x * a.mask.sW;
+        keep = (A)1 - ld<A>(mp);
+    }
+    A* ts = (A*)a.tscal + 2ll * p;
+    ts[0] = keep / d;
+    // d(normaliser)/d(S_w) is 0 where clip(1e-7) was active (softsplat.py:266); for zeroeps the
+    // replaced entries have out == 0, hence dot == 0, on their own
+    const bool clipped = a.eps == DCB_EPS_CLIP && d == (A)0.0000001;
+    ts[1] = clipped ? (A)0 : -dot / d;
+}
+
+// K3b -- source-side gather.
+template <class T, class TF>
+__global__ void __launch_bounds__(256) k_bwd_source(const BwdArgs a) {
+    using A = typename Acc<T>::type;
+    extern __shared__ unsigned char smem_raw[];
+    A* red = (A*)smem_raw;                                        // [cs][px][4] when cs > 1
+
+    const int tx = threadIdx.x, ty = threadIdx.y;
+    const unsigned p = blockIdx.x * a.px + tx;
+    const bool live = p < a.total;
+    const unsigned pc = live ? p : 0;
+    const unsigned n = pc / a.HW, r = pc - n * a.HW;
+    const int y = (int)(r / (unsigned)a.W), x = (int)(r - (unsigned)y * (unsigned)a.W);
+    const int W = a.W, H = a.H;
+    const bool normalised = a.mode != DCB_MODE_SUM;
+
+    const TF* fp = (const TF*)a.flow.p + n * a.flow.sN + y * a.flow.sH + x * a.flow.sW;
+    const Foot<A> f = make_foot<A>(x, y, ld<A>(fp), ld<A>(fp + a.flow.sC));
+    const int x1 = (int)((unsigned)f.x0 + 1u), y1 = (int)((unsigned)f.y0 + 1u);
+    const bool vx0 = (unsigned)f.x0 < (unsigned)W, vx1 = (unsigned)x1 < (unsigned)W;
+    const bool vy0 = (unsigned)f.y0 < (unsigned)H, vy1 = (unsigned)y1 < (unsigned)H;
+    const bool ok = live && f.finite;                             // softsplat.py:389-390, 460-461
+    const bool b[4] = {ok && vx0 && vy0, ok && vx1 && vy0, ok && vx0 && vy1, ok && vx1 && vy1};
+    const A w[4] = {f.wnw, f.wne, f.wsw, f.wse};
+    // gradOut offsets of the four corners (strided)
+    long long go[4];
+    go[0] = (long long)f.y0 * a.gout.sH + (long long)f.x0 * a.gout.sW;
+    go[1] = go[0] + a.gout.sW;
+    go[2] = go[0] + a.gout.sH;
+    go[3] = go[2] + a.gout.sW;
+
+    A g = (A)1, gprime = (A)1;
+    if (a.mode == DCB_MODE_LINEAR || a.mode == DCB_MODE_SOFT) {
+        const T* mp = (const T*)a.metric.p + n * a.metric.sN + y * a.metric.sH + x * a.metric.sW;
+        const A m = ld<A>(mp);
+        g = a.mode == DCB_MODE_SOFT ? exp_t(m) : m;
+        gprime = a.mode == DCB_MODE_SOFT ? g : (A)1;
+    }
+
+    A ak[4] = {(A)1, (A)1, (A)1, (A)1}, tk[4] = {(A)0, (A)0, (A)0, (A)0};
+    if (normalised) {
+        const A* ts = (const A*)a.tscal + 2ll * ((long long)n * a.HW + (long long)f.y0 * W + f.x0);
+        const long long to[4] = {0, 2, 2ll * W, 2ll * W + 2};
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+            if (b[k]) { ak[k] = ts[to[k]]; tk[k] = ts[to[k] + 1]; }
+    }
+    A wa[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) wa[k] = b[k] ? w[k] * ak[k] : (A)0;
+
+    const T* gp = (const T*)a.gout.p + n * a.gout.sN;
+    const T* ip = (const T*)a.in.p + n * a.in.sN + y * a.in.sH + x * a.in.sW;
+    T* gi = a.gin ? (T*)a.gin + (long long)n * a.C * a.HW + r : nullptr;
+
+    A Ak[4] = {(A)0, (A)0, (A)0, (A)0};
+    const bool need_A = (a.gflow != nullptr) || (a.gmetric != nullptr);
+    for (int c = ty; c < a.C; c += a.cs) {
+        const T* gc = gp + c * a.gout.sC;
+        A gk[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) gk[k] = b[k] ? ld<A>(gc + go[k]) : (A)0;
+        if (gi && live) {
+            A s = (A)0;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) s = fma_rn(gk[k], wa[k], s);
+            st<T, A>(gi + (long long)c * a.HW, s * g);            // non-finite flow: all b[k] false -> 0
+        }
+        if (need_A && ok) {
+            const A v = ld<A>(ip + c * a.in.sC);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) Ak[k] = fma_rn(gk[k], v, Ak[k]);
+        }
+    }
+    if (!need_A) return;
+
+    if (a.cs > 1) {                                               // reduce A_k over the channel slices
+        A* mine = red + ((size_t)ty * a.px + tx) * 4;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) mine[k] = Ak[k];
+        __syncthreads();
+        if (ty != 0) return;
+        for (int s = 1; s < a.cs; ++s) {
+            const A* o = red + ((size_t)s * a.px + tx) * 4;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) Ak[k] += o[k];
+        }
+    }
+    if (!live) return;
+
+    A B[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) B[k] = b[k] ? (normalised ? fma_rn(ak[k], Ak[k], tk[k]) : Ak[k]) : (A)0;
+
+    if (a.gmetric) {
+        A s = (A)0;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) s = fma_rn(w[k], B[k], s);
+        st<T, A>((T*)a.gmetric + p, ok ? s * gprime : (A)0);
+    }
+    if (a.gflow) {
+        // d w / d flow, softsplat.py:477-487
+        const A ey = sub_rn((A)y1, f.fy), dy = sub_rn(f.fy, (A)f.y0);
+        const A ex = sub_rn((A)x1, f.fx), dx = sub_rn(f.fx, (A)f.x0);
+        A gx = (B[1] - B[0]) * ey + (B[3] - B[2]) * dy;
+        A gy = (B[2] - B[0]) * ex + (B[3] - B[1]) * dx;
+        if (!ok) { gx = (A)0; gy = (A)0; }
+        // gradFlow has the dtype of the flow tensor
+        TF* gf = (TF*)a.gflow + (long long)n * 2 * a.HW + r;
+        st<TF, A>(gf, gx * g);
+        st<TF, A>(gf + a.HW, gy * g);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+long long splat_bwd_workspace(long long N, long long H, long long W, int dtype, int mode) {
+    if (mode == DCB_MODE_SUM) return 0;
+    return align_up(N * H * W * 2 * (dtype == DCB_F64 ? 8 : 4), 256);
+}
+
+template <class T, class TF>
+static int launch_bwd(BwdArgs& a, cudaStream_t st) {
+    using A = typename Acc<T>::type;
+    if (a.mode != DCB_MODE_SUM) {
+        k_bwd_target<T><<<(a.total + 255) / 256, 256, 0, st>>>(a);
+        DCB_CHECK_LAUNCH("k_bwd_target");
+    }
+    // channel slices: fill ~148 SMs x 8 CTAs when pixels are scarce
+    int cs = 1;
+    while (cs < 32 && cs * 2 <= a.C && (long long)a.total * cs < 148LL * 2048) cs *= 2;
+    a.cs = cs;
+    a.px = 256 / cs;
+    dim3 block(a.px, cs);
+    const unsigned blocks = (a.total + a.px - 1) / a.px;
+    const size_t smem = cs > 1 ? (size_t)256 * 4 * sizeof(A) : 0;
+    k_bwd_source<T, TF><<<blocks, block, smem, st>>>(a);
+    DCB_CHECK_LAUNCH("k_bwd_source");
+    return DCB_OK;
+}
+
+int splat_bwd_impl(const DcbTensor* gout, const DcbTensor* in, const DcbTensor* flow, const DcbTensor* metric,
+                   const DcbTensor* out, const DcbTensor* norm, const DcbTensor* mask, const DcbTensor* gin,
+                   const DcbTensor* gflow, const DcbTensor* gmetric, void* ws, long long ws_bytes, int mode,
+                   int eps, cudaStream_t st) {
+    BwdArgs a;
+    a.gout = make_view(gout);
+    a.in = make_view(in);
+    a.flow = make_view(flow);
+    a.metric = make_view(metric);
+    a.mask = make_view(mask);
+    a.out = out ? out->ptr : nullptr;
+    a.norm = norm ? norm->ptr : nullptr;
+    a.gin = gin ? gin->ptr : nullptr;
+    a.gflow = gflow ? gflow->ptr : nullptr;
+    a.gmetric = gmetric ? gmetric->ptr : nullptr;
+    a.N = (int)in->size[0]; a.C = (int)in->size[1]; a.H = (int)in->size[2]; a.W = (int)in->size[3];
+    a.HW = (unsigned)(in->size[2] * in->size[3]);
+    a.total = (unsigned)(in->size[0] * in->size[2] * in->size[3]);
+    a.mode = mode;
+    a.eps = eps;
+    a.tscal = nullptr;
+    if (a.total == 0) return DCB_OK;
+    if (!a.gin && !a.gflow && !a.gmetric) return DCB_OK;
+    if (mode != DCB_MODE_SUM) {
+        const long long need = splat_bwd_workspace(a.N, a.H, a.W, in->dtype, mode);
+        if (!ws || ws_bytes < need || ((uintptr_t)ws & 255))
+            return set_error(DCB_E_WORKSPACE, "splat_bwd: workspace of %lld bytes (256 B aligned) required, got %lld",
+                             need, ws_bytes);
+        a.tscal = ws;
+    }
+    const bool flow_f32 = flow->dtype == DCB_F32;
+    switch (in->dtype) {
+        case DCB_F32: return launch_bwd<float, float>(a, st);
+        case DCB_F64: return launch_bwd<double, double>(a, st);
+        case DCB_BF16:
+            return flow_f32 ? launch_bwd<__nv_bfloat16, float>(a, st) : launch_bwd<__nv_bfloat16, __nv_bfloat16>(a, st);
+    }
+    return set_error(DCB_E_DTYPE, "splat_bwd: unsupported dtype %d", in->dtype);
+}
+
+}  // namespace dcb

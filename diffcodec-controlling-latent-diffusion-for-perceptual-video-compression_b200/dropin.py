@@ -1,0 +1,37 @@
+"""Install this package in place of the reference's hot-path modules.
+
+After ``install()``, ``from controlnet.softsplat import softsplat`` and
+``from controlnet.control_utils import compute_mask, FeatureWarperSoftsplat, ...`` (the imports
+used by the reference's ``extractors.py:4``, ``dataset.py:11-12``, ``residual_utils.py:10-13``,
+``flownet.py:8``) resolve to the B200 implementations; the rest of the pipeline is untouched.
+"""
+from __future__ import annotations
+
+import importlib
+import sys
+import types
+
+__all__ = ["install"]
+
+
+def install(force: bool = True) -> None:
+    # the package re-exports the function `softsplat` under the submodule's name: go through importlib
+    softsplat = importlib.import_module(__package__ + ".softsplat")
+    control_utils = importlib.import_module(__package__ + ".control_utils")
+    warp = importlib.import_module(__package__ + ".warp")
+
+    try:
+        pkg = importlib.import_module("controlnet")
+    except Exception:
+        pkg = types.ModuleType("controlnet")
+        pkg.__path__ = []
+        sys.modules["controlnet"] = pkg
+    for name, mod in (("softsplat", softsplat), ("control_utils", control_utils)):
+        full = f"controlnet.{name}"
+        if force or full not in sys.modules:
+            sys.modules[full] = mod
+            setattr(pkg, name, mod)
+    # the dormant bilinear backward warp lives under cmp.models.modules.warp in the reference
+    full = "cmp.models.modules.warp"
+    if full in sys.modules:
+        sys.modules[full].WarpingLayerBWFlow = warp.WarpingLayerBWFlow

@@ -1,0 +1,182 @@
+/*
+ * diffcodec_b200.h -- C ABI of the B200-native motion-compensation library
+ * (libdiffcodec_b200.so, hand-written sm_100a CUDA).
+ *
+ * This is the drop-in boundary for ONE path of the reference
+ * (Maryamsana-1998/DiffCodec-...): forward splatting by optical flow in the
+ * sum / avg / linear / soft modes with its backward, the bilinear backward warp,
+ * and the residual / occlusion-mask / fusion arithmetic that builds the
+ * ControlNet conditioning. The reference has no C FFI of its own: its de-facto
+ * native boundary is the CuPy launch of three JIT-compiled kernels with raw
+ * data_ptr()s (controlnet/softsplat.py:285-290, 340-345, 369-376, 430-435,
+ * 440-447, 519-524). Each entry point below cites the reference interface it
+ * replaces (paths relative to the reference repository root).
+ *
+ * Contract (all entry points):
+ *   - plain pointers and sizes only; no torch types;
+ *   - every pointer is DEVICE memory of the current CUDA device, owned by the
+ *     caller; the library never allocates, never synchronises, never creates a
+ *     stream, and does not retain pointers after returning (CUDA-graph safe);
+ *   - all work is enqueued on `stream` (a cudaStream_t passed as void*);
+ *   - returns 0 on success, a negative DCB_E_* for argument errors, a positive
+ *     cudaError_t for launch errors; text via dcb_last_error() (thread-local);
+ *   - there is no CPU fallback of any kind.
+ */
+#ifndef DIFFCODEC_B200_H
+#define DIFFCODEC_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DCB_VERSION 100 /* 0.1.0 */
+
+/* element types */
+enum { DCB_F32 = 0, DCB_BF16 = 1, DCB_F64 = 2 };
+
+/* splat modes: controlnet/softsplat.py:232-274 (strMode.split('-')[0]) */
+enum { DCB_MODE_SUM = 0, DCB_MODE_AVG = 1, DCB_MODE_LINEAR = 2, DCB_MODE_SOFT = 3 };
+
+/* normaliser variants: controlnet/softsplat.py:256-266 (strMode.split('-')[1]) */
+enum { DCB_EPS_ADD = 0, DCB_EPS_ZERO = 1, DCB_EPS_CLIP = 2 };
+
+/* flags */
+enum {
+    DCB_FLAG_DETERMINISTIC = 1, /* sort-then-reduce: bit-identical run to run and to the sequential oracle */
+    DCB_FLAG_WS_CLEAN = 2       /* caller guarantees the accumulator part of the workspace is all-zero on entry;
+                                   the library leaves it all-zero on exit (saves the memset) */
+};
+
+/* residual recipe variants */
+enum {
+    DCB_RECIPE_DATASET = 0, /* controlnet/dataset.py:233-265  (occlusion masks are the fusion weights) */
+    DCB_RECIPE_WRAPPER = 1  /* controlnet/residual_utils.py:159-199 (ones metrics + double-hole fill) */
+};
+
+/* error codes */
+enum {
+    DCB_OK = 0,
+    DCB_E_NULL = -1,      /* required pointer missing */
+    DCB_E_SHAPE = -2,     /* shapes disagree (the reference would assert / index out of range) */
+    DCB_E_DTYPE = -3,     /* unsupported or mixed element types */
+    DCB_E_MODE = -4,      /* unknown mode / eps / variant / flag combination */
+    DCB_E_WORKSPACE = -5, /* workspace missing, too small or misaligned (256 B) */
+    DCB_E_LIMIT = -6,     /* a size exceeds what the kernels index (H*W < 2^31, C <= 65535 ...) */
+    DCB_E_ALIGN = -7      /* pointer not aligned to its element size */
+};
+
+/* 4-d NCHW-indexed view with arbitrary element strides. */
+typedef struct DcbTensor {
+    void* ptr;
+    int32_t dtype;     /* DCB_F32 / DCB_BF16 / DCB_F64 */
+    int32_t reserved;
+    int64_t size[4];   /* N, C, H, W */
+    int64_t stride[4]; /* in elements */
+} DcbTensor;
+
+int dcb_version(void);
+const char* dcb_last_error(void);
+/* static description of the build: arch, kernels, compile flags */
+const char* dcb_build_info(void);
+/* number of kernels this library has launched in the calling process (all threads); for bench.py's gpu_launches */
+int64_t dcb_launch_count(void);
+
+/*
+ * Workspace size (bytes) for dcb_splat_fwd / dcb_splat_bwd with these sizes. 0 is a valid answer.
+ * `elem_dtype` is the dtype of tenIn.
+ */
+int64_t dcb_splat_workspace_bytes(int64_t N, int64_t C, int64_t H, int64_t W, int32_t elem_dtype,
+                                  int32_t mode, int32_t flags);
+
+/*
+ * Forward splat. Replaces, in one call, the eager pre-ops, `new_zeros`, the `softsplat_out`
+ * kernel and the eager post-ops of softsplat() -- controlnet/softsplat.py:232-274 and
+ * softsplat_func.forward :277-355. With mode = DCB_MODE_SUM it is exactly
+ * softsplat_func.apply(tenIn, tenFlow).
+ *
+ *   in      [N,C,H,W]  any strides
+ *   flow    [N,2,H,W]  any strides; same dtype as `in`, or F32 when `in` is BF16
+ *   metric  [N,1,H,W]  required for LINEAR/SOFT, must be NULL for SUM/AVG (softsplat.py:235-238)
+ *   out     [N,C,H,W]  contiguous NCHW, same dtype as `in` (softsplat.py:281)
+ *   norm    [N,1,H,W]  optional (may be NULL): receives the normaliser AFTER the eps rule, in the
+ *                      accumulator type (F32 for F32/BF16 input, F64 for F64); dcb_splat_bwd needs it
+ *   mask    [N,1,H,W]  optional: out is multiplied by (1 - mask) -- controlnet/control_utils.py:69-70
+ */
+int dcb_splat_fwd(const DcbTensor* in, const DcbTensor* flow, const DcbTensor* metric,
+                  const DcbTensor* out, const DcbTensor* norm, const DcbTensor* mask,
+                  void* workspace, int64_t workspace_bytes,
+                  int32_t mode, int32_t eps, int32_t flags, void* stream);
+
+/*
+ * Backward of dcb_splat_fwd. Replaces softsplat_func.backward (kernels `softsplat_ingrad`,
+ * `softsplat_flowgrad`, controlnet/softsplat.py:357-528) fused with the autograd of the eager
+ * pre/post ops (exp, mul, cat, slice, add-eps, div; softsplat.py:240-270) and of the (1 - mask)
+ * product. Any of grad_in / grad_flow / grad_metric may be NULL (needs_input_grad gating,
+ * softsplat.py:364-365). With mode = DCB_MODE_SUM it is exactly softsplat_func.backward.
+ *
+ *   grad_out [N,C,H,W] any strides;  in/flow/metric/mask as given to the forward
+ *   out, norm: what the forward produced (ignored for SUM)
+ *   grad_in [N,C,H,W], grad_flow [N,2,H,W], grad_metric [N,1,H,W]: contiguous, fully overwritten
+ */
+int dcb_splat_bwd(const DcbTensor* grad_out, const DcbTensor* in, const DcbTensor* flow,
+                  const DcbTensor* metric, const DcbTensor* out, const DcbTensor* norm,
+                  const DcbTensor* mask,
+                  const DcbTensor* grad_in, const DcbTensor* grad_flow, const DcbTensor* grad_metric,
+                  void* workspace, int64_t workspace_bytes,
+                  int32_t mode, int32_t eps, int32_t flags, void* stream);
+
+/*
+ * Bilinear backward warp (+ optional fused residual). Replaces WarpingLayerBWFlow.forward,
+ * cmp/models/modules/warp.py:9-25 (flow normalisation, linspace grid, grid_sample with zeros
+ * padding). align_corners = 0 reproduces the layer as executed by current torch (grid_sample
+ * default), 1 the convention its normalisation was written for.
+ *
+ *   image [N,C,H,W], flow [N,2,H,W] any strides; warped [N,C,H,W] contiguous
+ *   gt / residual: both NULL, or both given: residual = gt - warped (controlnet/residual_utils.py:199)
+ */
+int dcb_backwarp_fwd(const DcbTensor* image, const DcbTensor* flow, const DcbTensor* gt,
+                     const DcbTensor* warped, const DcbTensor* residual,
+                     int32_t align_corners, void* stream);
+
+/*
+ * Backward of dcb_backwarp_fwd w.r.t. image and flow (what autograd derives through
+ * grid_sample in cmp/models/modules/warp.py:25). grad_image is fully overwritten (zeroed, then
+ * scatter-added); either output may be NULL. A workspace is needed only for BF16 grad_image
+ * (fp32 accumulation, rounded once).
+ */
+int64_t dcb_backwarp_bwd_workspace_bytes(int64_t N, int64_t C, int64_t H, int64_t W, int32_t elem_dtype);
+int dcb_backwarp_bwd(const DcbTensor* grad_warped, const DcbTensor* image, const DcbTensor* flow,
+                     const DcbTensor* grad_image, const DcbTensor* grad_flow,
+                     int32_t align_corners, void* workspace, int64_t workspace_bytes, void* stream);
+
+/*
+ * Occlusion mask. Replaces compute_mask(), controlnet/control_utils.py:11-17:
+ *   warp = softsplat(flow_a, flow_b, ones, 'soft');  mask = (||flow_b + warp||_2 > 0.3).float()
+ * flow_a, flow_b [N,2,H,W]; mask [N,1,H,W] contiguous, same dtype.
+ */
+int64_t dcb_occlusion_mask_workspace_bytes(int64_t N, int64_t H, int64_t W);
+int dcb_occlusion_mask(const DcbTensor* flow_a, const DcbTensor* flow_b, const DcbTensor* mask,
+                       void* workspace, int64_t workspace_bytes, int32_t flags, void* stream);
+
+/*
+ * Conditioning builder: warped frame, two occlusion masks, confidence fusion, residual, in two
+ * launches. Replaces the arithmetic of ResidueDataset.__getitem__ (controlnet/dataset.py:233-265,
+ * variant DCB_RECIPE_DATASET) and WarpingDatasetWrapper.__getitem__
+ * (controlnet/residual_utils.py:159-199, variant DCB_RECIPE_WRAPPER), batched over N.
+ *
+ *   image1, gt [N,C,H,W] (C <= 3... any C); flow1, flow2 [N,2,H,W]
+ *   fused, residual [N,C,H,W] contiguous; occ_fwd / occ_bwd [N,1,H,W] optional outputs
+ */
+int64_t dcb_residual_workspace_bytes(int64_t N, int64_t C, int64_t H, int64_t W);
+int dcb_residual_fused(const DcbTensor* image1, const DcbTensor* flow1, const DcbTensor* flow2,
+                       const DcbTensor* gt, const DcbTensor* fused, const DcbTensor* residual,
+                       const DcbTensor* occ_fwd, const DcbTensor* occ_bwd,
+                       void* workspace, int64_t workspace_bytes,
+                       int32_t variant, int32_t flags, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DIFFCODEC_B200_H */

@@ -1,0 +1,126 @@
+"""CPU-only checks: the C-ABI library loads and exports exactly what include/*.h declares, the
+host logic (mode parsing, asserts, sharding) behaves, the N>1 gather path works over gloo."""
+import os
+import re
+import subprocess
+import sys
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _header_symbols():
+    text = open(os.path.join(ROOT, "include", "diffcodec_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(dcb_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol():
+    import diffcodec_b200
+    L = diffcodec_b200._lib
+    lib = L.lib()                                   # loads without a GPU (static cudart, no compute calls)
+    declared = _header_symbols()
+    assert declared == sorted(L.SYMBOLS), "ctypes table and header disagree"
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert lib.dcb_version() == 100
+    assert b"sm_100a" in lib.dcb_build_info()
+    out = subprocess.run(["nm", "-D", "--defined-only", L.LIB_PATH], capture_output=True, text=True).stdout
+    exported = sorted(set(re.findall(r" T (dcb_[a-z0-9_]+)", out)))
+    assert exported == declared
+
+
+def test_workspace_queries_need_no_gpu():
+    import diffcodec_b200
+    L = diffcodec_b200._lib
+    lib = L.lib()
+    assert lib.dcb_splat_workspace_bytes(1, 3, 1080, 1920, L.DCB_F32, L.MODE_SOFT, 0) == 1080 * 1920 * 16
+    assert lib.dcb_splat_workspace_bytes(1, 3, 1080, 1920, L.DCB_F32, L.MODE_SUM, 0) == 0
+    assert lib.dcb_splat_workspace_bytes(8, 64, 256, 256, L.DCB_F32, L.MODE_SOFT, 0) == 8 * 65 * 256 * 256 * 4
+    assert lib.dcb_occlusion_mask_workspace_bytes(2, 64, 64) == 2 * 64 * 64 * 16
+    assert lib.dcb_residual_workspace_bytes(1, 3, 1080, 1920) == 1080 * 1920 * 40
+
+
+def test_cpu_tensors_are_refused_like_the_reference():
+    import diffcodec_b200 as d
+    tin, flow = torch.zeros(1, 3, 4, 4), torch.zeros(1, 2, 4, 4)
+    with pytest.raises(AssertionError):
+        d.softsplat(tin, flow, None, "sum")          # reference: assert(False) on non-CUDA, softsplat.py:347-348
+    with pytest.raises(AssertionError):
+        d.softsplat(tin, flow, None, "soft")         # metric required, softsplat.py:238
+    with pytest.raises(AssertionError):
+        d.softsplat(tin, flow, torch.zeros(1, 1, 4, 4), "avg")
+    with pytest.raises(AssertionError):
+        d.softsplat(tin, flow, None, "median")
+
+
+def test_missing_library_fails_loudly(tmp_path, monkeypatch):
+    import diffcodec_b200 as d
+    L = d._lib
+    monkeypatch.setattr(L, "_lib", None)
+    monkeypatch.setattr(L, "LIB_PATH", str(tmp_path / "nope.so"))
+    with pytest.raises(RuntimeError, match="no CPU or PyTorch fallback"):
+        L.lib()
+
+
+def test_product_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "diffcodec-controlling-latent-diffusion-for-perceptual-video-compression_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                text = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle", text, flags=re.M), f
+                assert "liboracle" not in text, f
+
+
+def test_dropin_install():
+    import diffcodec_b200 as d
+    d.install()
+    from controlnet.softsplat import softsplat                      # noqa: the reference's import lines
+    from controlnet.control_utils import zero_module, resize_and_normalize_flow_batched, FeatureWarperSoftsplat, compute_mask, FDN  # noqa
+    assert softsplat is d.softsplat and compute_mask is d.compute_mask
+
+
+def test_gop_sharding():
+    import diffcodec_b200 as d
+    units = d.enumerate_gops()
+    assert len(units) == 975 and sum(u.inter_frames for u in units) == 2925
+    for world in (1, 2, 4, 8):
+        shards = [d.shard_units(units, r, world) for r in range(world)]
+        assert sorted(sum(shards, []), key=lambda u: (u.sequence, u.index)) == sorted(units, key=lambda u: (u.sequence, u.index))
+        assert max(map(len, shards)) - min(map(len, shards)) <= 1
+    assert units[0].seed() == d.enumerate_gops()[0].seed() and units[0].seed() != units[1].seed()
+    assert d.enumerate_gops([("x", 9)], gop=8)[0].inter_frames == 7 and len(d.enumerate_gops([("x", 9)], gop=8)) == 1
+
+
+_WORKER = r"""
+import os, sys, torch, torch.distributed as dist
+sys.path.insert(0, os.environ["DCB_ROOT"])
+import diffcodec_b200 as d
+dist.init_process_group("gloo", rank=int(os.environ["RANK"]), world_size=int(os.environ["WORLD_SIZE"]))
+rank, world = dist.get_rank(), dist.get_world_size()
+units = d.shard_units(d.enumerate_gops([("a", 20), ("b", 12)]), rank, world)
+table = torch.stack([d.checksum(torch.full((4, 4), float(u.seed() % 97))) for u in units])
+allsums = d.gather_checksums(table)
+assert allsums.shape[0] == world and allsums.shape[2] == 3
+total = float(allsums[..., 2].sum())
+assert total == 16 * 8, total                      # 8 GOPs, 16 elements each, none lost or duplicated
+outs = d.gather_outputs(torch.full((2, 3), float(rank)), dst=0)
+if rank == 0:
+    assert [float(o[0, 0]) for o in outs] == [0.0, 1.0]
+else:
+    assert outs is None
+dist.destroy_process_group()
+print("ok", rank)
+"""
+
+
+def test_gather_over_gloo_world2(tmp_path):
+    script = tmp_path / "worker.py"
+    script.write_text(_WORKER)
+    env = dict(os.environ, DCB_ROOT=ROOT, MASTER_ADDR="127.0.0.1", MASTER_PORT="29611", WORLD_SIZE="2")
+    procs = [subprocess.Popen([sys.executable, str(script)], env=dict(env, RANK=str(r)), stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True) for r in range(2)]
+    outs = [p.communicate(timeout=240)[0] for p in procs]
+    assert all(p.returncode == 0 for p in procs), "\n".join(outs)

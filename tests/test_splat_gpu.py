@@ -1,0 +1,268 @@
+"""GPU parity tests of the forward splat and its backward, through the C ABI, against the CPU
+oracle (oracle/) and the reference-derived golden fixtures (tests/golden/ref_emu_*.npz).
+
+Tolerances (BASELINE.json north_star): 1e-5 relative in fp32 (atomic order is not deterministic),
+1e-2 in bf16, bit-exact in deterministic mode."""
+import glob
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from tests.util import assert_close, cuda_run, make_inputs, oracle_run
+
+pytestmark = pytest.mark.gpu
+
+MODES = ["sum", "avg", "linear", "soft", "linear-zeroeps", "linear-clipeps", "soft-zeroeps", "soft-clipeps", "soft-addeps"]
+SHAPES = [(1, 3, 9, 13), (2, 1, 16, 16), (2, 4, 33, 47), (1, 7, 40, 24), (3, 2, 5, 64), (1, 65, 12, 12)]
+
+
+@pytest.fixture(scope="module")
+def dcb():
+    import diffcodec_b200
+    return diffcodec_b200
+
+
+@pytest.fixture(scope="module")
+def orc():
+    from oracle import oracle
+    oracle.lib()
+    return oracle
+
+
+@pytest.mark.parametrize("mode", MODES)
+@pytest.mark.parametrize("shape", SHAPES, ids=lambda s: "x".join(map(str, s)))
+def test_forward_backward_fp32(dcb, orc, mode, shape):
+    tin, flow, metric, gout = make_inputs(hash((mode, shape)) % 1000, *shape, flow_scale=2.5)
+    if mode.startswith("linear"):
+        metric = metric.abs() + 0.1          # keep the normaliser away from cancellation (tolerance is relative)
+    ref = oracle_run(orc, tin, flow, metric, gout, mode)
+    got = cuda_run(dcb.softsplat, tin, flow, metric, gout, mode)
+    for k in ("out", "gin", "gflow", "gmetric"):
+        if ref[k] is not None:
+            assert_close(got[k], ref[k], 1e-5, f"{mode} {shape} {k}")
+    assert got["out"].is_contiguous() and got["out"].dtype == torch.float32
+
+
+@pytest.mark.parametrize("mode", ["sum", "avg", "soft", "linear"])
+def test_forward_backward_fp64(dcb, orc, mode):
+    tin, flow, metric, gout = make_inputs(5, 2, 3, 17, 19, flow_scale=3.0, dtype=torch.float64)
+    ref = oracle_run(orc, tin, flow, metric, gout, mode)
+    got = cuda_run(dcb.softsplat, tin, flow, metric, gout, mode)
+    for k in ("out", "gin", "gflow", "gmetric"):
+        if ref[k] is not None:
+            assert_close(got[k], ref[k], 1e-12, f"{mode} fp64 {k}")
+
+
+FIXTURES = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "ref_emu_*_fast.npz")))
+GOLDEN_MODES = ["sum", "avg", "linear", "soft", "avg-zeroeps", "linear-clipeps", "soft-zeroeps", "soft-clipeps", "soft-addeps"]
+
+
+@pytest.mark.parametrize("mode", GOLDEN_MODES)
+@pytest.mark.parametrize("path", FIXTURES, ids=[os.path.basename(p)[8:-9] for p in FIXTURES])
+def test_golden_reference_vectors(dcb, path, mode):
+    """Outputs of the reference's own kernel text (sequential CPU emulation): includes integer /
+    half-integer / out-of-frame / NaN / +-Inf / 1e30 flows and an all-to-one-pixel collision."""
+    z = np.load(path)
+    f64 = z["tin"].dtype == np.float64
+    t = lambda k: torch.from_numpy(z[k])
+    got = cuda_run(dcb.softsplat, t("tin"), t("flow"), t("metric"), t("gout"), mode)
+    rel = 1e-12 if f64 else 1e-5
+    for k in ("out", "gin", "gflow", "gmetric"):
+        key = f"{mode}/{k}"
+        if key in z.files:
+            assert_close(got[k], t(key), rel, f"{os.path.basename(path)} {key}")
+
+
+def test_func_level_matches_golden(dcb):
+    for path in FIXTURES:
+        z = np.load(path)
+        ti = torch.from_numpy(z["tin"]).cuda().requires_grad_(True)
+        fl = torch.from_numpy(z["flow"]).cuda().requires_grad_(True)
+        out = dcb.softsplat_func.apply(ti, fl)
+        out.backward(torch.from_numpy(z["gout"]).cuda())
+        rel = 1e-12 if z["tin"].dtype == np.float64 else 1e-5
+        assert_close(out, torch.from_numpy(z["func/out"]), rel, "func out")
+        assert_close(ti.grad, torch.from_numpy(z["func/gin"]), rel, "func gin")
+        assert_close(fl.grad, torch.from_numpy(z["func/gflow"]), rel, "func gflow")
+
+
+@pytest.mark.parametrize("mode", ["sum", "avg", "linear", "soft"])
+@pytest.mark.parametrize("flow_fp32", [False, True])
+def test_bf16_within_1e2(dcb, orc, mode, flow_fp32):
+    """bf16 semantics: inputs bf16, positions/weights/accumulation fp32, one rounding at the output.
+    Oracle = fp32 reference on the up-cast inputs."""
+    tin, flow, metric, gout = make_inputs(7, 2, 4, 24, 40, flow_scale=1.5)
+    if mode == "linear":
+        metric = metric.abs() + 0.25
+    tb, mb, gb = tin.bfloat16(), metric.bfloat16(), gout.bfloat16()
+    fb = flow if flow_fp32 else flow.bfloat16()
+    ref = oracle_run(orc, tb.float(), fb.float(), mb.float(), gb.float(), mode)
+    got = cuda_run(dcb.softsplat, tb, fb, mb, gb, mode)
+    assert got["out"].dtype == torch.bfloat16
+    for k in ("out", "gin", "gflow", "gmetric"):
+        if ref[k] is not None:
+            assert_close(got[k].float(), ref[k], 1e-2, f"bf16 {mode} {k}")
+
+
+def test_bf16_accumulates_in_fp32(dcb):
+    """4096 sources land on one pixel: a bf16 accumulator would stall at 256."""
+    h = w = 64
+    tin = torch.ones(1, 1, h, w, dtype=torch.bfloat16, device="cuda")
+    ys, xs = torch.meshgrid(torch.arange(h), torch.arange(w), indexing="ij")
+    flow = torch.stack([(5 - xs).float(), (7 - ys).float()])[None].cuda()
+    out = dcb.softsplat(tenIn=tin, tenFlow=flow, tenMetric=None, strMode="sum")
+    assert out[0, 0, 7, 5].item() == 4096.0
+    assert out.sum().item() == 4096.0
+
+
+@pytest.mark.parametrize("mode", ["sum", "avg", "linear"])
+def test_deterministic_bit_exact(dcb, orc, mode):
+    """sort-then-reduce mode: identical bits to the sequential oracle and from run to run."""
+    tin, flow, metric, gout = make_inputs(21, 2, 3, 31, 45, flow_scale=4.0)
+    flow[0, :, :8, :8] = 0.0
+    ys, xs = torch.meshgrid(torch.arange(31), torch.arange(45), indexing="ij")
+    flow[1, 0] = (10.25 - xs).float()                       # frame 1: 1395-way collision
+    flow[1, 1] = (9.5 - ys).float()
+    me = metric if mode == "linear" else None
+    ref = orc.softsplat(tin, flow, me, mode)
+    with dcb.deterministic(True):
+        a = dcb.softsplat(tenIn=tin.cuda(), tenFlow=flow.cuda(), tenMetric=None if me is None else me.cuda(), strMode=mode)
+        b = dcb.softsplat(tenIn=tin.cuda(), tenFlow=flow.cuda(), tenMetric=None if me is None else me.cuda(), strMode=mode)
+    assert torch.equal(a, b)
+    assert torch.equal(a.cpu(), ref), f"max diff {(a.cpu() - ref).abs().max().item()}"
+
+
+def test_deterministic_soft_run_to_run(dcb, orc):
+    tin, flow, metric, _ = make_inputs(22, 1, 3, 64, 64, flow_scale=6.0)
+    with dcb.deterministic(True):
+        outs = [dcb.softsplat(tenIn=tin.cuda(), tenFlow=flow.cuda(), tenMetric=metric.cuda(), strMode="soft") for _ in range(3)]
+    assert torch.equal(outs[0], outs[1]) and torch.equal(outs[0], outs[2])
+    assert_close(outs[0], orc.softsplat(tin, flow, metric, "soft"), 1e-5, "det soft")
+
+
+def test_known_answers(dcb):
+    dev = "cuda"
+    tin = torch.randn(2, 3, 12, 20, device=dev)
+    zero = torch.zeros(2, 2, 12, 20, device=dev)
+    # C-1: zero flow, sum -> identity, bit exact
+    assert torch.equal(dcb.softsplat(tin, zero, None, "sum"), tin)
+    # C-2: integer flow -> exact shift with zero fill
+    fl = zero.clone(); fl[:, 0] = 3.0; fl[:, 1] = -2.0
+    out = dcb.softsplat(tin, fl, None, "sum")
+    exp = torch.zeros_like(tin); exp[:, :, :-2, 3:] = tin[:, :, 2:, :-3]
+    assert torch.equal(out, exp)
+    # C-3: half-pixel flow -> average of neighbours (exact in fp32)
+    fl = zero.clone(); fl[:, 0] = 0.5
+    out = dcb.softsplat(tin, fl, None, "sum")
+    exp = 0.5 * tin; exp[:, :, :, 1:] += 0.5 * tin[:, :, :, :-1]
+    assert torch.equal(out, exp)
+    # C-4: avg under zero flow -> in / (1 + 1e-7); holes -> 0
+    out = dcb.softsplat(tin, zero, None, "avg")
+    assert torch.equal(out, tin / (torch.ones_like(tin[:, :1]) + 0.0000001))
+    fl = zero.clone(); fl[:, 0] = 1000.0
+    assert torch.count_nonzero(dcb.softsplat(tin, fl, None, "avg")) == 0
+    # C-7: non-finite flow contributes nothing and gets zero gradients
+    fl = (torch.rand(2, 2, 12, 20, device=dev) * 2).requires_grad_(True)
+    with torch.no_grad():
+        fl[0, 0, 3, 4] = float("nan"); fl[1, 1, 5, 6] = float("inf")
+    ti = tin.clone().requires_grad_(True)
+    out = dcb.softsplat(ti, fl, None, "sum")
+    assert torch.isfinite(out).all()
+    out.sum().backward()
+    assert ti.grad[0, :, 3, 4].abs().sum() == 0 and ti.grad[1, :, 5, 6].abs().sum() == 0
+    assert fl.grad[0, :, 3, 4].abs().sum() == 0 and fl.grad[1, :, 5, 6].abs().sum() == 0
+    # C-8: soft with a constant metric == avg (up to the eps scaling); metric -inf removes a pixel
+    m = torch.full((2, 1, 12, 20), 0.7, device=dev)
+    fl = torch.randn(2, 2, 12, 20, device=dev)
+    a = dcb.softsplat(tin, fl, None, "avg"); s = dcb.softsplat(tin, fl, m, "soft")
+    assert_close(s, a, 1e-5, "soft(const) vs avg")
+    m2 = torch.zeros(2, 1, 12, 20, device=dev); m2[:, :, 0, 0] = -float("inf")
+    t2 = tin.clone(); t2[:, :, 0, 0] = 12345.0
+    assert dcb.softsplat(t2, zero, m2, "soft")[:, :, 0, 0].abs().max() == 0
+
+
+def test_mass_conservation_1080p(dcb):
+    """Size-independent property at BASELINE's full frame size: with every corner in range,
+    sum(out) == sum(in) to fp32 reassociation error."""
+    g = torch.Generator(device="cuda").manual_seed(0)
+    tin = torch.rand(1, 3, 1080, 1920, device="cuda", generator=g)
+    flow = torch.randn(1, 2, 1080, 1920, device="cuda", generator=g) * 8
+    ys, xs = torch.meshgrid(torch.arange(1080, device="cuda"), torch.arange(1920, device="cuda"), indexing="ij")
+    flow[:, 0] = torch.minimum(torch.maximum(flow[:, 0], 0.25 - xs), 1918.5 - xs)
+    flow[:, 1] = torch.minimum(torch.maximum(flow[:, 1], 0.25 - ys), 1078.5 - ys)
+    out = dcb.softsplat(tin, flow, None, "sum")
+    assert abs(out.double().sum().item() - tin.double().sum().item()) < 1e-6 * tin.double().sum().item()
+    # avg: where anything landed, a constant image stays constant
+    ones = torch.full_like(tin, 3.0)
+    avg = dcb.softsplat(ones, flow, None, "avg")
+    hit = dcb.softsplat(torch.ones_like(tin[:, :1]), flow, None, "sum") > 1e-3
+    assert_close(avg[:, :1][hit], torch.full_like(avg[:, :1][hit], 3.0), 1e-4, "avg of constant")
+
+
+def test_stride_contract(dcb):
+    """channels_last and sliced inputs give the same result as .contiguous(); output is NCHW-contiguous."""
+    tin = torch.randn(2, 6, 20, 28, device="cuda")
+    flow = torch.randn(2, 4, 20, 28, device="cuda") * 2
+    metric = torch.randn(2, 3, 20, 28, device="cuda") * 0.3
+    with dcb.deterministic(True):
+        base = dcb.softsplat(tin[:, :3].contiguous(), flow[:, 1:3].contiguous(), metric[:, 1:2].contiguous(), "soft")
+        a = dcb.softsplat(tin[:, :3], flow[:, 1:3], metric[:, 1:2], "soft")
+        b = dcb.softsplat(tin[:, :3].contiguous(memory_format=torch.channels_last), flow[:, 1:3], metric[:, 1:2], "soft")
+        c = dcb.softsplat(tin.permute(0, 1, 3, 2)[:, :3].permute(0, 1, 3, 2), flow[:, 1:3], metric[:, 1:2], "soft")
+    assert a.is_contiguous() and torch.equal(a, base) and torch.equal(b, base) and torch.equal(c, base)
+    # strided upstream gradient
+    ti = tin[:, :3].clone().requires_grad_(True)
+    out = dcb.softsplat(ti, flow[:, :2], None, "avg")
+    g = torch.randn(2, 3, 28, 20, device="cuda").permute(0, 1, 3, 2)
+    out.backward(g)
+    ti2 = tin[:, :3].clone().requires_grad_(True)
+    dcb.softsplat(ti2, flow[:, :2].contiguous(), None, "avg").backward(g.contiguous())
+    assert_close(ti.grad, ti2.grad, 1e-6, "strided grad")
+
+
+def test_needs_input_grad_gating(dcb):
+    tin = torch.randn(1, 3, 8, 8, device="cuda", requires_grad=True)
+    flow = torch.randn(1, 2, 8, 8, device="cuda")
+    metric = torch.randn(1, 1, 8, 8, device="cuda", requires_grad=True)
+    dcb.softsplat(tin, flow, metric, "soft").sum().backward()
+    assert tin.grad is not None and metric.grad is not None and flow.grad is None
+
+
+def test_autocast_casts_to_fp32(dcb):
+    tin = torch.randn(1, 3, 8, 8, device="cuda", dtype=torch.float16)
+    flow = torch.randn(1, 2, 8, 8, device="cuda", dtype=torch.float16)
+    with torch.autocast("cuda", dtype=torch.float16):
+        out = dcb.softsplat(tin, flow, None, "avg")
+    assert out.dtype == torch.float32          # custom_fwd(cast_inputs=float32), softsplat.py:279
+
+
+def test_asserts_like_reference(dcb):
+    tin = torch.randn(1, 3, 8, 8, device="cuda"); flow = torch.zeros(1, 2, 8, 8, device="cuda"); m = torch.zeros(1, 1, 8, 8, device="cuda")
+    for args in [(tin, flow, m, "sum"), (tin, flow, m, "avg"), (tin, flow, None, "soft"), (tin, flow, None, "linear"), (tin, flow, None, "max")]:
+        with pytest.raises(AssertionError):
+            dcb.softsplat(*args)
+    with pytest.raises(AssertionError):
+        dcb.softsplat(tin.cpu(), flow.cpu(), None, "sum")            # no CPU path, like the reference
+    with pytest.raises(AssertionError):
+        dcb.softsplat(tin, torch.zeros(1, 2, 8, 9, device="cuda"), None, "sum")
+
+
+def test_empty_and_ragged(dcb):
+    out = dcb.softsplat(torch.zeros(0, 3, 8, 8, device="cuda"), torch.zeros(0, 2, 8, 8, device="cuda"), None, "avg")
+    assert out.shape == (0, 3, 8, 8)
+    for shape in [(1, 1, 1, 1), (1, 3, 1, 37), (2, 2, 37, 1), (1, 5, 3, 257)]:
+        tin = torch.randn(*shape, device="cuda"); fl = torch.randn(shape[0], 2, shape[2], shape[3], device="cuda")
+        from oracle import oracle as orc
+        assert_close(dcb.softsplat(tin, fl, None, "avg"), orc.softsplat(tin.cpu(), fl.cpu(), None, "avg"), 1e-5, str(shape))
+
+
+def test_small_spatial_many_channels(dcb, orc):
+    """ControlNet pyramid shapes (extractors.py:245-248): channel-sliced backward path."""
+    for (n, c, r) in [(2, 160, 32), (2, 320, 16), (2, 640, 8)]:
+        tin, flow, metric, gout = make_inputs(c, n, c, r, r, flow_scale=0.7)
+        ref = oracle_run(orc, tin, flow, metric, gout, "soft")
+        got = cuda_run(dcb.softsplat, tin, flow, metric, gout, "soft")
+        for k in ("out", "gin", "gflow", "gmetric"):
+            assert_close(got[k], ref[k], 2e-5, f"pyramid {c}x{r} {k}")

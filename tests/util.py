@@ -1,0 +1,52 @@
+"""Shared helpers for the parity tests."""
+import numpy as np
+import torch
+
+
+def make_inputs(seed, n, c, h, w, flow_scale=2.0, dtype=torch.float32, smooth=False):
+    g = torch.Generator().manual_seed(seed)
+    tin = torch.randn(n, c, h, w, generator=g, dtype=torch.float32)
+    flow = torch.randn(n, 2, h, w, generator=g, dtype=torch.float32) * flow_scale
+    if smooth and h >= 8 and w >= 8:
+        k = 5
+        flow = torch.nn.functional.avg_pool2d(torch.nn.functional.pad(flow, (k // 2,) * 4, mode="replicate"), k, stride=1) * 2.0
+    metric = torch.randn(n, 1, h, w, generator=g, dtype=torch.float32) * 0.5
+    gout = torch.randn(n, c, h, w, generator=g, dtype=torch.float32)
+    return tin.to(dtype), flow.to(dtype), metric.to(dtype), gout.to(dtype)
+
+
+def assert_close(actual, ref, rel=1e-5, what=""):
+    """|actual - ref| <= rel * (|ref| + max|ref|): 'within rel relative', robust at zero crossings."""
+    a = actual.detach().double().cpu()
+    r = ref.detach().double().cpu()
+    assert a.shape == r.shape, (what, a.shape, r.shape)
+    scale = float(r.abs().max()) if r.numel() else 0.0
+    tol = rel * (r.abs() + max(scale, 1e-30))
+    err = (a - r).abs()
+    bad = ~(err <= tol)                      # also catches NaN
+    same_nan = torch.isnan(a) & torch.isnan(r)
+    bad &= ~same_nan
+    if bad.any():
+        i = int(torch.argmax(torch.where(bad, err / tol, torch.zeros_like(err))))
+        raise AssertionError(f"{what}: {int(bad.sum())}/{a.numel()} elements off; worst idx {i}: "
+                             f"got {a.flatten()[i].item():.9g} want {r.flatten()[i].item():.9g} (tol {tol.flatten()[i].item():.3g})")
+
+
+def oracle_run(orc, tin, flow, metric, gout, mode):
+    """Forward + all gradients through the CPU oracle (float32/float64 CPU tensors)."""
+    ti = tin.clone().requires_grad_(True)
+    fl = flow.clone().requires_grad_(True)
+    me = metric.clone().requires_grad_(True) if mode.split("-")[0] in ("linear", "soft") else None
+    out = orc.softsplat(ti, fl, me, mode)
+    out.backward(gout[:, : out.shape[1]])
+    return {"out": out.detach(), "gin": ti.grad, "gflow": fl.grad, "gmetric": None if me is None else me.grad}
+
+
+def cuda_run(softsplat, tin, flow, metric, gout, mode, device="cuda"):
+    ti = tin.to(device).requires_grad_(True)
+    fl = flow.to(device).requires_grad_(True)
+    me = metric.to(device).requires_grad_(True) if mode.split("-")[0] in ("linear", "soft") else None
+    out = softsplat(tenIn=ti, tenFlow=fl, tenMetric=me, strMode=mode)
+    out.backward(gout[:, : out.shape[1]].to(device))
+    torch.cuda.synchronize()
+    return {"out": out.detach(), "gin": ti.grad, "gflow": fl.grad, "gmetric": None if me is None else me.grad}

@@ -121,20 +121,26 @@ int64_t dcb_launch_count(void) { return (int64_t)g_launches.load(); }
 const char* dcb_build_info(void) {
     return "libdiffcodec_b200 " __DATE__ " nvcc " DCB_STR(__CUDACC_VER_MAJOR__) "." DCB_STR(__CUDACC_VER_MINOR__)
            " target sm_100a; kernels: k_scatter_planar k_scatter_vec4 k_normalize k_bwd_target k_bwd_source "
-           "k_backwarp_fwd k_backwarp_bwd k_mask_scatter k_mask_epilogue k_recipe_scatter k_recipe_epilogue "
+           "k_splat_pipe k_backwarp_fwd k_backwarp_bwd k_mask_scatter k_mask_epilogue k_recipe_scatter k_recipe_epilogue "
            "k_det_count k_det_scan k_det_fill k_det_reduce";
 }
 
-int64_t dcb_splat_workspace_bytes(int64_t N, int64_t C, int64_t H, int64_t W, int32_t dtype, int32_t mode, int32_t flags) {
+int64_t dcb_splat_fwd_workspace_bytes(int64_t N, int64_t C, int64_t H, int64_t W, int32_t dtype, int32_t mode, int32_t flags) {
     if (N < 0 || C < 0 || H < 0 || W < 0) return 0;
-    long long f = splat_fwd_workspace(N, C, H, W, dtype, mode);
-    long long b = splat_bwd_workspace(N, H, W, dtype, mode);
-    long long need = f > b ? f : b;
-    if (flags & DCB_FLAG_DETERMINISTIC) {
-        long long d = det_workspace(N, C, H, W, dtype, mode);
-        if (d > need) need = d;
-    }
-    return (int64_t)need;
+    if (flags & DCB_FLAG_DETERMINISTIC) return (int64_t)det_workspace(N, C, H, W, dtype, mode);
+    return (int64_t)splat_fwd_workspace(N, C, H, W, dtype, mode);
+}
+
+int64_t dcb_splat_bwd_workspace_bytes(int64_t N, int64_t C, int64_t H, int64_t W, int32_t dtype, int32_t mode, int32_t flags) {
+    (void)C; (void)flags;
+    if (N < 0 || H < 0 || W < 0) return 0;
+    return (int64_t)splat_bwd_workspace(N, H, W, dtype, mode);
+}
+
+int64_t dcb_splat_workspace_bytes(int64_t N, int64_t C, int64_t H, int64_t W, int32_t dtype, int32_t mode, int32_t flags) {
+    const int64_t f = dcb_splat_fwd_workspace_bytes(N, C, H, W, dtype, mode, flags);
+    const int64_t b = dcb_splat_bwd_workspace_bytes(N, C, H, W, dtype, mode, flags);
+    return f > b ? f : b;
 }
 
 int dcb_splat_fwd(const DcbTensor* in, const DcbTensor* flow, const DcbTensor* metric, const DcbTensor* out,

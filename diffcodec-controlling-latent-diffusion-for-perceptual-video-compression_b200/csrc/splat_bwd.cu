@@ -159,11 +159,12 @@ __global__ void __launch_bounds__(256) k_bwd_source(const BwdArgs a) {
 #pragma unroll
     for (int k = 0; k < 4; ++k) B[k] = b[k] ? (normalised ? fma_rn(ak[k], Ak[k], tk[k]) : Ak[k]) : (A)0;
 
+    const bool any = b[0] || b[1] || b[2] || b[3];   // a huge finite flow gives inf weights with no corner in range
     if (a.gmetric) {
         A s = (A)0;
 #pragma unroll
-        for (int k = 0; k < 4; ++k) s = fma_rn(w[k], B[k], s);
-        st<T, A>((T*)a.gmetric + p, ok ? s * gprime : (A)0);
+        for (int k = 0; k < 4; ++k) if (b[k]) s = fma_rn(w[k], B[k], s);
+        st<T, A>((T*)a.gmetric + p, any ? s * gprime : (A)0);
     }
     if (a.gflow) {
         // d w / d flow, softsplat.py:477-487
@@ -171,7 +172,7 @@ __global__ void __launch_bounds__(256) k_bwd_source(const BwdArgs a) {
         const A ex = sub_rn((A)x1, f.fx), dx = sub_rn(f.fx, (A)f.x0);
         A gx = (B[1] - B[0]) * ey + (B[3] - B[2]) * dy;
         A gy = (B[2] - B[0]) * ex + (B[3] - B[1]) * dx;
-        if (!ok) { gx = (A)0; gy = (A)0; }
+        if (!any) { gx = (A)0; gy = (A)0; }
         // gradFlow has the dtype of the flow tensor
         TF* gf = (TF*)a.gflow + (long long)n * 2 * a.HW + r;
         st<TF, A>(gf, gx * g);

@@ -18,6 +18,8 @@
 //     memset (DCB_FLAG_WS_CLEAN).
 #include "dcb_common.cuh"
 
+#include <stdlib.h>
+
 namespace dcb {
 
 constexpr int kThreads = 256;
@@ -200,18 +202,25 @@ __global__ void __launch_bounds__(kThreads) k_normalize(const FwdArgs a) {
 // ---------------------------------------------------------------------------------------------
 // host
 // ---------------------------------------------------------------------------------------------
-static bool use_vec4(int dtype, int mode, long long C) {
-    if (dtype == DCB_F64) return false;
-    const long long cacc = C + (mode == DCB_MODE_SUM ? 0 : 1);
-    if (mode == DCB_MODE_SUM && dtype == DCB_F32) return false;   // reds go straight into `out`
-    return cacc <= 4;
+// implemented in splat_pipe.cu
+long long pipe_workspace(long long N, long long H, long long W);
+int splat_pipe_impl(const DcbTensor* in, const DcbTensor* flow, const DcbTensor* metric, const DcbTensor* out,
+                    const DcbTensor* norm, const DcbTensor* mask, void* ws, int mode, int eps, bool ws_clean,
+                    cudaStream_t st);
+
+// C+1 <= 4 channels in fp32 / bf16: the persistent pipelined kernel (splat_pipe.cu)
+static bool use_pipe(int dtype, int mode, long long C) {
+    static const bool disabled = getenv("DCB_NO_PIPE") != nullptr;      // debugging / A-B measurements only
+    if (disabled || dtype == DCB_F64) return false;
+    return C + (mode == DCB_MODE_SUM ? 0 : 1) <= 4;
 }
 
 long long splat_fwd_workspace(long long N, long long C, long long H, long long W, int dtype, int mode) {
     const long long cacc = C + (mode == DCB_MODE_SUM ? 0 : 1);
     const long long esz = dtype == DCB_F64 ? 8 : 4;
-    if (mode == DCB_MODE_SUM && dtype != DCB_BF16) return 0;      // accumulate in `out`
-    if (use_vec4(dtype, mode, C)) return align_up(N * H * W * 16, 256);
+    if (use_pipe(dtype, mode, C)) return pipe_workspace(N, H, W);
+    if (mode == DCB_MODE_SUM && dtype != DCB_BF16) return 0;      // planar reds go straight into `out`
+    if (dtype != DCB_F64 && cacc <= 4) return align_up(N * H * W * 16, 256);   // (DCB_NO_PIPE) vec4 accumulators
     return align_up(N * cacc * H * W * esz, 256);
 }
 
@@ -287,7 +296,14 @@ int splat_fwd_impl(const DcbTensor* in, const DcbTensor* flow, const DcbTensor* 
     a.norm = norm ? norm->ptr : nullptr;
     if (a.total == 0 || a.C == 0) return DCB_OK;
 
-    const bool vec4 = use_vec4(in->dtype, mode, a.C);
+    if (use_pipe(in->dtype, mode, a.C)) {
+        const long long need = pipe_workspace(a.N, a.H, a.W);
+        if (!ws || ws_bytes < need || ((uintptr_t)ws & 255))
+            return set_error(DCB_E_WORKSPACE, "splat_fwd: workspace of %lld bytes (256 B aligned) required, got %lld", need, ws_bytes);
+        return splat_pipe_impl(in, flow, metric, out, norm, mask, ws, mode, eps, (flags & DCB_FLAG_WS_CLEAN) != 0, st);
+    }
+    // the one-kernel-per-stage vec4 path is kept for A-B measurements (DCB_NO_PIPE=1)
+    const bool vec4 = in->dtype != DCB_F64 && a.Cacc <= 4 && !(mode == DCB_MODE_SUM && in->dtype == DCB_F32);
     const bool acc_is_out = (mode == DCB_MODE_SUM && in->dtype != DCB_BF16 && !mask);
     long long acc_bytes;
     if (acc_is_out) {

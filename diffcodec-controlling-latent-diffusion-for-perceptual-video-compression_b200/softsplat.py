@@ -80,7 +80,7 @@ def _forward(tenIn, tenFlow, tenMetric, mask, mode: int, eps: int, det: bool, wa
     dt = _lib._DTYPES.get(tenIn.dtype)
     if dt is None:
         raise ValueError(f"softsplat: unsupported dtype {tenIn.dtype} (float32, bfloat16, float64)")
-    need = lib.dcb_splat_workspace_bytes(n, c, h, w, dt, mode, flags)
+    need = lib.dcb_splat_fwd_workspace_bytes(n, c, h, w, dt, mode, flags)
     ws, ws_ptr = None, None
     if need > 0:
         if det:
@@ -106,7 +106,7 @@ def _backward(gout, tenIn, tenFlow, tenMetric, out, norm, mask, mode: int, eps: 
     gin = torch.empty_like(tenIn, memory_format=torch.contiguous_format) if need[0] else None
     gflow = torch.empty((n, 2, h, w), dtype=tenFlow.dtype, device=dev) if need[1] else None
     gmetric = torch.empty((n, 1, h, w), dtype=tenIn.dtype, device=dev) if (need[2] and tenMetric is not None) else None
-    nbytes = lib.dcb_splat_workspace_bytes(n, c, h, w, _lib._DTYPES[tenIn.dtype], mode, 0)
+    nbytes = lib.dcb_splat_bwd_workspace_bytes(n, c, h, w, _lib._DTYPES[tenIn.dtype], mode, 0)
     ws = _lib.workspace(dev, nbytes, "scratch") if (mode != _lib.MODE_SUM and nbytes > 0) else None
     with torch.cuda.device(dev):
         rc = lib.dcb_splat_bwd(_lib.desc(gout), _lib.desc(tenIn), _lib.desc(tenFlow), _lib.desc(tenMetric),

@@ -89,6 +89,11 @@ int64_t dcb_launch_count(void);
  */
 int64_t dcb_splat_workspace_bytes(int64_t N, int64_t C, int64_t H, int64_t W, int32_t elem_dtype,
                                   int32_t mode, int32_t flags);
+/* the two halves of the above (it returns their maximum), for callers that keep separate buffers */
+int64_t dcb_splat_fwd_workspace_bytes(int64_t N, int64_t C, int64_t H, int64_t W, int32_t elem_dtype,
+                                      int32_t mode, int32_t flags);
+int64_t dcb_splat_bwd_workspace_bytes(int64_t N, int64_t C, int64_t H, int64_t W, int32_t elem_dtype,
+                                      int32_t mode, int32_t flags);
 
 /*
  * Forward splat. Replaces, in one call, the eager pre-ops, `new_zeros`, the `softsplat_out`

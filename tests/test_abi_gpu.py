@@ -25,7 +25,7 @@ def test_raw_call_and_error_codes(L):
     ws = torch.empty(need, dtype=torch.uint8, device="cuda")
     before = lib.dcb_launch_count()
     rc = lib.dcb_splat_fwd(L.desc(tin), L.desc(flow), None, L.desc(out), None, None, ws.data_ptr(), need, L.MODE_AVG, L.EPS_ADD, 0, st)
-    assert rc == 0 and lib.dcb_launch_count() - before == 2          # scatter + normalise (memset is not a kernel of ours)
+    assert rc == 0 and lib.dcb_launch_count() - before == 1          # ONE persistent kernel (the memset is not a kernel of ours)
     torch.cuda.synchronize()
     assert_close(out, tin / (1 + 1e-7), 1e-6, "raw avg")
     # workspace too small / missing
@@ -36,14 +36,14 @@ def test_raw_call_and_error_codes(L):
     assert lib.dcb_splat_fwd(None, L.desc(flow), None, L.desc(out), None, None, None, 0, L.MODE_SUM, 0, 0, st) == L.E_NULL
     # metric rules (softsplat.py:235-238)
     m = torch.zeros(1, 1, 16, 16, device="cuda")
-    assert lib.dcb_splat_fwd(L.desc(tin), L.desc(flow), L.desc(m), L.desc(out), None, None, None, 0, L.MODE_SUM, 0, 0, st) == L.E_MODE
+    assert lib.dcb_splat_fwd(L.desc(tin), L.desc(flow), L.desc(m), L.desc(out), None, None, ws.data_ptr(), need, L.MODE_SUM, 0, 0, st) == L.E_MODE
     assert lib.dcb_splat_fwd(L.desc(tin), L.desc(flow), None, L.desc(out), None, None, ws.data_ptr(), need, L.MODE_SOFT, 0, 0, st) == L.E_MODE
     assert lib.dcb_splat_fwd(L.desc(tin), L.desc(flow), None, L.desc(out), None, None, ws.data_ptr(), need, 9, 0, 0, st) == L.E_MODE
     # shape / dtype
     bad = torch.zeros(1, 2, 16, 17, device="cuda")
-    assert lib.dcb_splat_fwd(L.desc(tin), L.desc(bad), None, L.desc(out), None, None, None, 0, L.MODE_SUM, 0, 0, st) == L.E_SHAPE
-    assert lib.dcb_splat_fwd(L.desc(tin), L.desc(flow.double()), None, L.desc(out), None, None, None, 0, L.MODE_SUM, 0, 0, st) == L.E_DTYPE
-    assert lib.dcb_splat_fwd(L.desc(tin), L.desc(flow), None, L.desc(out.permute(0, 1, 3, 2)), None, None, None, 0, L.MODE_SUM, 0, 0, st) == L.E_SHAPE
+    assert lib.dcb_splat_fwd(L.desc(tin), L.desc(bad), None, L.desc(out), None, None, ws.data_ptr(), need, L.MODE_SUM, 0, 0, st) == L.E_SHAPE
+    assert lib.dcb_splat_fwd(L.desc(tin), L.desc(flow.double()), None, L.desc(out), None, None, ws.data_ptr(), need, L.MODE_SUM, 0, 0, st) == L.E_DTYPE
+    assert lib.dcb_splat_fwd(L.desc(tin), L.desc(flow), None, L.desc(out.permute(0, 1, 3, 2)), None, None, ws.data_ptr(), need, L.MODE_SUM, 0, 0, st) == L.E_SHAPE
     torch.cuda.synchronize()
 
 

@@ -15,13 +15,20 @@ def make_inputs(seed, n, c, h, w, flow_scale=2.0, dtype=torch.float32, smooth=Fa
     return tin.to(dtype), flow.to(dtype), metric.to(dtype), gout.to(dtype)
 
 
-def assert_close(actual, ref, rel=1e-5, what=""):
-    """|actual - ref| <= rel * (|ref| + max|ref|): 'within rel relative', robust at zero crossings."""
+def assert_close(actual, ref, rel=1e-5, what="", truth=None):
+    """|actual - ref| <= rel * (|ref| + max|ref|): 'within rel relative', robust at zero crossings.
+
+    `truth` (optional): the same quantity from the fp64 oracle. Where the fp32 reference itself
+    is ill-conditioned (a target pixel whose normaliser is a tiny weight amplifies rounding by
+    1/D in the gradients) the allowance grows by 4x the reference's own distance to the truth:
+    we must be as close to the exact answer as the reference is, not reproduce its rounding."""
     a = actual.detach().double().cpu()
     r = ref.detach().double().cpu()
     assert a.shape == r.shape, (what, a.shape, r.shape)
     scale = float(r.abs().max()) if r.numel() else 0.0
     tol = rel * (r.abs() + max(scale, 1e-30))
+    if truth is not None:
+        tol = tol + 4.0 * (r - truth.detach().double().cpu()).abs()
     err = (a - r).abs()
     bad = ~(err <= tol)                      # also catches NaN
     same_nan = torch.isnan(a) & torch.isnan(r)

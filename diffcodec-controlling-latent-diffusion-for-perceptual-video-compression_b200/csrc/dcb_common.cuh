@@ -85,6 +85,13 @@ template <> __device__ __forceinline__ float ld<float, __nv_bfloat16>(const __nv
 template <class T, class A> __device__ __forceinline__ void st(T* p, A v) { *p = (T)v; }
 template <> __device__ __forceinline__ void st<__nv_bfloat16, float>(__nv_bfloat16* p, float v) { *p = __float2bfloat16_rn(v); }
 
+// streaming variants (ld.global.cs / st.global.cs: evict-first in L1 and L2) for data touched once:
+// they keep the inputs / outputs from pushing the fp32 accumulators out of L2
+__device__ __forceinline__ float ld_stream(const float* p) { return __ldcs(p); }
+__device__ __forceinline__ float ld_stream(const __nv_bfloat16* p) { return __bfloat162float(__ldcs(p)); }
+__device__ __forceinline__ void st_stream(float* p, float v) { __stcs(p, v); }
+__device__ __forceinline__ void st_stream(__nv_bfloat16* p, float v) { __stcs(p, __float2bfloat16_rn(v)); }
+
 // rounded (non-contracted) arithmetic: the reference rounds every product before the atomic add
 __device__ __forceinline__ float mul_rn(float a, float b) { return __fmul_rn(a, b); }
 __device__ __forceinline__ double mul_rn(double a, double b) { return __dmul_rn(a, b); }

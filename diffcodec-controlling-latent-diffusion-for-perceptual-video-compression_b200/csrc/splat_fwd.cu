@@ -207,6 +207,7 @@ long long pipe_workspace(long long N, long long H, long long W);
 int splat_pipe_impl(const DcbTensor* in, const DcbTensor* flow, const DcbTensor* metric, const DcbTensor* out,
                     const DcbTensor* norm, const DcbTensor* mask, void* ws, int mode, int eps, bool ws_clean,
                     cudaStream_t st);
+bool pipe_supported(const DcbTensor* in, const DcbTensor* flow, const DcbTensor* metric);
 
 // C+1 <= 4 channels in fp32 / bf16: the persistent pipelined kernel (splat_pipe.cu)
 static bool use_pipe(int dtype, int mode, long long C) {
@@ -296,7 +297,7 @@ int splat_fwd_impl(const DcbTensor* in, const DcbTensor* flow, const DcbTensor* 
     a.norm = norm ? norm->ptr : nullptr;
     if (a.total == 0 || a.C == 0) return DCB_OK;
 
-    if (use_pipe(in->dtype, mode, a.C)) {
+    if (use_pipe(in->dtype, mode, a.C) && pipe_supported(in, flow, metric)) {
         const long long need = pipe_workspace(a.N, a.H, a.W);
         if (!ws || ws_bytes < need || ((uintptr_t)ws & 255))
             return set_error(DCB_E_WORKSPACE, "splat_fwd: workspace of %lld bytes (256 B aligned) required, got %lld", need, ws_bytes);

@@ -1,28 +1,28 @@
-// splat_pipe.cu -- the forward splat for C+1 <= 4 channels (frames, flows, SD latents) as ONE
-// persistent, software-pipelined kernel (sm_100a).
+// splat_pipe.cu -- the forward splat for C+1 <= 4 channels (frames, flows, SD latents) as a
+// software pipeline of plain, synchronisation-free kernels (sm_100a).
 //
 // Why (measured on B200, profiles/r01/): L2 reductions retire at most one 32-byte sector per
 // slice per clock (~360 G sectors/s), so the reference's 4 corner adds per pixel (~3 sectors/px on
-// realistic flow) cap a scatter at ~120 Gpx/s, and fp32 accumulators that round-trip through HBM
+// realistic flow) cap a scatter at ~120 Gpx/s; fp32 accumulators that round-trip through HBM
 // triple the DRAM traffic (only ~1.5 frames of 1080p accumulators stay L2-resident next to the
-// streaming inputs). This kernel
+// streaming inputs). Two persistent-kernel variants (CTA-granular with TMA-staged tiles, and
+// warp-granular with global tickets) were built and measured first: their in-kernel dependency
+// tracking (gpu-scope fences, acquire polling, bar.sync) cost more than it saved
+// (profiles/r01/NOTES.md). What survived:
 //
-//  1. stages each 256 x 8 source tile (flow, metric, channels) in SHARED MEMORY with TMA bulk
-//     copies (cp.async.bulk + mbarrier, two stages per CTA): the loads of the next tile are in
-//     flight while the current one is scattered, with no registers or issue slots spent on them;
-//  2. merges corner contributions in REGISTERS before they reach L2: a warp owns 32 columns x 8
-//     rows; the east column of lane i is handed to lane i+1 by shuffle when their footprints abut,
-//     the south row of a pixel is carried to the next row of the same thread when they abut
-//     vertically. Smooth flow -> ~1.2 `red.global.add.v4.f32` per pixel instead of 4; any flow
-//     stays correct (unmatched pieces are simply issued alone);
-//  3. keeps the fp32 accumulators L2-RESIDENT: frames go in order through a ring of `ring`
-//     frame-sized accumulators; scatter tiles S(f) and normalise chunks N(f) are work items drawn
-//     from one atomic ticket in the order  S0 | N0,S1 | N1,S2 | ...  so that every dependency
-//     (N(f) after all of S(f); S(f+ring) after all of N(f)) points at EARLIER tickets: waiting
-//     CTAs only ever wait for CTAs that are already running -> no co-residency requirement, no
-//     cooperative launch, no deadlock;
-//  4. is ONE launch for any number of frames: no memset (N re-zeroes what it read), no launch
-//     gaps; normalise of frame f overlaps scatter of frame f+1 on the same SMs.
+//  1. the KERNEL BOUNDARY is the only synchronisation: step k is one launch that normalises frame
+//     group k-1 and scatters frame group k, two independent jobs on two accumulator slots; the
+//     in-order stream gives "N(g) after all of S(g)" and "S(g+2) after all of N(g)" for free;
+//  2. the fp32 accumulators stay L2-RESIDENT: a ring of two slots, each one frame group (groups
+//     are sized to ~32 MB: one 1080p frame, or dozens of latents), is re-zeroed by the normalise
+//     pass that reads it, so there is no memset and no accumulator traffic to HBM;
+//  3. one 16-byte `red.global.add.v4.f32` per corner carries all C+1 channels, and corner pieces
+//     are merged IN REGISTERS before they reach L2: the east column of lane i is handed to lane
+//     i+1 by shuffle when their footprints abut, the south row of a pixel is carried to the next
+//     row of the same thread when they abut vertically (~1.2 reds per pixel instead of 4 on smooth
+//     flow; any flow stays correct -- an unmatched piece is simply issued alone);
+//  4. all loads of 8 rows are in flight before the first use; the pre-op (1 | m | exp(m), in*g)
+//     and the post-op (eps rule, divide, (1 - mask), cast, saved normaliser) never touch memory.
 //
 // Replaces controlnet/softsplat.py:240-270 (pre/post ops) + :281-345 (zero-init + softsplat_out).
 #include "dcb_common.cuh"
@@ -31,272 +31,148 @@
 
 namespace dcb {
 
-constexpr int kPipeThreads = 256;
-constexpr int kTW = 256, kTH = 8;           // source tile: one column per thread, 8 rows per warp
-constexpr int kPlaneElems = kTW * kTH;
-constexpr int kMaxPlanes = 6;               // flow_x, flow_y, up to 4 value planes (C values [+ metric])
-constexpr int kStageBytes = kMaxPlanes * kPlaneElems * 4;
-constexpr int kChunk = 2048;                // target pixels per normalise item
-constexpr int kCtrlWords = 64;              // [0] ticket, [1] exit count; then done_s[N], done_n[N]
+constexpr int kPipeThreads = 128;           // 4 independent warps per CTA
+constexpr int kWarpsPerCta = kPipeThreads / 32;
+constexpr int kRows = 4;                    // rows loaded at once by a warp
+constexpr int kPasses = 2;                  // consecutive row groups per strip (the vertical carry spans them)
+constexpr int kMinCtas = 8;                 // register budget: 64 per thread -> 32 warps per SM
+constexpr int kStripH = kRows * kPasses;    // a scatter item: 32 columns x 16 rows
+constexpr int kNPer = 8;                    // normalise: pixels per lane per batch
+constexpr int kNBatches = 2;
+constexpr int kChunk = 32 * kNPer * kNBatches;   // a normalise item: 512 target pixels
+constexpr long long kGroupBytes = 34ll << 20;    // accumulator bytes per ring slot (one 1080p frame = 31.6 MiB)
 
 struct PipeArgs {
     View in, flow, metric, mask;
-    float* acc;              // ring * HW * 4 floats, all-zero on entry and on exit
-    unsigned* ctrl;
+    float* acc;              // 2 slots x G frames x HW x 4 floats, all-zero on entry and on exit
     void* out;               // [N,C,H,W]
     void* norm;              // [N,1,H,W] fp32 or null
     int N, C, H, W;
     unsigned HW;
     int eps;
-    int ring;
-    int tiles_x, ts, tn;     // scatter tiles per row / per frame, normalise chunks per frame
-    unsigned total_items;
-    int bulk;                // inputs are row-contiguous and 16-byte aligned: TMA bulk staging
+    int G;                   // frames per group (per accumulator slot)
+    int tiles_x, ts, tn;     // scatter strips per row / per frame, normalise chunks per frame
+    int s_frame0, s_frames;  // this step scatters frames [s_frame0, s_frame0 + s_frames)
+    int n_frame0, n_frames;  // ... and normalises frames [n_frame0, n_frame0 + n_frames)
+    int dbg;                 // experiments only (DCB_DBG): 1 = no reds, 2 = no input loads, 4 = skip normalise items, 8 = skip scatter items
 };
 
 // ---------------------------------------------------------------------------------------------
-// PTX helpers: mbarrier, bulk async copy
+// scatter of one 32 x (kRows * kPasses) strip.  CA = accumulated channels (C, or C + 1 with the
+// appended weight channel) is a template parameter: no per-channel runtime tests in the hot loop.
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
-    unsigned ok = 0;
-    const unsigned addr = smem_u32(bar);
-    do {
-        asm volatile(
-            "{\n\t.reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-            "selp.u32 %0, 1, 0, p;\n\t}"
-            : "=r"(ok) : "r"(addr), "r"(parity) : "memory");
-    } while (!ok);
-}
-__device__ __forceinline__ unsigned long long policy_evict_first() {
-    unsigned long long p;
-    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
-    return p;
-}
-// global -> shared bulk copy (TMA, no tensor map): 16-byte aligned, size a multiple of 16
-__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned bytes, unsigned long long* bar, unsigned long long pol) {
-    asm volatile(
-        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
-        ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)), "l"(pol) : "memory");
-}
-
-__device__ __forceinline__ unsigned ld_acquire(const unsigned* p) {
-    unsigned v;
-    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-    return v;
-}
-__device__ __forceinline__ void wait_count(const unsigned* p, unsigned want) {
-    if (threadIdx.x == 0) {
-        unsigned ns = 32;
-        while (ld_acquire(p) < want) {
-            __nanosleep(ns);
-            if (ns < 512) ns *= 2;
-        }
-    }
-    __syncthreads();
-}
-__device__ __forceinline__ void signal_done(unsigned* p) {
-    // bar.sync orders every thread's reds / stores before thread 0's gpu-scope fence (the fence is
-    // cumulative), so one MEMBAR per CTA publishes the whole item -- the grid-sync idiom
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        __threadfence();
-        atomicAdd(p, 1u);
-    }
-}
-
-// ---------------------------------------------------------------------------------------------
-// work-item decoding: tickets in the order S0 .. S(L-1) | N0,S(L) | N1,S(L+1) | ... | N tail
-// ---------------------------------------------------------------------------------------------
-struct Item { bool scatter; int frame, idx; };
-
-__device__ __forceinline__ Item decode(const PipeArgs& a, unsigned t) {
-    Item it;
-    const int L = a.ring - 1;                                            // normalise lags scatter by L frames
-    const unsigned n1 = (unsigned)min(a.N, L) * a.ts;                    // S-only groups
-    const unsigned per = (unsigned)(a.ts + a.tn);
-    const unsigned n2 = (unsigned)max(a.N - L, 0) * per;                 // groups holding N(q) and S(q+L)
-    if (t < n1) { it.scatter = true; it.frame = t / a.ts; it.idx = t - it.frame * a.ts; }
-    else if (t - n1 < n2) {
-        t -= n1;
-        // With L > 0 the normalise items go first, which keeps every dependency one stage away;
-        // with L == 0 the scatter items must precede the normalise items that wait for them.
-        const unsigned q = t / per, r = t - q * per;
-        const unsigned first = L > 0 ? (unsigned)a.tn : (unsigned)a.ts;
-        const bool in_first = r < first;
-        it.scatter = (L > 0) ? !in_first : in_first;
-        it.idx = (int)(in_first ? r : r - first);
-        it.frame = it.scatter ? (int)q + L : (int)q;
-    } else {
-        t -= n1 + n2;
-        const unsigned i = t / a.tn;
-        it.scatter = false; it.frame = max(a.N - L, 0) + (int)i; it.idx = (int)(t - i * a.tn);
-    }
-    return it;
-}
-
-// staged planes: 0 flow_x, 1 flow_y, 2.. values, then metric
-template <int MODE> __device__ __forceinline__ int plane_count(int C) { return 2 + C + (MODE >= DCB_MODE_LINEAR ? 1 : 0); }
-
-// ---------------------------------------------------------------------------------------------
-// staging
-// ---------------------------------------------------------------------------------------------
-template <class T, class TF, int MODE>
-__device__ __forceinline__ void stage_issue_bulk(const PipeArgs& a, int frame, int tile, unsigned char* stage,
-                                                 unsigned long long* bar, int lane, unsigned long long pol) {
-    const int tx = tile % a.tiles_x, ty = tile / a.tiles_x;
-    const int x0 = tx * kTW, y0 = ty * kTH;
-    const int cols = min(kTW, a.W - x0), rows = min(kTH, a.H - y0);
-    const int planes = plane_count<MODE>(a.C);
-    const unsigned bytes_v = (unsigned)cols * sizeof(T), bytes_f = (unsigned)cols * sizeof(TF);
-    if (lane == 0) mbar_expect_tx(bar, (unsigned)rows * (2u * bytes_f + (unsigned)(planes - 2) * bytes_v));
-    __syncwarp();
-    const int copies = planes * rows;
-    for (int i = lane; i < copies; i += 32) {
-        const int p = i / rows, r = i - p * rows;
-        const long long y = y0 + r;
-        unsigned char* dst = stage + (size_t)p * (kPlaneElems * 4);
-        if (p < 2) {
-            const TF* src = (const TF*)a.flow.p + frame * a.flow.sN + p * a.flow.sC + y * a.flow.sH + x0;
-            bulk_g2s(dst + (size_t)r * kTW * sizeof(TF), src, bytes_f, bar, pol);
-        } else if (p < 2 + a.C) {
-            const T* src = (const T*)a.in.p + frame * a.in.sN + (p - 2) * a.in.sC + y * a.in.sH + x0;
-            bulk_g2s(dst + (size_t)r * kTW * sizeof(T), src, bytes_v, bar, pol);
-        } else {
-            const T* src = (const T*)a.metric.p + frame * a.metric.sN + y * a.metric.sH + x0;
-            bulk_g2s(dst + (size_t)r * kTW * sizeof(T), src, bytes_v, bar, pol);
-        }
-    }
-}
-
-// any strides / alignment: all threads copy the tile with ordinary loads (synchronous)
-template <class T, class TF, int MODE>
-__device__ __forceinline__ void stage_generic(const PipeArgs& a, int frame, int tile, unsigned char* stage) {
-    const int tx = tile % a.tiles_x, ty = tile / a.tiles_x;
-    const int x = tx * kTW + threadIdx.x, y0 = ty * kTH;
-    const int rows = min(kTH, a.H - y0);
-    if (x < a.W) {
-        for (int r = 0; r < rows; ++r) {
-            const long long y = y0 + r;
-            const int e = r * kTW + threadIdx.x;
-            const TF* fp = (const TF*)a.flow.p + frame * a.flow.sN + y * a.flow.sH + x * a.flow.sW;
-            ((TF*)stage)[e] = fp[0];
-            ((TF*)(stage + kPlaneElems * 4))[e] = fp[a.flow.sC];
-            const T* ip = (const T*)a.in.p + frame * a.in.sN + y * a.in.sH + x * a.in.sW;
-            for (int c = 0; c < a.C; ++c) ((T*)(stage + (size_t)(2 + c) * kPlaneElems * 4))[e] = ip[c * a.in.sC];
-            if (MODE >= DCB_MODE_LINEAR)
-                ((T*)(stage + (size_t)(2 + a.C) * kPlaneElems * 4))[e] =
-                    ((const T*)a.metric.p)[frame * a.metric.sN + y * a.metric.sH + x * a.metric.sW];
-        }
-    }
-    __syncthreads();
-}
-
-// ---------------------------------------------------------------------------------------------
-// scatter of one staged tile
-// ---------------------------------------------------------------------------------------------
+// predicated vector reduction: no branch, the address is formed unconditionally but only used if p
 __device__ __forceinline__ void red4_if(bool p, float* acc, int off, const float (&v)[4]) {
-    if (p) red_add_v4(acc + (long long)off * 4, v[0], v[1], v[2], v[3]);
+    float* addr = acc + (long long)off * 4;
+    asm volatile(
+        "{\n\t.reg .pred q;\n\t"
+        "setp.ne.s32 q, %0, 0;\n\t"
+        "@q red.global.add.v4.f32 [%1], {%2, %3, %4, %5};\n\t}"
+        ::"r"((int)p), "l"(addr), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]) : "memory");
 }
 
-template <class T, class TF, int MODE>
-__device__ __forceinline__ void scatter_tile(const PipeArgs& a, int tile, const unsigned char* stage, float* acc) {
-    const int lane = threadIdx.x & 31;
+template <class T, class TF, int MODE, int CA>
+__device__ __forceinline__ void scatter_strip(const PipeArgs& a, int frame, int tile, float* acc, int lane) {
+    constexpr int C = CA - (MODE != DCB_MODE_SUM ? 1 : 0);
     const int tx = tile % a.tiles_x, ty = tile / a.tiles_x;
-    const int x = tx * kTW + threadIdx.x, yb = ty * kTH;
-    const int W = a.W, H = a.H, C = a.C;
-    const int rows = min(kTH, H - yb);
+    const int x = tx * 32 + lane;
+    const int W = a.W, H = a.H;
     const bool xin = x < W;
     const unsigned full = 0xffffffffu;
-    const int kDead = -7;
+    constexpr int kDead = -7;
     const int pitch = W + 2;                       // key = (y0 + 1) * pitch + (x0 + 1) identifies a footprint
-    const int CA = C + (MODE != DCB_MODE_SUM ? 1 : 0);
-
-    const TF* sfx = (const TF*)stage + threadIdx.x;
-    const TF* sfy = (const TF*)(stage + kPlaneElems * 4) + threadIdx.x;
-    const T* sv = (const T*)(stage + 2 * kPlaneElems * 4) + threadIdx.x;
-    const T* sm = (const T*)(stage + (size_t)(2 + C) * kPlaneElems * 4) + threadIdx.x;
-    constexpr int kPlaneT = kPlaneElems * 4 / sizeof(T);   // plane pitch in elements of T
 
     float pend[4] = {0.f, 0.f, 0.f, 0.f};
     int pend_key = kDead, pend_off = 0;
     bool pend_ok = false;
 
-#pragma unroll
-    for (int r = 0; r < kTH; ++r) {
-        const bool in_img = xin && r < rows;
-        float flx = 0.f, fly = 0.f;
-        if (in_img) { flx = ld<float>(sfx + r * kTW); fly = ld<float>(sfy + r * kTW); }
-        const float fx = add_rn((float)x, flx), fy = add_rn((float)(yb + r), fly);   // softsplat.py:298-299
-        const float x0f = floorf(fx), y0f = floorf(fy);
-        const int x0 = __float2int_rz(x0f), y0 = __float2int_rz(y0f);
-        // finite landing point (softsplat.py:301-302) with at least one corner inside the frame
-        const bool alive = in_img && fabsf(fx) < 3.0e38f && fabsf(fy) < 3.0e38f &&
-                           ((unsigned)x0 + 1u) <= (unsigned)W && ((unsigned)y0 + 1u) <= (unsigned)H;
-        const float ex = sub_rn(add_rn(x0f, 1.f), fx), ey = sub_rn(add_rn(y0f, 1.f), fy);  // softsplat.py:315-318
-        const float dx = sub_rn(fx, x0f), dy = sub_rn(fy, y0f);
-        const float wnw = mul_rn(ex, ey), wne = mul_rn(dx, ey), wsw = mul_rn(ex, dy), wse = mul_rn(dx, dy);
+    const int xs = xin ? x : 0;
+    const TF* fbase = (const TF*)a.flow.p + frame * a.flow.sN;
+    const T* ibase = (const T*)a.in.p + frame * a.in.sN;
+    const T* mbase = (MODE >= DCB_MODE_LINEAR) ? (const T*)a.metric.p + frame * a.metric.sN : nullptr;
+    // element offsets fit 32 bits (checked by the host)
+    const int f_sH = (int)a.flow.sH, f_sC = (int)a.flow.sC, i_sH = (int)a.in.sH, i_sC = (int)a.in.sC, m_sH = (int)a.metric.sH;
+    const int f_x = xs * (int)a.flow.sW, i_x = xs * (int)a.in.sW, m_x = xs * (int)a.metric.sW;
 
-        float v[4] = {0.f, 0.f, 0.f, 0.f};
-        if (in_img) {
+#pragma unroll 1
+    for (int pass = 0; pass < kPasses; ++pass) {
+        const int yb = ty * kStripH + pass * kRows;
+        if (yb >= H) break;                                              // warp-uniform
+        const int rows = min(kRows, H - yb);
+        // ---- every load of the pass in flight before the first use ----
+        float flx[kRows], fly[kRows], mv[kRows], iv[kRows][C > 0 ? C : 1];
+#pragma unroll
+        for (int r = 0; r < kRows; ++r) {
+            const bool on = xin && r < rows && !(a.dbg & 2);
+            const int y = yb + r;
+            flx[r] = fly[r] = 0.f; mv[r] = 0.f;
+#pragma unroll
+            for (int c = 0; c < C; ++c) iv[r][c] = 0.f;
+            if (on) {
+                const TF* fp = fbase + (y * f_sH + f_x);
+                flx[r] = ld_stream(fp); fly[r] = ld_stream(fp + f_sC);
+                if (MODE >= DCB_MODE_LINEAR) mv[r] = ld_stream(mbase + (y * m_sH + m_x));
+                const T* ip = ibase + (y * i_sH + i_x);
+#pragma unroll
+                for (int c = 0; c < C; ++c) iv[r][c] = ld_stream(ip + c * i_sC);
+            }
+        }
+#pragma unroll
+        for (int r = 0; r < kRows; ++r) {
+            const bool in_img = xin && r < rows && !(a.dbg & 1);
+            const float fx = add_rn((float)x, flx[r]), fy = add_rn((float)(yb + r), fly[r]);   // softsplat.py:298-299
+            const float x0f = floorf(fx), y0f = floorf(fy);
+            const int x0 = __float2int_rz(x0f), y0 = __float2int_rz(y0f);
+            // finite landing point (softsplat.py:301-302) with at least one corner inside the frame
+            const bool alive = in_img && fabsf(fx) < 3.0e38f && fabsf(fy) < 3.0e38f &&
+                               ((unsigned)x0 + 1u) <= (unsigned)W && ((unsigned)y0 + 1u) <= (unsigned)H;
+            const float ex = sub_rn(add_rn(x0f, 1.f), fx), ey = sub_rn(add_rn(y0f, 1.f), fy);  // softsplat.py:315-318
+            const float dx = sub_rn(fx, x0f), dy = sub_rn(fy, y0f);
+            const float wnw = mul_rn(ex, ey), wne = mul_rn(dx, ey), wsw = mul_rn(ex, dy), wse = mul_rn(dx, dy);
+
             float g = 1.f;
-            if (MODE == DCB_MODE_LINEAR) g = ld<float>(sm + r * kTW);
-            if (MODE == DCB_MODE_SOFT) g = expf(ld<float>(sm + r * kTW));
+            if (MODE == DCB_MODE_LINEAR) g = mv[r];
+            if (MODE == DCB_MODE_SOFT) g = expf(mv[r]);
+            float nw[4] = {0.f, 0.f, 0.f, 0.f}, ne[4] = {0.f, 0.f, 0.f, 0.f}, sw[4] = {0.f, 0.f, 0.f, 0.f}, se[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-            for (int c = 0; c < 4; ++c) {
-                if (c < C) {
-                    const float t = ld<float>(sv + c * kPlaneT + r * kTW);
-                    v[c] = (MODE >= DCB_MODE_LINEAR) ? mul_rn(t, g) : t;                  // softsplat.py:244,247
-                } else if (c == C && MODE != DCB_MODE_SUM) {
-                    v[c] = g;                                                             // appended channel
-                }
+            for (int c = 0; c < CA; ++c) {
+                float v;
+                if (c < C) v = (MODE >= DCB_MODE_LINEAR) ? mul_rn(iv[r][c < C ? c : 0], g) : iv[r][c < C ? c : 0];   // softsplat.py:244,247
+                else v = g;                                                                     // appended channel
+                nw[c] = mul_rn(v, wnw); ne[c] = mul_rn(v, wne);
+                sw[c] = mul_rn(v, wsw); se[c] = mul_rn(v, wse);
             }
-        }
-        float nw[4], ne[4], sw[4], se[4];
-#pragma unroll
-        for (int c = 0; c < 4; ++c) {
-            nw[c] = mul_rn(v[c], wnw); ne[c] = mul_rn(v[c], wne);
-            sw[c] = mul_rn(v[c], wsw); se[c] = mul_rn(v[c], wse);
-        }
-        const int key = alive ? (y0 + 1) * pitch + (x0 + 1) : kDead;
-        const int off = y0 * W + x0;
-        const bool vx0 = x0 >= 0, vx1 = x0 < W - 1, vy0 = y0 >= 0, vy1 = y0 < H - 1;
+            const int key = alive ? (y0 + 1) * pitch + (x0 + 1) : kDead;
+            const int off = y0 * W + x0;
+            const bool vx0 = x0 >= 0, vx1 = x0 < W - 1, vy0 = y0 >= 0, vy1 = y0 < H - 1;
 
-        // ---- horizontal hand-over: my east column goes to lane + 1 if our footprints abut ----
-        const int lkey = __shfl_up_sync(full, key, 1);
-        const bool take = lane > 0 && alive && lkey != kDead && lkey + 1 == key;
-        const bool given = (__shfl_down_sync(full, (int)take, 1) != 0) && lane < 31;
+            // ---- horizontal hand-over: my east column goes to lane + 1 if our footprints abut ----
+            // (the kernel is bound by L2 reduction sectors, not by issue slots: 12 shuffles per pixel
+            //  buy ~20 % fewer sectors on rough flow and ~45 % on smooth flow -- profiles/r01/NOTES.md)
+            const int lkey = __shfl_up_sync(full, key, 1);
+            const bool take = lane > 0 && alive && lkey != kDead && lkey + 1 == key;
+            const bool given = (__shfl_down_sync(full, (int)take, 1) != 0) && lane < 31;
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
-            if (c < CA) {
+            for (int c = 0; c < CA; ++c) {
                 const float en = __shfl_up_sync(full, ne[c], 1), es = __shfl_up_sync(full, se[c], 1);
-                if (take) { nw[c] = add_rn(nw[c], en); sw[c] = add_rn(sw[c], es); }
+                nw[c] = take ? add_rn(nw[c], en) : nw[c];
+                sw[c] = take ? add_rn(sw[c], es) : sw[c];
             }
-        }
-        const bool east = alive && !given && vx1;
-        red4_if(east && vy0, acc, off + 1, ne);
-        red4_if(east && vy1, acc, off + W + 1, se);
-        // ---- vertical carry: the previous row's south piece joins my north piece if they abut ----
-        const bool join = pend_key == key && alive;            // kDead never equals a live key
-        if (join) {
+            const bool east = alive && !given && vx1;
+            red4_if(east && vy0, acc, off + 1, ne);
+            red4_if(east && vy1, acc, off + W + 1, se);
+            // ---- vertical carry: the previous row's south piece joins my north piece if they abut ----
+            const bool join = pend_key == key && alive;            // kDead never equals a live key
 #pragma unroll
-            for (int c = 0; c < 4; ++c) nw[c] = add_rn(nw[c], pend[c]);
-        }
-        red4_if(pend_ok && !join, acc, pend_off, pend);
-        red4_if(alive && vx0 && vy0, acc, off, nw);
+            for (int c = 0; c < CA; ++c) nw[c] = join ? add_rn(nw[c], pend[c]) : nw[c];
+            red4_if(pend_ok && !join, acc, pend_off, pend);
+            red4_if(alive && vx0 && vy0, acc, off, nw);
 #pragma unroll
-        for (int c = 0; c < 4; ++c) pend[c] = sw[c];
-        pend_key = alive ? key + pitch : kDead;
-        pend_off = off + W;
-        pend_ok = alive && vx0 && vy1;
+            for (int c = 0; c < CA; ++c) pend[c] = sw[c];
+            pend_key = alive ? key + pitch : kDead;
+            pend_off = off + W;
+            pend_ok = alive && vx0 && vy1;
+        }
     }
     red4_if(pend_ok, acc, pend_off, pend);
 }
@@ -304,175 +180,140 @@ __device__ __forceinline__ void scatter_tile(const PipeArgs& a, int tile, const 
 // ---------------------------------------------------------------------------------------------
 // normalise chunk: eps rule, divide, (1 - mask), cast, save normaliser, re-zero
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ float eps_rule(float d, int eps) {
-    if (eps == DCB_EPS_ADD) return add_rn(d, 0.0000001f);                // softsplat.py:257,260
-    if (eps == DCB_EPS_ZERO) return d == 0.f ? 1.f : d;                  // :263
-    return d < 0.0000001f ? 0.0000001f : d;                              // :266
-}
-
-template <class T, int MODE>
-__device__ __forceinline__ void normalize_chunk(const PipeArgs& a, int frame, int chunk, float* acc) {
-    const unsigned base = (unsigned)chunk * kChunk + threadIdx.x;
-    T* out = (T*)a.out + (long long)frame * a.C * a.HW;
-    constexpr int kPer = kChunk / kPipeThreads;                          // 8 pixels per thread
-    float4 s[kPer];
+template <class T, int MODE, int CA>
+__device__ __forceinline__ void normalize_chunk(const PipeArgs& a, int frame, int chunk, float* acc, int lane) {
+    constexpr int C = CA - (MODE != DCB_MODE_SUM ? 1 : 0);
+    T* out = (T*)a.out + (long long)frame * C * a.HW;
+    const bool plain = a.norm == nullptr && a.mask.p == nullptr;        // warp-uniform
+#pragma unroll 1
+    for (int b = 0; b < kNBatches; ++b) {
+        const unsigned base = (unsigned)chunk * kChunk + b * (32 * kNPer) + lane;
+        if (base - lane >= a.HW) break;
+        float4 s[kNPer];
 #pragma unroll
-    for (int i = 0; i < kPer; ++i) {                                     // all L2 reads in flight first
-        const unsigned r = base + i * kPipeThreads;
-        s[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (r < a.HW) s[i] = __ldcg((const float4*)acc + r);             // written by other SMs' reds: L2 is the point of coherence
-    }
-#pragma unroll
-    for (int i = 0; i < kPer; ++i) {
-        const unsigned r = base + i * kPipeThreads;
-        if (r >= a.HW) break;
-        __stcg((float4*)acc + r, make_float4(0.f, 0.f, 0.f, 0.f));       // accumulators leave the kernel all-zero
-        const float sv[4] = {s[i].x, s[i].y, s[i].z, s[i].w};
-        float d = 1.f;
-        if (MODE != DCB_MODE_SUM) {
-            d = eps_rule(a.C == 3 ? sv[3] : (a.C == 2 ? sv[2] : (a.C == 1 ? sv[1] : sv[0])), a.eps);
-            if (a.norm) __stcs((float*)a.norm + (long long)frame * a.HW + r, d);
-        }
-        float keep = 1.f;
-        if (a.mask.p) {
-            const int y = (int)(r / (unsigned)a.W), x = (int)(r - (unsigned)y * (unsigned)a.W);
-            const T* mp = (const T*)a.mask.p + frame * a.mask.sN + (long long)y * a.mask.sH + (long long)x * a.mask.sW;
-            keep = sub_rn(1.f, ld<float>(mp));                           // control_utils.py:69-70
+        for (int i = 0; i < kNPer; ++i) {                                // all L2 reads in flight first
+            const unsigned r = base + i * 32;
+            s[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (r < a.HW) s[i] = __ldcg((const float4*)acc + r);         // written by other SMs' reds: L2 is the point of coherence
         }
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
-            if (c < a.C) {
-                float o = (MODE != DCB_MODE_SUM) ? sv[c] / d : sv[c];    // true division, as the reference (softsplat.py:270)
-                if (a.mask.p) o = mul_rn(o, keep);
-                st<T, float>(out + (long long)c * a.HW + r, o);
+        for (int i = 0; i < kNPer; ++i) {
+            const unsigned r = base + i * 32;
+            if (r < a.HW) {
+                __stcg((float4*)acc + r, make_float4(0.f, 0.f, 0.f, 0.f));   // accumulators leave the kernel all-zero
+                const float sv[4] = {s[i].x, s[i].y, s[i].z, s[i].w};
+                float scale = 1.f;
+                if (MODE != DCB_MODE_SUM) {
+                    float d = sv[C];
+                    // softsplat.py:256-266
+                    if (a.eps == DCB_EPS_ADD) d = add_rn(d, 0.0000001f);
+                    else if (a.eps == DCB_EPS_ZERO) d = (d == 0.f) ? 1.f : d;
+                    else d = (d < 0.0000001f) ? 0.0000001f : d;
+                    // one correctly-rounded reciprocal and C multiplies instead of C IEEE divisions
+                    // (<= 1 ulp from softsplat.py:270; the deterministic path divides exactly)
+                    scale = __frcp_rn(d);
+                    if (!plain && a.norm) __stcs((float*)a.norm + (long long)frame * a.HW + r, d);
+                }
+                if (!plain && a.mask.p) {
+                    const int y = (int)(r / (unsigned)a.W), x = (int)(r - (unsigned)y * (unsigned)a.W);
+                    const T* mp = (const T*)a.mask.p + frame * a.mask.sN + (long long)y * a.mask.sH + (long long)x * a.mask.sW;
+                    scale = mul_rn(scale, sub_rn(1.f, ld<float>(mp)));   // control_utils.py:69-70
+                }
+                T* o = out + r;
+#pragma unroll
+                for (int c = 0; c < C; ++c) {
+                    const float val = (MODE != DCB_MODE_SUM) ? mul_rn(sv[c], scale) : ((!plain && a.mask.p) ? mul_rn(sv[c], scale) : sv[c]);
+                    st_stream(o + (size_t)c * a.HW, val);
+                }
             }
         }
     }
 }
 
 // ---------------------------------------------------------------------------------------------
-// the kernel
+// the step kernel: warp w of CTA b owns item 4b + w; normalise items first, then scatter items
 // ---------------------------------------------------------------------------------------------
-template <class T, class TF, int MODE>
-__global__ void __launch_bounds__(kPipeThreads, 2) k_splat_pipe(const __grid_constant__ PipeArgs a) {
-    extern __shared__ __align__(128) unsigned char smem[];               // 2 stages of kStageBytes
-    __shared__ __align__(8) unsigned long long s_bar[2];
-    __shared__ unsigned s_tk[2];
-    __shared__ unsigned s_last;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    unsigned* done_s = a.ctrl + kCtrlWords;
-    unsigned* done_n = done_s + a.N;
-    unsigned long long pol = 0;
-
-    if (threadIdx.x == 0) {
-        mbar_init(&s_bar[0], 1);
-        mbar_init(&s_bar[1], 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    __syncthreads();
-
-    // warp 0 owns the ticket counter and the TMA issue; the ticket of the NEXT item is drawn (and
-    // its tile put in flight) before the current item is processed
-    auto fetch = [&](int slot) {
-        unsigned t = 0;
-        if (lane == 0) { t = atomicAdd(a.ctrl, 1u); s_tk[slot] = t; }
-        t = __shfl_sync(0xffffffffu, t, 0);
-        if (a.bulk && t < a.total_items) {
-            const Item it = decode(a, t);
-            if (it.scatter) stage_issue_bulk<T, TF, MODE>(a, it.frame, it.idx, smem + (size_t)slot * kStageBytes, &s_bar[slot], lane, pol);
-        }
-    };
-    if (warp == 0) { pol = policy_evict_first(); fetch(0); }
-    __syncthreads();
-
-    unsigned parity[2] = {0u, 0u};
-    for (unsigned n = 0;; ++n) {
-        const int slot = n & 1;
-        const unsigned t = s_tk[slot];
-        if (t >= a.total_items) break;
-        if (warp == 0) fetch(slot ^ 1);                                  // stage slot^1 was released by the barrier that ended item n-1
-        const Item it = decode(a, t);
-        float* acc = a.acc + (size_t)(it.frame % a.ring) * a.HW * 4;
-        if (it.scatter) {
-            unsigned char* stage = smem + (size_t)slot * kStageBytes;
-            if (a.bulk) { mbar_wait(&s_bar[slot], parity[slot]); parity[slot] ^= 1u; }
-            else stage_generic<T, TF, MODE>(a, it.frame, it.idx, stage);
-            if (it.frame >= a.ring) wait_count(done_n + (it.frame - a.ring), (unsigned)a.tn);   // ring slot is free again
-            scatter_tile<T, TF, MODE>(a, it.idx, stage, acc);
-            signal_done(done_s + it.frame);
-        } else {
-            wait_count(done_s + it.frame, (unsigned)a.ts);               // every source of the frame has landed
-            normalize_chunk<T, MODE>(a, it.frame, it.idx, acc);
-            signal_done(done_n + it.frame);
-        }
-    }
-    // The last CTA to leave puts the control block back to all-zero, so the whole workspace
-    // (accumulators AND control words) is clean again when the kernel ends.
-    __syncthreads();
-    if (threadIdx.x == 0) s_last = (atomicAdd(a.ctrl + 1, 1u) == gridDim.x - 1) ? 1u : 0u;
-    __syncthreads();
-    if (s_last) {
-        __threadfence();
-        for (int i = threadIdx.x; i < kCtrlWords + 2 * a.N; i += kPipeThreads) a.ctrl[i] = 0u;
+template <class T, class TF, int MODE, int CA>
+__global__ void __launch_bounds__(kPipeThreads, kMinCtas) k_splat_step(const __grid_constant__ PipeArgs a) {
+    const int lane = threadIdx.x & 31;
+    const unsigned item = blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5);
+    const unsigned n_items = (unsigned)a.n_frames * a.tn;
+    const size_t slot_floats = (size_t)a.G * a.HW * 4;
+    if (item < n_items) {
+        if (a.dbg & 4) return;
+        const int f = a.n_frame0 + item / a.tn, chunk = item % a.tn;
+        float* acc = a.acc + (size_t)((f / a.G) & 1) * slot_floats + (size_t)(f % a.G) * a.HW * 4;
+        normalize_chunk<T, MODE, CA>(a, f, chunk, acc, lane);
+    } else {
+        const unsigned s = item - n_items;
+        if (s >= (unsigned)a.s_frames * a.ts || (a.dbg & 8)) return;
+        const int f = a.s_frame0 + s / a.ts, strip = s % a.ts;
+        float* acc = a.acc + (size_t)((f / a.G) & 1) * slot_floats + (size_t)(f % a.G) * a.HW * 4;
+        scatter_strip<T, TF, MODE, CA>(a, f, strip, acc, lane);
     }
 }
 
 // ---------------------------------------------------------------------------------------------
 // host
 // ---------------------------------------------------------------------------------------------
-constexpr int kMaxRing = 3;
-
-static int pipe_ring(long long N) {
-    static int cap = 0;
-    if (cap == 0) {                                   // DCB_PIPE_RING=1|2|3: experiments only
-        const char* e = getenv("DCB_PIPE_RING");
-        cap = e ? atoi(e) : 2;
-        if (cap < 1 || cap > kMaxRing) cap = 2;
-    }
-    return N >= cap ? cap : (int)(N < 1 ? 1 : N);
+static long long group_frames(long long N, long long H, long long W) {
+    long long g = kGroupBytes / (H * W * 16 > 0 ? H * W * 16 : 1);
+    if (g < 1) g = 1;
+    return g > N ? (N < 1 ? 1 : N) : g;
 }
 
-// sized for the largest ring so that the workspace query does not depend on the environment
 long long pipe_acc_bytes(long long N, long long H, long long W) {
-    const long long slots = N >= kMaxRing ? kMaxRing : (N < 1 ? 1 : N);
-    return align_up(slots * H * W * 16, 256);
+    const long long G = group_frames(N, H, W);
+    const long long slots = N > G ? 2 : 1;
+    return align_up(slots * G * H * W * 16, 256);
 }
 
-long long pipe_workspace(long long N, long long H, long long W) {
-    return pipe_acc_bytes(N, H, W) + align_up((kCtrlWords + 2 * N) * 4, 256);
-}
+long long pipe_workspace(long long N, long long H, long long W) { return pipe_acc_bytes(N, H, W); }
 
-static bool aligned16(const void* p) { return ((uintptr_t)p & 15) == 0; }
-
-template <class T> static bool bulk_ok(const DcbTensor* t, long long W) {
-    if (!t) return true;
-    const long long es = sizeof(T);
-    return t->stride[3] == 1 && aligned16(t->ptr) && (t->stride[0] * es) % 16 == 0 && (t->stride[1] * es) % 16 == 0 &&
-           (t->stride[2] * es) % 16 == 0 && (W * es) % 16 == 0;
-}
-
-template <class T, class TF, int MODE> static int launch_pipe_mode(const PipeArgs& a, cudaStream_t st) {
-    static int grid_cap = 0;
-    const size_t smem = 2 * (size_t)kStageBytes;
-    if (grid_cap == 0) {
-        DCB_CHECK_CUDA(cudaFuncSetAttribute(k_splat_pipe<T, TF, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        int per_sm = 0;
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_splat_pipe<T, TF, MODE>, kPipeThreads, smem) != cudaSuccess || per_sm < 1) per_sm = 1;
-        grid_cap = device_sm_count() * per_sm;
+template <class T, class TF, int MODE, int CA> static int launch_steps(PipeArgs& a, cudaStream_t st) {
+    const int groups = (a.N + a.G - 1) / a.G;
+    for (int k = 0; k <= groups; ++k) {
+        a.s_frame0 = k * a.G;
+        a.s_frames = k < groups ? (a.N - a.s_frame0 < a.G ? a.N - a.s_frame0 : a.G) : 0;
+        a.n_frame0 = (k - 1) * a.G;
+        a.n_frames = k > 0 ? (a.N - a.n_frame0 < a.G ? a.N - a.n_frame0 : a.G) : 0;
+        const long long items = (long long)a.n_frames * a.tn + (long long)a.s_frames * a.ts;
+        const unsigned grid = (unsigned)((items + kWarpsPerCta - 1) / kWarpsPerCta);
+        k_splat_step<T, TF, MODE, CA><<<grid, kPipeThreads, 0, st>>>(a);
+        DCB_CHECK_LAUNCH("k_splat_step");
     }
-    const int grid = (int)(a.total_items < (unsigned)grid_cap ? a.total_items : (unsigned)grid_cap);
-    k_splat_pipe<T, TF, MODE><<<grid, kPipeThreads, smem, st>>>(a);
-    DCB_CHECK_LAUNCH("k_splat_pipe");
     return DCB_OK;
 }
 
-template <class T, class TF> static int launch_pipe(const PipeArgs& a, int mode, cudaStream_t st) {
-    switch (mode) {
-        case DCB_MODE_SUM: return launch_pipe_mode<T, TF, DCB_MODE_SUM>(a, st);
-        case DCB_MODE_AVG: return launch_pipe_mode<T, TF, DCB_MODE_AVG>(a, st);
-        case DCB_MODE_LINEAR: return launch_pipe_mode<T, TF, DCB_MODE_LINEAR>(a, st);
-        default: return launch_pipe_mode<T, TF, DCB_MODE_SOFT>(a, st);
+template <class T, class TF, int MODE> static int launch_mode(PipeArgs& a, cudaStream_t st) {
+    const int ca = a.C + (MODE != DCB_MODE_SUM ? 1 : 0);
+    switch (ca) {
+        case 1: if (MODE == DCB_MODE_SUM) return launch_steps<T, TF, DCB_MODE_SUM, 1>(a, st); break;
+        case 2: return launch_steps<T, TF, MODE, 2>(a, st);
+        case 3: return launch_steps<T, TF, MODE, 3>(a, st);
+        case 4: return launch_steps<T, TF, MODE, 4>(a, st);
     }
+    return set_error(DCB_E_LIMIT, "splat_pipe: %d accumulated channels", ca);
+}
+
+template <class T, class TF> static int launch_pipe(PipeArgs& a, int mode, cudaStream_t st) {
+    switch (mode) {
+        case DCB_MODE_SUM: return launch_mode<T, TF, DCB_MODE_SUM>(a, st);
+        case DCB_MODE_AVG: return launch_mode<T, TF, DCB_MODE_AVG>(a, st);
+        case DCB_MODE_LINEAR: return launch_mode<T, TF, DCB_MODE_LINEAR>(a, st);
+        default: return launch_mode<T, TF, DCB_MODE_SOFT>(a, st);
+    }
+}
+
+// every element offset the kernels form must fit a signed 32-bit integer
+static bool offsets_fit32(const DcbTensor* t) {
+    if (!t) return true;
+    long long span = 0;
+    for (int d = 1; d < 4; ++d) span += (t->size[d] - 1) * (t->stride[d] < 0 ? -t->stride[d] : t->stride[d]);
+    return span < (1ll << 31);
+}
+bool pipe_supported(const DcbTensor* in, const DcbTensor* flow, const DcbTensor* metric) {
+    return offsets_fit32(in) && offsets_fit32(flow) && offsets_fit32(metric) && in->size[2] * in->size[3] < (1ll << 28);
 }
 
 // Preconditions (checked by the caller): C + (mode != SUM) <= 4, dtype F32/BF16, workspace >= pipe_workspace().
@@ -484,27 +325,19 @@ int splat_pipe_impl(const DcbTensor* in, const DcbTensor* flow, const DcbTensor*
     a.N = (int)in->size[0]; a.C = (int)in->size[1]; a.H = (int)in->size[2]; a.W = (int)in->size[3];
     a.HW = (unsigned)(in->size[2] * in->size[3]);
     a.eps = eps;
-    a.ring = pipe_ring(a.N);
-    a.tiles_x = (a.W + kTW - 1) / kTW;
-    a.ts = a.tiles_x * ((a.H + kTH - 1) / kTH);
+    a.G = (int)group_frames(a.N, a.H, a.W);
+    a.tiles_x = (a.W + 31) / 32;
+    a.ts = a.tiles_x * ((a.H + kStripH - 1) / kStripH);
     a.tn = (int)((a.HW + kChunk - 1) / kChunk);
-    a.total_items = (unsigned)((long long)a.N * (a.ts + a.tn));
     a.out = out->ptr;
     a.norm = norm ? norm->ptr : nullptr;
-    const long long acc_bytes = pipe_acc_bytes(a.N, a.H, a.W);
     a.acc = (float*)ws;
-    a.ctrl = (unsigned*)((char*)ws + acc_bytes);
+    { static int dbg = -1; if (dbg < 0) { const char* e = getenv("DCB_DBG"); dbg = e ? atoi(e) : 0; } a.dbg = dbg; }
     if (!ws_clean) DCB_CHECK_CUDA(cudaMemsetAsync(ws, 0, (size_t)pipe_workspace(a.N, a.H, a.W), st));
     const bool ff = flow->dtype == DCB_F32;
-    if (in->dtype == DCB_F32) {
-        a.bulk = bulk_ok<float>(in, a.W) && bulk_ok<float>(flow, a.W) && bulk_ok<float>(metric, a.W);
-        return launch_pipe<float, float>(a, mode, st);
-    }
-    if (in->dtype == DCB_BF16) {
-        a.bulk = bulk_ok<__nv_bfloat16>(in, a.W) && bulk_ok<__nv_bfloat16>(metric, a.W) &&
-                 (ff ? bulk_ok<float>(flow, a.W) : bulk_ok<__nv_bfloat16>(flow, a.W));
+    if (in->dtype == DCB_F32) return launch_pipe<float, float>(a, mode, st);
+    if (in->dtype == DCB_BF16)
         return ff ? launch_pipe<__nv_bfloat16, float>(a, mode, st) : launch_pipe<__nv_bfloat16, __nv_bfloat16>(a, mode, st);
-    }
     return set_error(DCB_E_DTYPE, "splat_pipe: unsupported dtype %d", in->dtype);
 }
 

@@ -36,9 +36,9 @@ def test_workspace_queries_need_no_gpu():
     import diffcodec_b200
     L = diffcodec_b200._lib
     lib = L.lib()
-    # C+1 <= 4: a ring of min(N,3) frame-sized float4 accumulators + a small control block
-    assert lib.dcb_splat_workspace_bytes(1, 3, 1080, 1920, L.DCB_F32, L.MODE_SOFT, 0) == 1080 * 1920 * 16 + 512
-    assert lib.dcb_splat_fwd_workspace_bytes(64, 3, 1080, 1920, L.DCB_F32, L.MODE_SOFT, 0) == 3 * 1080 * 1920 * 16 + 768
+    # C+1 <= 4: one or two L2-sized slots of float4 accumulators (a slot = one 1080p frame)
+    assert lib.dcb_splat_fwd_workspace_bytes(1, 3, 1080, 1920, L.DCB_F32, L.MODE_SOFT, 0) == 1080 * 1920 * 16
+    assert lib.dcb_splat_fwd_workspace_bytes(64, 3, 1080, 1920, L.DCB_F32, L.MODE_SOFT, 0) == 2 * 1080 * 1920 * 16
     assert lib.dcb_splat_workspace_bytes(1, 8, 64, 64, L.DCB_F32, L.MODE_SUM, 0) == 0        # planar reds straight into out
     assert lib.dcb_splat_workspace_bytes(8, 64, 256, 256, L.DCB_F32, L.MODE_SOFT, 0) == 8 * 65 * 256 * 256 * 4
     assert lib.dcb_splat_bwd_workspace_bytes(64, 3, 1080, 1920, L.DCB_F32, L.MODE_SOFT, 0) == 64 * 1080 * 1920 * 8

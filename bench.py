@@ -12,7 +12,8 @@ frames are C1/C3-shaped: 3 x 1080 x 1920, smooth synthetic flow of ~8 px). Print
   e2e          same metric through the public Python API from PINNED HOST buffers: H2D of the
                step's inputs, the op, D2H of the result, all inside the timed region
   roofline     algorithmic bytes (36 B/px) / measured duration of one
-               forward (scatter + normalise launches) vs the measured HBM copy peak
+               k_splat_step launch (F+1 launches per step of F frames; launch k scatters frame k
+               and normalises frame k-1) vs the measured HBM copy peak
   cpu_baseline the oracle port (C + pthreads over frames) on a bounded sample, rank 0, N=1 only
   extra        secondary configs of BASELINE.json (C1 avg latency, C2 bf16 latents, C3 residual
                recipe + backwarp, C4 fwd+bwd), measured outside the timed region
@@ -295,7 +296,7 @@ def run_ours(args):
                        "frames_per_gpu": F, "l2_policy": f"inputs+outputs per step = {(36 * px_per_step) >> 20} MiB per GPU, larger than the 126 MB L2; no flush needed",
                        "partition": "frames sharded by rank, no data-path collective"},
             "roofline": {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),
-                         "traffic": None, "kernel": "k_scatter_vec4 + k_normalize (one forward = 2 launches)",
+                         "traffic": None, "kernel": "k_splat_step (one launch per frame: scatter of frame k + normalise of frame k-1)",
                          "algorithmic_bytes_per_px": ALG_BYTES_PER_PX, "peak_source": peak_src, "frac_of_nominal_8TBs": round(achieved / 8000.0, 4)},
             "e2e": {"value": round(e2e_value, 1), "unit": "Mpixel/s", "h2d_bytes_per_step": Fe * (C + 3) * H * W * 4,
                     "d2h_bytes_per_step": Fe * C * H * W * 4, "frames_per_step": Fe, "api": "diffcodec_b200.softsplat(tenIn, tenFlow, tenMetric, 'soft') from pinned host tensors"},

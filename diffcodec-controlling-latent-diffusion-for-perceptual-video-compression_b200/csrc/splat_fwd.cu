@@ -206,7 +206,7 @@ __global__ void __launch_bounds__(kThreads) k_normalize(const FwdArgs a) {
 long long pipe_workspace(long long N, long long H, long long W);
 int splat_pipe_impl(const DcbTensor* in, const DcbTensor* flow, const DcbTensor* metric, const DcbTensor* out,
                     const DcbTensor* norm, const DcbTensor* mask, void* ws, int mode, int eps, bool ws_clean,
-                    cudaStream_t st);
+                    cudaStream_t st, bool ones_metric = false, const DcbTensor* mask_out = nullptr);
 bool pipe_supported(const DcbTensor* in, const DcbTensor* flow, const DcbTensor* metric);
 
 // C+1 <= 4 channels in fp32 / bf16: the persistent pipelined kernel (splat_pipe.cu)

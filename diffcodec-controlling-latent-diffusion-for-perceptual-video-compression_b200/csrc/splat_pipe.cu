@@ -33,13 +33,23 @@ namespace dcb {
 
 constexpr int kPipeThreads = 128;           // 4 independent warps per CTA
 constexpr int kWarpsPerCta = kPipeThreads / 32;
-constexpr int kRows = 4;                    // rows loaded at once by a warp
-constexpr int kPasses = 2;                  // consecutive row groups per strip (the vertical carry spans them)
-constexpr int kMinCtas = 8;                 // register budget: 64 per thread -> 32 warps per SM
+#ifndef DCB_KROWS
+#define DCB_KROWS 4
+#endif
+#ifndef DCB_KPASSES
+#define DCB_KPASSES 1
+#endif
+#ifndef DCB_MINCTAS
+#define DCB_MINCTAS 8
+#endif
+constexpr int kRows = DCB_KROWS;            // rows loaded at once by a warp
+constexpr int kPasses = DCB_KPASSES;        // consecutive row groups per strip (the vertical carry spans them)
+constexpr int kMinCtas = DCB_MINCTAS;       // register budget: 64 per thread -> 32 warps per SM
 constexpr int kStripH = kRows * kPasses;    // a scatter item: 32 columns x 16 rows
 constexpr int kNPer = 8;                    // normalise: pixels per lane per batch
 constexpr int kNBatches = 2;
 constexpr int kChunk = 32 * kNPer * kNBatches;   // a normalise item: 512 target pixels
+constexpr float kExp1 = 2.7182817459106445f;     // expf(1.0f): what tenMetric.exp() yields for an all-ones metric
 constexpr long long kGroupBytes = 34ll << 20;    // accumulator bytes per ring slot (one 1080p frame = 31.6 MiB)
 
 struct PipeArgs {
@@ -54,6 +64,10 @@ struct PipeArgs {
     int tiles_x, ts, tn;     // scatter strips per row / per frame, normalise chunks per frame
     int s_frame0, s_frames;  // this step scatters frames [s_frame0, s_frame0 + s_frames)
     int n_frame0, n_frames;  // ... and normalises frames [n_frame0, n_frame0 + n_frames)
+    View epi_flow;           // epilogue 1 (occlusion mask): the motion field compared with the splatted one
+    void* mask_out;          // epilogue 1: [N,1,H,W] in T
+    int epi;                 // 0 = normalise (softsplat), 1 = occlusion mask (control_utils.py:15-16)
+    int ones;                // metric is all-ones and not materialised (compute_mask, dataset wrappers)
     int dbg;                 // experiments only (DCB_DBG): 1 = no reds, 2 = no input loads, 4 = skip normalise items, 8 = skip scatter items
 };
 
@@ -89,7 +103,7 @@ __device__ __forceinline__ void scatter_strip(const PipeArgs& a, int frame, int 
     const int xs = xin ? x : 0;
     const TF* fbase = (const TF*)a.flow.p + frame * a.flow.sN;
     const T* ibase = (const T*)a.in.p + frame * a.in.sN;
-    const T* mbase = (MODE >= DCB_MODE_LINEAR) ? (const T*)a.metric.p + frame * a.metric.sN : nullptr;
+    const T* mbase = (MODE >= DCB_MODE_LINEAR && !a.ones) ? (const T*)a.metric.p + frame * a.metric.sN : nullptr;
     // element offsets fit 32 bits (checked by the host)
     const int f_sH = (int)a.flow.sH, f_sC = (int)a.flow.sC, i_sH = (int)a.in.sH, i_sC = (int)a.in.sC, m_sH = (int)a.metric.sH;
     const int f_x = xs * (int)a.flow.sW, i_x = xs * (int)a.in.sW, m_x = xs * (int)a.metric.sW;
@@ -111,7 +125,7 @@ __device__ __forceinline__ void scatter_strip(const PipeArgs& a, int frame, int 
             if (on) {
                 const TF* fp = fbase + (y * f_sH + f_x);
                 flx[r] = ld_stream(fp); fly[r] = ld_stream(fp + f_sC);
-                if (MODE >= DCB_MODE_LINEAR) mv[r] = ld_stream(mbase + (y * m_sH + m_x));
+                if (MODE >= DCB_MODE_LINEAR && !a.ones) mv[r] = ld_stream(mbase + (y * m_sH + m_x));
                 const T* ip = ibase + (y * i_sH + i_x);
 #pragma unroll
                 for (int c = 0; c < C; ++c) iv[r][c] = ld_stream(ip + c * i_sC);
@@ -131,8 +145,8 @@ __device__ __forceinline__ void scatter_strip(const PipeArgs& a, int frame, int 
             const float wnw = mul_rn(ex, ey), wne = mul_rn(dx, ey), wsw = mul_rn(ex, dy), wse = mul_rn(dx, dy);
 
             float g = 1.f;
-            if (MODE == DCB_MODE_LINEAR) g = mv[r];
-            if (MODE == DCB_MODE_SOFT) g = expf(mv[r]);
+            if (MODE == DCB_MODE_LINEAR) g = a.ones ? 1.f : mv[r];
+            if (MODE == DCB_MODE_SOFT) g = a.ones ? kExp1 : expf(mv[r]);
             float nw[4] = {0.f, 0.f, 0.f, 0.f}, ne[4] = {0.f, 0.f, 0.f, 0.f}, sw[4] = {0.f, 0.f, 0.f, 0.f}, se[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
             for (int c = 0; c < CA; ++c) {
@@ -231,6 +245,43 @@ __device__ __forceinline__ void normalize_chunk(const PipeArgs& a, int frame, in
 }
 
 // ---------------------------------------------------------------------------------------------
+// occlusion epilogue (compute_mask, controlnet/control_utils.py:11-17): the accumulators hold the
+// soft splat of a 2-channel flow (x*e, y*e, e); mask = (||motion + splat/(norm + 1e-7)||_2 > 0.3)
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ float occlusion(float wx, float wy, float d, float mx, float my) {
+    const float n = add_rn(d, 0.0000001f);
+    const float ex = add_rn(mx, wx / n), ey = add_rn(my, wy / n);
+    return sqrtf(add_rn(mul_rn(ex, ex), mul_rn(ey, ey))) > 0.3f ? 1.f : 0.f;
+}
+
+template <class T>
+__device__ __forceinline__ void mask_chunk(const PipeArgs& a, int frame, int chunk, float* acc, int lane) {
+    T* out = (T*)a.mask_out + (long long)frame * a.HW;
+#pragma unroll 1
+    for (int b = 0; b < kNBatches; ++b) {
+        const unsigned base = (unsigned)chunk * kChunk + b * (32 * kNPer) + lane;
+        if (base - lane >= a.HW) break;
+        float4 s[kNPer];
+#pragma unroll
+        for (int i = 0; i < kNPer; ++i) {
+            const unsigned r = base + i * 32;
+            s[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (r < a.HW) s[i] = __ldcg((const float4*)acc + r);
+        }
+#pragma unroll
+        for (int i = 0; i < kNPer; ++i) {
+            const unsigned r = base + i * 32;
+            if (r < a.HW) {
+                __stcg((float4*)acc + r, make_float4(0.f, 0.f, 0.f, 0.f));
+                const int y = (int)(r / (unsigned)a.W), x = (int)(r - (unsigned)y * (unsigned)a.W);
+                const T* fp = (const T*)a.epi_flow.p + frame * a.epi_flow.sN + (long long)y * a.epi_flow.sH + (long long)x * a.epi_flow.sW;
+                st<T, float>(out + r, occlusion(s[i].x, s[i].y, s[i].z, ld<float>(fp), ld<float>(fp + a.epi_flow.sC)));
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 // the step kernel: warp w of CTA b owns item 4b + w; normalise items first, then scatter items
 // ---------------------------------------------------------------------------------------------
 template <class T, class TF, int MODE, int CA>
@@ -243,7 +294,8 @@ __global__ void __launch_bounds__(kPipeThreads, kMinCtas) k_splat_step(const __g
         if (a.dbg & 4) return;
         const int f = a.n_frame0 + item / a.tn, chunk = item % a.tn;
         float* acc = a.acc + (size_t)((f / a.G) & 1) * slot_floats + (size_t)(f % a.G) * a.HW * 4;
-        normalize_chunk<T, MODE, CA>(a, f, chunk, acc, lane);
+        if (a.epi == 1) mask_chunk<T>(a, f, chunk, acc, lane);
+        else normalize_chunk<T, MODE, CA>(a, f, chunk, acc, lane);
     } else {
         const unsigned s = item - n_items;
         if (s >= (unsigned)a.s_frames * a.ts || (a.dbg & 8)) return;
@@ -319,8 +371,12 @@ bool pipe_supported(const DcbTensor* in, const DcbTensor* flow, const DcbTensor*
 // Preconditions (checked by the caller): C + (mode != SUM) <= 4, dtype F32/BF16, workspace >= pipe_workspace().
 int splat_pipe_impl(const DcbTensor* in, const DcbTensor* flow, const DcbTensor* metric, const DcbTensor* out,
                     const DcbTensor* norm, const DcbTensor* mask, void* ws, int mode, int eps, bool ws_clean,
-                    cudaStream_t st) {
+                    cudaStream_t st, bool ones_metric, const DcbTensor* mask_out) {
     PipeArgs a;
+    a.ones = ones_metric ? 1 : 0;
+    a.epi = mask_out ? 1 : 0;
+    a.epi_flow = make_view(mask_out ? flow : nullptr);
+    a.mask_out = mask_out ? mask_out->ptr : nullptr;
     a.in = make_view(in); a.flow = make_view(flow); a.metric = make_view(metric); a.mask = make_view(mask);
     a.N = (int)in->size[0]; a.C = (int)in->size[1]; a.H = (int)in->size[2]; a.W = (int)in->size[3];
     a.HW = (unsigned)(in->size[2] * in->size[3]);
@@ -329,7 +385,7 @@ int splat_pipe_impl(const DcbTensor* in, const DcbTensor* flow, const DcbTensor*
     a.tiles_x = (a.W + 31) / 32;
     a.ts = a.tiles_x * ((a.H + kStripH - 1) / kStripH);
     a.tn = (int)((a.HW + kChunk - 1) / kChunk);
-    a.out = out->ptr;
+    a.out = out ? out->ptr : nullptr;
     a.norm = norm ? norm->ptr : nullptr;
     a.acc = (float*)ws;
     { static int dbg = -1; if (dbg < 0) { const char* e = getenv("DCB_DBG"); dbg = e ? atoi(e) : 0; } a.dbg = dbg; }

@@ -61,8 +61,10 @@ def residual_conditioning(image1, flow1, flow2, gt, variant: str = "dataset", re
         dev = image1.device
         fused = torch.empty((n, c, h, w), dtype=image1.dtype, device=dev)
         residual = torch.empty_like(fused)
-        occ_fwd = torch.empty((n, 1, h, w), dtype=image1.dtype, device=dev) if return_masks else None
-        occ_bwd = torch.empty_like(occ_fwd) if return_masks else None
+        # always hand the masks their own storage: the library's in-workspace mask scratch would
+        # dirty the shared, kept-zero accumulator buffer
+        occ_fwd = torch.empty((n, 1, h, w), dtype=image1.dtype, device=dev)
+        occ_bwd = torch.empty_like(occ_fwd)
         need = lib.dcb_residual_workspace_bytes(n, c, h, w)
         ws = _lib.workspace(dev, need, "acc")
         with torch.cuda.device(dev):

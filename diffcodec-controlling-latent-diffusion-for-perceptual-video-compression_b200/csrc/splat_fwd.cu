@@ -208,6 +208,11 @@ int splat_pipe_impl(const DcbTensor* in, const DcbTensor* flow, const DcbTensor*
                     const DcbTensor* norm, const DcbTensor* mask, void* ws, int mode, int eps, bool ws_clean,
                     cudaStream_t st, bool ones_metric = false, const DcbTensor* mask_out = nullptr);
 bool pipe_supported(const DcbTensor* in, const DcbTensor* flow, const DcbTensor* metric);
+// implemented in splat_planar.cu
+long long planar_workspace(long long N, long long C, long long H, long long W, int dtype, int mode);
+int splat_planar_impl(const DcbTensor* in, const DcbTensor* flow, const DcbTensor* metric, const DcbTensor* out,
+                      const DcbTensor* norm, const DcbTensor* mask, void* ws, int mode, int eps, bool ws_clean,
+                      cudaStream_t st);
 
 // C+1 <= 4 channels in fp32 / bf16: the persistent pipelined kernel (splat_pipe.cu)
 static bool use_pipe(int dtype, int mode, long long C) {
@@ -219,7 +224,9 @@ static bool use_pipe(int dtype, int mode, long long C) {
 long long splat_fwd_workspace(long long N, long long C, long long H, long long W, int dtype, int mode) {
     const long long cacc = C + (mode == DCB_MODE_SUM ? 0 : 1);
     const long long esz = dtype == DCB_F64 ? 8 : 4;
+    static const bool no_pipe = getenv("DCB_NO_PIPE") != nullptr;
     if (use_pipe(dtype, mode, C)) return pipe_workspace(N, H, W);
+    if (!no_pipe && dtype != DCB_F64) return planar_workspace(N, C, H, W, dtype, mode);
     if (mode == DCB_MODE_SUM && dtype != DCB_BF16) return 0;      // planar reds go straight into `out`
     if (dtype != DCB_F64 && cacc <= 4) return align_up(N * H * W * 16, 256);   // (DCB_NO_PIPE) vec4 accumulators
     return align_up(N * cacc * H * W * esz, 256);
@@ -303,7 +310,13 @@ int splat_fwd_impl(const DcbTensor* in, const DcbTensor* flow, const DcbTensor* 
             return set_error(DCB_E_WORKSPACE, "splat_fwd: workspace of %lld bytes (256 B aligned) required, got %lld", need, ws_bytes);
         return splat_pipe_impl(in, flow, metric, out, norm, mask, ws, mode, eps, (flags & DCB_FLAG_WS_CLEAN) != 0, st);
     }
-    // the one-kernel-per-stage vec4 path is kept for A-B measurements (DCB_NO_PIPE=1)
+    if (in->dtype != DCB_F64 && getenv("DCB_NO_PIPE") == nullptr) {
+        const long long need = planar_workspace(a.N, a.C, a.H, a.W, in->dtype, mode);
+        if (need > 0 && (!ws || ws_bytes < need || ((uintptr_t)ws & 255)))
+            return set_error(DCB_E_WORKSPACE, "splat_fwd: workspace of %lld bytes (256 B aligned) required, got %lld", need, ws_bytes);
+        return splat_planar_impl(in, flow, metric, out, norm, mask, ws, mode, eps, (flags & DCB_FLAG_WS_CLEAN) != 0, st);
+    }
+    // the one-kernel-per-stage paths below: fp64, and A-B measurements (DCB_NO_PIPE=1)
     const bool vec4 = in->dtype != DCB_F64 && a.Cacc <= 4 && !(mode == DCB_MODE_SUM && in->dtype == DCB_F32);
     const bool acc_is_out = (mode == DCB_MODE_SUM && in->dtype != DCB_BF16 && !mask);
     long long acc_bytes;

@@ -1,0 +1,344 @@
+// splat_planar.cu -- forward splat for MANY channels (feature maps: C = 64 .. 640) in fp32 / bf16,
+// as the same kernel-per-step software pipeline as splat_pipe.cu, with planar accumulators.
+//
+// Replaces controlnet/softsplat.py:240-270 (pre/post ops) + :281-345 (zero-init + softsplat_out)
+// for C + 1 > 4. The reference runs one thread per (pixel, channel): flow is re-read and the four
+// weights recomputed C+1 times per pixel, and every element issues 4 scalar atomics. Here
+//
+//   * a warp owns a 32-column x 4-row strip of ONE frame for ALL channels: the footprint of every
+//     pixel (corner offset, 4 weights, which pieces merge with the lane to the right / the row
+//     below) is computed once and kept in registers, then the channels stream through it;
+//   * per channel the east column is handed to lane+1 by shuffle and the south row is carried to
+//     the next row when footprints abut, so smooth flow costs ~1.2-2 scalar reds per element
+//     instead of 4; a warp's reds of one channel fall on one or two 128-byte lines of one plane;
+//   * accumulators are planar fp32 [frame][C+1][H][W] in a ring of two L2-sized slots; step k
+//     normalises frame group k-1 (and re-zeroes it) while it scatters group k; the kernel boundary
+//     is the only synchronisation; inputs/outputs use streaming loads/stores.
+#include "dcb_common.cuh"
+
+namespace dcb {
+
+constexpr int kPThreads = 128;
+constexpr int kPWarps = kPThreads / 32;
+constexpr int kPRows = 4;                         // strip: 32 columns x 4 rows
+constexpr int kPChunk = 128;                      // normalise item: 128 target pixels (4 per lane)
+constexpr long long kPGroupBytes = 34ll << 20;    // accumulator bytes per ring slot
+constexpr float kExp1p = 2.7182817459106445f;
+
+struct PlanarArgs {
+    View in, flow, metric, mask;
+    float* acc;              // channel planes: 2 slots x G frames x C x HW floats (or `out` when acc_is_out)
+    float* dacc;             // normaliser planes: 3 slots x G frames x HW floats (read by several warps, re-zeroed one step later)
+    void* out;               // [N,C,H,W]
+    void* norm;              // [N,1,H,W] fp32 or null
+    int N, C, Cacc, H, W;
+    unsigned HW;
+    int mode, eps;
+    int G;
+    int tiles_x, ts, tn;
+    int cg_s, ncg_s;         // scatter: channels per item, items per strip
+    int cg_n, ncg_n;         // normalise: channels per item, items per chunk
+    int tz;                  // re-zero items per frame (1024 normaliser cells each)
+    int step;                // pipeline step k: scatter group k, normalise group k-1, re-zero normaliser slot (k+1) % 3
+    int s_frame0, s_frames, n_frame0, n_frames;
+    int acc_is_out;          // SUM in fp32: reds go straight into `out`, no normalise items
+};
+
+__device__ __forceinline__ void red1_if(bool p, float* addr, float v) {
+    asm volatile(
+        "{\n\t.reg .pred q;\n\t"
+        "setp.ne.s32 q, %0, 0;\n\t"
+        "@q red.global.add.f32 [%1], %2;\n\t}"
+        ::"r"((int)p), "l"(addr), "f"(v) : "memory");
+}
+
+template <class T, class TF>
+__device__ __forceinline__ void planar_scatter_strip(const PlanarArgs& a, int frame, int tile, int c_begin, int c_end,
+                                                     float* acc, float* dplane, int lane) {
+    const int tx = tile % a.tiles_x, ty = tile / a.tiles_x;
+    const int x = tx * 32 + lane, yb = ty * kPRows;
+    const int W = a.W, H = a.H, C = a.C;
+    const bool xin = x < W;
+    const int rows = min(kPRows, H - yb);
+    const unsigned full = 0xffffffffu;
+    constexpr int kDead = -7;
+    const int pitch = W + 2;
+    const int xs = xin ? x : 0;
+
+    // ---- footprints of the strip's 4 pixels per lane: computed once, reused for every channel ----
+    float wnw[kPRows], wne[kPRows], wsw[kPRows], wse[kPRows], g[kPRows];
+    int off[kPRows];
+    bool take[kPRows], e_n[kPRows], e_s[kPRows], join[kPRows], n_ok[kPRows], flush_prev[kPRows];
+    bool last_ok = false;
+    int last_off = 0;
+    {
+        const TF* fbase = (const TF*)a.flow.p + frame * a.flow.sN + (long long)xs * a.flow.sW;
+        const T* mbase = a.metric.p ? (const T*)a.metric.p + frame * a.metric.sN + (long long)xs * a.metric.sW : nullptr;
+        int pend_key = kDead;
+        bool pend_ok = false;
+#pragma unroll
+        for (int r = 0; r < kPRows; ++r) {
+            const bool in_img = xin && r < rows;
+            const long long y = yb + r;
+            float flx = 0.f, fly = 0.f, m = 0.f;
+            if (in_img) {
+                const TF* fp = fbase + y * a.flow.sH;
+                flx = ld_stream(fp); fly = ld_stream(fp + a.flow.sC);
+                if (mbase) m = ld_stream(mbase + y * a.metric.sH);
+            }
+            const float fx = add_rn((float)x, flx), fy = add_rn((float)(yb + r), fly);       // softsplat.py:298-299
+            const float x0f = floorf(fx), y0f = floorf(fy);
+            const int x0 = __float2int_rz(x0f), y0 = __float2int_rz(y0f);
+            const bool alive = in_img && fabsf(fx) < 3.0e38f && fabsf(fy) < 3.0e38f &&
+                               ((unsigned)x0 + 1u) <= (unsigned)W && ((unsigned)y0 + 1u) <= (unsigned)H;
+            const float ex = sub_rn(add_rn(x0f, 1.f), fx), ey = sub_rn(add_rn(y0f, 1.f), fy);  // softsplat.py:315-318
+            const float dx = sub_rn(fx, x0f), dy = sub_rn(fy, y0f);
+            wnw[r] = mul_rn(ex, ey); wne[r] = mul_rn(dx, ey); wsw[r] = mul_rn(ex, dy); wse[r] = mul_rn(dx, dy);
+            g[r] = a.mode == DCB_MODE_SOFT ? expf(m) : (a.mode == DCB_MODE_LINEAR ? m : 1.f);
+            const int key = alive ? (y0 + 1) * pitch + (x0 + 1) : kDead;
+            off[r] = y0 * W + x0;
+            const bool vx0 = x0 >= 0, vx1 = x0 < W - 1, vy0 = y0 >= 0, vy1 = y0 < H - 1;
+            const int lkey = __shfl_up_sync(full, key, 1);
+            take[r] = lane > 0 && alive && lkey != kDead && lkey + 1 == key;
+            const bool given = (__shfl_down_sync(full, (int)take[r], 1) != 0) && lane < 31;
+            const bool east = alive && !given && vx1;
+            e_n[r] = east && vy0; e_s[r] = east && vy1;
+            join[r] = pend_key == key && alive;
+            flush_prev[r] = pend_ok && !join[r];
+            n_ok[r] = alive && vx0 && vy0;
+            pend_key = alive ? key + pitch : kDead;
+            pend_ok = alive && vx0 && vy1;
+        }
+        last_ok = pend_ok;
+        last_off = off[kPRows - 1] + W;
+    }
+
+    // ---- stream the channels through the footprints ----
+    const T* ibase = (const T*)a.in.p + frame * a.in.sN + (long long)xs * a.in.sW + (long long)yb * a.in.sH;
+    for (int c = c_begin; c < c_end; ++c) {
+        float v[kPRows];
+        if (c < C) {
+            const T* ip = ibase + (long long)c * a.in.sC;
+#pragma unroll
+            for (int r = 0; r < kPRows; ++r) {
+                v[r] = 0.f;
+                if (xin && r < rows) v[r] = ld_stream(ip + (long long)r * a.in.sH);
+            }
+#pragma unroll
+            for (int r = 0; r < kPRows; ++r) v[r] = (a.mode >= DCB_MODE_LINEAR) ? mul_rn(v[r], g[r]) : v[r];   // softsplat.py:244,247
+        } else {
+#pragma unroll
+            for (int r = 0; r < kPRows; ++r) v[r] = g[r];                                                       // appended channel
+        }
+        float* plane = c < C ? acc + (size_t)c * a.HW : dplane;
+        float pend = 0.f;
+#pragma unroll
+        for (int r = 0; r < kPRows; ++r) {
+            float nw = mul_rn(v[r], wnw[r]), sw = mul_rn(v[r], wsw[r]);
+            const float ne = mul_rn(v[r], wne[r]), se = mul_rn(v[r], wse[r]);
+            const float en = __shfl_up_sync(full, ne, 1), es = __shfl_up_sync(full, se, 1);
+            nw = take[r] ? add_rn(nw, en) : nw;
+            sw = take[r] ? add_rn(sw, es) : sw;
+            red1_if(e_n[r], plane + off[r] + 1, ne);
+            red1_if(e_s[r], plane + off[r] + W + 1, se);
+            if (r > 0) red1_if(flush_prev[r], plane + off[r - 1] + W, pend);
+            nw = join[r] ? add_rn(nw, pend) : nw;
+            red1_if(n_ok[r], plane + off[r], nw);
+            pend = sw;
+        }
+        red1_if(last_ok, plane + last_off, pend);
+    }
+}
+
+template <class T>
+__device__ __forceinline__ void planar_normalize_chunk(const PlanarArgs& a, int frame, int chunk, int c_begin, int c_end,
+                                                       float* acc, const float* dplane, int lane) {
+    const int C = a.C;
+    T* out = (T*)a.out + (long long)frame * C * a.HW;
+    constexpr int kPer = kPChunk / 32;
+    const unsigned base = (unsigned)chunk * kPChunk + lane;
+    float scale[kPer];
+    const bool normalised = a.mode != DCB_MODE_SUM;
+#pragma unroll
+    for (int i = 0; i < kPer; ++i) {
+        const unsigned r = base + i * 32;
+        scale[i] = 1.f;
+        if (r < a.HW) {
+            if (normalised) {
+                float d = __ldcg(dplane + r);     // shared by the warps of every channel group: re-zeroed a step later
+                // softsplat.py:256-266
+                if (a.eps == DCB_EPS_ADD) d = add_rn(d, 0.0000001f);
+                else if (a.eps == DCB_EPS_ZERO) d = (d == 0.f) ? 1.f : d;
+                else d = (d < 0.0000001f) ? 0.0000001f : d;
+                if (a.norm && c_begin == 0) __stcs((float*)a.norm + (long long)frame * a.HW + r, d);
+                scale[i] = __frcp_rn(d);          // <= 1 ulp from the true quotient of softsplat.py:270
+            }
+            if (a.mask.p) {
+                const int y = (int)(r / (unsigned)a.W), x = (int)(r - (unsigned)y * (unsigned)a.W);
+                const T* mp = (const T*)a.mask.p + frame * a.mask.sN + (long long)y * a.mask.sH + (long long)x * a.mask.sW;
+                scale[i] = mul_rn(scale[i], sub_rn(1.f, ld<float>(mp)));     // control_utils.py:69-70
+            }
+        }
+    }
+    const bool scaled = normalised || a.mask.p != nullptr;
+    constexpr int kCU = 4;                           // channels in flight
+    (void)C;
+    for (int c0 = c_begin; c0 < c_end; c0 += kCU) {
+        float s[kCU][kPer];
+#pragma unroll
+        for (int j = 0; j < kCU; ++j)
+#pragma unroll
+            for (int i = 0; i < kPer; ++i) {
+                const unsigned r = base + i * 32;
+                s[j][i] = 0.f;
+                if (c0 + j < c_end && r < a.HW) s[j][i] = __ldcg(acc + (size_t)(c0 + j) * a.HW + r);
+            }
+#pragma unroll
+        for (int j = 0; j < kCU; ++j)
+#pragma unroll
+            for (int i = 0; i < kPer; ++i) {
+                const unsigned r = base + i * 32;
+                if (c0 + j < c_end && r < a.HW) {
+                    __stcg(acc + (size_t)(c0 + j) * a.HW + r, 0.f);
+                    st_stream(out + (size_t)(c0 + j) * a.HW + r, scaled ? mul_rn(s[j][i], scale[i]) : s[j][i]);
+                }
+            }
+    }
+}
+
+template <class T, class TF>
+__global__ void __launch_bounds__(kPThreads, 6) k_planar_step(const __grid_constant__ PlanarArgs a) {
+    const int lane = threadIdx.x & 31;
+    unsigned item = blockIdx.x * kPWarps + (threadIdx.x >> 5);
+    const size_t frame_floats = (size_t)a.C * a.HW, slot_floats = (size_t)a.G * frame_floats;
+    const size_t dslot = (size_t)a.G * a.HW;
+    const unsigned n_items = (unsigned)a.n_frames * a.tn * a.ncg_n;
+    const unsigned z_items = a.acc_is_out || a.mode == DCB_MODE_SUM ? 0u : (unsigned)a.G * a.tz;
+    if (item < n_items) {                                                 // normalise group step-1
+        const unsigned per = (unsigned)a.tn * a.ncg_n;
+        const int fi = item / per, q = item % per;
+        const int chunk = q % a.tn, cgi = q / a.tn;
+        const int f = a.n_frame0 + fi, g = a.step - 1;
+        float* acc = a.acc + (size_t)(g & 1) * slot_floats + (size_t)fi * frame_floats;
+        const float* dplane = a.dacc + (size_t)(g % 3) * dslot + (size_t)fi * a.HW;
+        planar_normalize_chunk<T>(a, f, chunk, cgi * a.cg_n, min(a.C, (cgi + 1) * a.cg_n), acc, dplane, lane);
+        return;
+    }
+    item -= n_items;
+    if (item < z_items) {                                                 // re-zero the normaliser slot of group step+1
+        const int fi = item / a.tz, q = item % a.tz;
+        float* dplane = a.dacc + (size_t)((a.step + 1) % 3) * dslot + (size_t)fi * a.HW;
+        for (unsigned r = (unsigned)q * 1024 + lane; r < min(a.HW, (unsigned)(q + 1) * 1024); r += 32) __stcg(dplane + r, 0.f);
+        return;
+    }
+    item -= z_items;
+    const unsigned per = (unsigned)a.ts * a.ncg_s;
+    if (item >= (unsigned)a.s_frames * per) return;
+    const int fi = item / per, q = item % per;                            // scatter group step
+    const int strip = q % a.ts, cgi = q / a.ts;
+    const int f = a.s_frame0 + fi;
+    float* acc = a.acc_is_out ? a.acc + (size_t)f * frame_floats
+                              : a.acc + (size_t)(a.step & 1) * slot_floats + (size_t)fi * frame_floats;
+    float* dplane = a.acc_is_out ? nullptr : a.dacc + (size_t)(a.step % 3) * dslot + (size_t)fi * a.HW;
+    planar_scatter_strip<T, TF>(a, f, strip, cgi * a.cg_s, min(a.Cacc, (cgi + 1) * a.cg_s), acc, dplane, lane);
+}
+
+// ---------------------------------------------------------------------------------------------
+// host
+// ---------------------------------------------------------------------------------------------
+static long long planar_group_frames(long long N, long long C, long long H, long long W) {
+    const long long per = C * H * W * 4;
+    long long g = kPGroupBytes / (per > 0 ? per : 1);
+    if (g < 1) g = 1;
+    return g > N ? (N < 1 ? 1 : N) : g;
+}
+
+static long long planar_chan_bytes(long long N, long long C, long long H, long long W) {
+    const long long G = planar_group_frames(N, C, H, W);
+    return align_up((N > G ? 2 : 1) * G * C * H * W * 4, 256);
+}
+
+long long planar_workspace(long long N, long long C, long long H, long long W, int dtype, int mode) {
+    if (mode == DCB_MODE_SUM && dtype == DCB_F32) return 0;               // reds go straight into `out`
+    const long long G = planar_group_frames(N, C, H, W);
+    const long long dbytes = mode == DCB_MODE_SUM ? 0 : align_up(3 * G * H * W * 4, 256);
+    return planar_chan_bytes(N, C, H, W) + dbytes;
+}
+
+// split channels over several warps when the frames are too small to fill the machine
+static void split_channels(long long items, int channels, int min_cg, int* cg, int* ncg) {
+    const long long want = 148ll * 24;
+    long long n = items > 0 ? (want + items - 1) / items : 1;
+    const int max_n = channels / min_cg > 0 ? channels / min_cg : 1;
+    if (n > max_n) n = max_n;
+    if (n < 1) n = 1;
+    *cg = (int)((channels + n - 1) / n);
+    *ncg = (channels + *cg - 1) / *cg;
+}
+
+template <class T, class TF> static int launch_planar(PlanarArgs& a, cudaStream_t st) {
+    if (a.acc_is_out) {
+        a.step = 0; a.s_frame0 = 0; a.s_frames = a.N; a.n_frame0 = 0; a.n_frames = 0;
+        const long long items = (long long)a.N * a.ts * a.ncg_s;
+        k_planar_step<T, TF><<<(unsigned)((items + kPWarps - 1) / kPWarps), kPThreads, 0, st>>>(a);
+        DCB_CHECK_LAUNCH("k_planar_step");
+        return DCB_OK;
+    }
+    const int groups = (a.N + a.G - 1) / a.G;
+    const bool normalised = a.mode != DCB_MODE_SUM;
+    for (int k = 0; k <= groups; ++k) {
+        a.step = k;
+        a.s_frame0 = k * a.G;
+        a.s_frames = k < groups ? (a.N - a.s_frame0 < a.G ? a.N - a.s_frame0 : a.G) : 0;
+        a.n_frame0 = (k - 1) * a.G;
+        a.n_frames = k > 0 ? (a.N - a.n_frame0 < a.G ? a.N - a.n_frame0 : a.G) : 0;
+        const long long items = (long long)a.n_frames * a.tn * a.ncg_n + (normalised ? (long long)a.G * a.tz : 0) +
+                                (long long)a.s_frames * a.ts * a.ncg_s;
+        k_planar_step<T, TF><<<(unsigned)((items + kPWarps - 1) / kPWarps), kPThreads, 0, st>>>(a);
+        DCB_CHECK_LAUNCH("k_planar_step");
+    }
+    // the normaliser slot read by the last step is the only part of the workspace left non-zero
+    if (normalised)
+        DCB_CHECK_CUDA(cudaMemsetAsync(a.dacc + (size_t)((groups - 1) % 3) * a.G * a.HW, 0, (size_t)a.G * a.HW * 4, st));
+    return DCB_OK;
+}
+
+// fp32 / bf16, any channel count. `ws` must hold planar_workspace() bytes (all-zero if ws_clean).
+int splat_planar_impl(const DcbTensor* in, const DcbTensor* flow, const DcbTensor* metric, const DcbTensor* out,
+                      const DcbTensor* norm, const DcbTensor* mask, void* ws, int mode, int eps, bool ws_clean,
+                      cudaStream_t st) {
+    PlanarArgs a;
+    a.in = make_view(in); a.flow = make_view(flow); a.metric = make_view(metric); a.mask = make_view(mask);
+    a.N = (int)in->size[0]; a.C = (int)in->size[1]; a.H = (int)in->size[2]; a.W = (int)in->size[3];
+    a.Cacc = a.C + (mode == DCB_MODE_SUM ? 0 : 1);
+    a.HW = (unsigned)(in->size[2] * in->size[3]);
+    a.mode = mode; a.eps = eps;
+    a.G = (int)planar_group_frames(a.N, a.C, a.H, a.W);
+    a.tiles_x = (a.W + 31) / 32;
+    a.ts = a.tiles_x * ((a.H + kPRows - 1) / kPRows);
+    a.tn = (int)((a.HW + kPChunk - 1) / kPChunk);
+    a.tz = (int)((a.HW + 1023) / 1024);
+    const int frames_per_step = a.N < a.G ? a.N : a.G;
+    split_channels((long long)frames_per_step * a.ts, a.Cacc, 8, &a.cg_s, &a.ncg_s);
+    split_channels((long long)frames_per_step * a.tn, a.C, 8, &a.cg_n, &a.ncg_n);
+    a.out = out->ptr;
+    a.norm = norm ? norm->ptr : nullptr;
+    a.acc_is_out = (mode == DCB_MODE_SUM && in->dtype == DCB_F32 && !mask) ? 1 : 0;
+    a.dacc = nullptr;
+    if (a.acc_is_out) {
+        a.acc = (float*)out->ptr;
+        split_channels((long long)a.N * a.ts, a.Cacc, 8, &a.cg_s, &a.ncg_s);
+        DCB_CHECK_CUDA(cudaMemsetAsync(out->ptr, 0, (size_t)a.N * a.C * a.HW * 4, st));
+    } else {
+        a.acc = (float*)ws;
+        a.dacc = (float*)((char*)ws + planar_chan_bytes(a.N, a.C, a.H, a.W));
+        if (!ws_clean) DCB_CHECK_CUDA(cudaMemsetAsync(ws, 0, (size_t)planar_workspace(a.N, a.C, a.H, a.W, in->dtype, mode), st));
+    }
+    const bool ff = flow->dtype == DCB_F32;
+    if (in->dtype == DCB_F32) return launch_planar<float, float>(a, st);
+    if (in->dtype == DCB_BF16)
+        return ff ? launch_planar<__nv_bfloat16, float>(a, st) : launch_planar<__nv_bfloat16, __nv_bfloat16>(a, st);
+    return set_error(DCB_E_DTYPE, "splat_planar: unsupported dtype %d", in->dtype);
+}
+
+}  // namespace dcb

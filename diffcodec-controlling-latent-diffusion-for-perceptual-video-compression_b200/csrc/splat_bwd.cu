@@ -39,7 +39,7 @@ struct BwdArgs {
     int px, cs;          // block shape
 };
 
-// K3a -- target-side scalars.
+// K3a -- target-side scalars. 8 channels (16 loads) in flight per thread.
 template <class T>
 __global__ void __launch_bounds__(256) k_bwd_target(const BwdArgs a) {
     using A = typename Acc<T>::type;
@@ -51,7 +51,16 @@ __global__ void __launch_bounds__(256) k_bwd_target(const BwdArgs a) {
     const T* gp = (const T*)a.gout.p + n * a.gout.sN + y * a.gout.sH + x * a.gout.sW;
     const T* op = (const T*)a.out + (long long)n * a.C * a.HW + r;
     A dot = (A)0;
-    for (int c = 0; c < a.C; ++c) dot += ld<A>(gp + c * a.gout.sC) * ld<A>(op + (long long)c * a.HW);
+    constexpr int U = 8;
+    int c = 0;
+    for (; c + U <= a.C; c += U) {
+        A gv[U], ov[U];
+#pragma unroll
+        for (int j = 0; j < U; ++j) { gv[j] = ld<A>(gp + (long long)(c + j) * a.gout.sC); ov[j] = ld<A>(op + (long long)(c + j) * a.HW); }
+#pragma unroll
+        for (int j = 0; j < U; ++j) dot += gv[j] * ov[j];
+    }
+    for (; c < a.C; ++c) dot += ld<A>(gp + (long long)c * a.gout.sC) * ld<A>(op + (long long)c * a.HW);
     A keep = (A)1;
     if (a.mask.p) {
         const T* mp = (const T*)a.mask.p + n * a.mask.sN + y * a.mask.sH + x * a.mask.sW;
@@ -65,7 +74,10 @@ __global__ void __launch_bounds__(256) k_bwd_target(const BwdArgs a) {
     ts[1] = clipped ? (A)0 : -dot / d;
 }
 
-// K3b -- source-side gather.
+// K3b -- source-side gather. blockDim = (px, cs): px source pixels, cs channel slices per pixel.
+// Loads are unconditional from always-valid addresses (an out-of-range corner reads element 0 of
+// its plane and is then zeroed by a select): no branches in the channel loop, 4 channels = 20
+// loads in flight per thread.
 template <class T, class TF>
 __global__ void __launch_bounds__(256) k_bwd_source(const BwdArgs a) {
     using A = typename Acc<T>::type;
@@ -88,13 +100,17 @@ __global__ void __launch_bounds__(256) k_bwd_source(const BwdArgs a) {
     const bool vy0 = (unsigned)f.y0 < (unsigned)H, vy1 = (unsigned)y1 < (unsigned)H;
     const bool ok = live && f.finite;                             // softsplat.py:389-390, 460-461
     const bool b[4] = {ok && vx0 && vy0, ok && vx1 && vy0, ok && vx0 && vy1, ok && vx1 && vy1};
+    const bool any = b[0] || b[1] || b[2] || b[3];
     const A w[4] = {f.wnw, f.wne, f.wsw, f.wse};
-    // gradOut offsets of the four corners (strided)
+    // gradOut element offsets of the four corners inside one (n, c) plane; 0 when out of range
     long long go[4];
-    go[0] = (long long)f.y0 * a.gout.sH + (long long)f.x0 * a.gout.sW;
-    go[1] = go[0] + a.gout.sW;
-    go[2] = go[0] + a.gout.sH;
-    go[3] = go[2] + a.gout.sW;
+    {
+        const long long o0 = (long long)f.y0 * a.gout.sH + (long long)f.x0 * a.gout.sW;
+        go[0] = b[0] ? o0 : 0;
+        go[1] = b[1] ? o0 + a.gout.sW : 0;
+        go[2] = b[2] ? o0 + a.gout.sH : 0;
+        go[3] = b[3] ? o0 + a.gout.sH + a.gout.sW : 0;
+    }
 
     A g = (A)1, gprime = (A)1;
     if (a.mode == DCB_MODE_LINEAR || a.mode == DCB_MODE_SOFT) {
@@ -112,29 +128,54 @@ __global__ void __launch_bounds__(256) k_bwd_source(const BwdArgs a) {
         for (int k = 0; k < 4; ++k)
             if (b[k]) { ak[k] = ts[to[k]]; tk[k] = ts[to[k] + 1]; }
     }
-    A wa[4];
+    A wa[4];                                                      // weight * (1 - mask) / D, 0 for dropped corners
 #pragma unroll
     for (int k = 0; k < 4; ++k) wa[k] = b[k] ? w[k] * ak[k] : (A)0;
 
     const T* gp = (const T*)a.gout.p + n * a.gout.sN;
     const T* ip = (const T*)a.in.p + n * a.in.sN + y * a.in.sH + x * a.in.sW;
-    T* gi = a.gin ? (T*)a.gin + (long long)n * a.C * a.HW + r : nullptr;
+    T* gi = (a.gin && live) ? (T*)a.gin + (long long)n * a.C * a.HW + r : nullptr;
+    const bool need_A = (a.gflow != nullptr) || (a.gmetric != nullptr);
 
     A Ak[4] = {(A)0, (A)0, (A)0, (A)0};
-    const bool need_A = (a.gflow != nullptr) || (a.gmetric != nullptr);
-    for (int c = ty; c < a.C; c += a.cs) {
-        const T* gc = gp + c * a.gout.sC;
+    constexpr int U = 4;
+    int c = ty;
+    for (; c + (U - 1) * a.cs < a.C; c += U * a.cs) {
+        A gk[U][4], v[U];
+#pragma unroll
+        for (int j = 0; j < U; ++j) {
+            const T* gc = gp + (long long)(c + j * a.cs) * a.gout.sC;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) gk[j][k] = ld<A>(gc + go[k]);
+            v[j] = need_A ? ld<A>(ip + (long long)(c + j * a.cs) * a.in.sC) : (A)0;
+        }
+#pragma unroll
+        for (int j = 0; j < U; ++j) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) gk[j][k] = b[k] ? gk[j][k] : (A)0;
+            if (gi) {
+                A s = (A)0;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) s = fma_rn(gk[j][k], wa[k], s);
+                st<T, A>(gi + (long long)(c + j * a.cs) * a.HW, s * g);
+            }
+#pragma unroll
+            for (int k = 0; k < 4; ++k) Ak[k] = fma_rn(gk[j][k], v[j], Ak[k]);
+        }
+    }
+    for (; c < a.C; c += a.cs) {
+        const T* gc = gp + (long long)c * a.gout.sC;
         A gk[4];
 #pragma unroll
-        for (int k = 0; k < 4; ++k) gk[k] = b[k] ? ld<A>(gc + go[k]) : (A)0;
-        if (gi && live) {
+        for (int k = 0; k < 4; ++k) { gk[k] = ld<A>(gc + go[k]); gk[k] = b[k] ? gk[k] : (A)0; }
+        if (gi) {
             A s = (A)0;
 #pragma unroll
             for (int k = 0; k < 4; ++k) s = fma_rn(gk[k], wa[k], s);
-            st<T, A>(gi + (long long)c * a.HW, s * g);            // non-finite flow: all b[k] false -> 0
+            st<T, A>(gi + (long long)c * a.HW, s * g);
         }
-        if (need_A && ok) {
-            const A v = ld<A>(ip + c * a.in.sC);
+        if (need_A) {
+            const A v = ld<A>(ip + (long long)c * a.in.sC);
 #pragma unroll
             for (int k = 0; k < 4; ++k) Ak[k] = fma_rn(gk[k], v, Ak[k]);
         }
@@ -159,7 +200,6 @@ __global__ void __launch_bounds__(256) k_bwd_source(const BwdArgs a) {
 #pragma unroll
     for (int k = 0; k < 4; ++k) B[k] = b[k] ? (normalised ? fma_rn(ak[k], Ak[k], tk[k]) : Ak[k]) : (A)0;
 
-    const bool any = b[0] || b[1] || b[2] || b[3];   // a huge finite flow gives inf weights with no corner in range
     if (a.gmetric) {
         A s = (A)0;
 #pragma unroll
@@ -172,9 +212,8 @@ __global__ void __launch_bounds__(256) k_bwd_source(const BwdArgs a) {
         const A ex = sub_rn((A)x1, f.fx), dx = sub_rn(f.fx, (A)f.x0);
         A gx = (B[1] - B[0]) * ey + (B[3] - B[2]) * dy;
         A gy = (B[2] - B[0]) * ex + (B[3] - B[1]) * dx;
-        if (!any) { gx = (A)0; gy = (A)0; }
-        // gradFlow has the dtype of the flow tensor
-        TF* gf = (TF*)a.gflow + (long long)n * 2 * a.HW + r;
+        if (!any) { gx = (A)0; gy = (A)0; }                       // a huge finite flow gives inf weights with no corner in range
+        TF* gf = (TF*)a.gflow + (long long)n * 2 * a.HW + r;      // gradFlow has the dtype of the flow tensor
         st<TF, A>(gf, gx * g);
         st<TF, A>(gf + a.HW, gy * g);
     }

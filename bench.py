@@ -176,10 +176,34 @@ def _extras(torch, d, dev, gen, peak):
         lat = (torch.randn(4, 4, 135, 240, device=dev, generator=gen) * 0.18215).bfloat16()
         met = (-torch.randn(4, 1, 135, 240, device=dev, generator=gen).abs()).bfloat16()
         fl = torch.randn(4, 2, 135, 240, device=dev, generator=gen)
-        ms = _time_cuda(torch, lambda: d.softsplat(lat, fl.bfloat16(), met, "soft"), 200, 20)
+        flb = fl.bfloat16()
+        ms = _time_cuda(torch, lambda: d.softsplat(lat, flb, met, "soft"), 200, 20)
         ms32 = _time_cuda(torch, lambda: d.softsplat(lat, fl, met, "soft"), 200, 20)
+        # the same call replayed from a CUDA graph: device time without the Python/ctypes host path
+        gs = torch.cuda.Stream(); gs.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(gs):
+            d.softsplat(lat, flb, met, "soft")
+            gr = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(gr, stream=gs):
+                d.softsplat(lat, flb, met, "soft")
+        torch.cuda.synchronize()
+        msg = _time_cuda(torch, gr.replay, 200, 20)
         ex["C2_soft_fwd_4x4x135x240_bf16"] = {"us_per_call": round(ms * 1e3, 2), "us_per_call_fp32_flow": round(ms32 * 1e3, 2),
+                                              "us_per_call_cuda_graph": round(msg * 1e3, 2), "launches_per_call": 2,
                                               "mpixel_s": round(4 * 135 * 240 / ms / 1e3, 1)}
+        # the live consumer: the 16 splats of one DualFlowControlNet forward (extractors.py:280-314), batch 2
+        pyr = []
+        for ch, r in ((160, 64), (160, 32), (320, 16), (640, 8)):
+            feat = torch.randn(2, ch, r, r, device=dev, generator=gen); f_ = torch.randn(2, 2, r, r, device=dev, generator=gen) * 0.3
+            m_ = torch.randn(2, 1, r, r, device=dev, generator=gen) * 0.1
+            pyr.append((feat, f_, -f_, m_))
+        def pyramid():
+            for feat, ff, fb, m_ in pyr:
+                of = d.compute_mask(ff, fb); ob = d.compute_mask(fb, ff)
+                d.softsplat(feat, ff, m_, "soft"); d.softsplat(feat, fb, m_, "soft")
+        with torch.no_grad():
+            msp = _time_cuda(torch, pyramid, 50, 10)
+        ex["controlnet_pyramid_16_splats_batch2_f32"] = {"us_per_forward": round(msp * 1e3, 1), "us_per_splat": round(msp * 1e3 / 16, 2)}
         # C3: 64-frame 1080p warp + residual: fused splat recipe and backwarp + residual
         n3 = 64
         img = torch.rand(n3, 3, H, W, device=dev, generator=gen); gt = torch.rand(n3, 3, H, W, device=dev, generator=gen)

@@ -38,6 +38,7 @@ class DcbTensor(ctypes.Structure):
 
 
 _P = ctypes.POINTER(DcbTensor)
+_I64x4 = ctypes.c_int64 * 4
 _lib = None
 _lock = threading.Lock()
 
@@ -116,16 +117,29 @@ def desc(t: torch.Tensor | None):
         raise AssertionError(f"expected a 4-d NCHW tensor, got {tuple(t.shape)}")
     if t.dtype not in _DTYPES:
         raise ValueError(f"unsupported dtype {t.dtype}: float32, bfloat16 and float64 are implemented")
-    d = DcbTensor()
-    d.ptr = t.data_ptr()
-    d.dtype = _DTYPES[t.dtype]
-    d.size[:] = list(t.shape)
-    d.stride[:] = list(t.stride())
-    return ctypes.byref(d)
+    return ctypes.byref(DcbTensor(t.data_ptr(), _DTYPES[t.dtype], 0, _I64x4(*t.shape), _I64x4(*t.stride())))
 
 
 def stream_ptr(device) -> int:
     return torch.cuda.current_stream(device).cuda_stream
+
+
+class on_device:
+    """`with on_device(dev):` -- torch.cuda.device(dev) only when dev is not already current (the
+    context manager costs ~5 us, more than the kernels of a latent-sized call)."""
+    __slots__ = ("ctx",)
+
+    def __init__(self, dev):
+        self.ctx = None if torch.cuda.current_device() == dev.index else torch.cuda.device(dev)
+
+    def __enter__(self):
+        if self.ctx is not None:
+            self.ctx.__enter__()
+
+    def __exit__(self, *exc):
+        if self.ctx is not None:
+            self.ctx.__exit__(*exc)
+        return False
 
 
 # -------------------------------------------------------------------------------------------------
@@ -138,8 +152,8 @@ def stream_ptr(device) -> int:
 _workspaces: dict = {}
 
 
-def workspace(device: torch.device, nbytes: int, kind: str) -> torch.Tensor:
-    key = (kind, device.index, stream_ptr(device))
+def workspace(device: torch.device, nbytes: int, kind: str, stream: int | None = None) -> torch.Tensor:
+    key = (kind, device.index, stream if stream is not None else stream_ptr(device))
     buf = _workspaces.get(key)
     if buf is None or buf.numel() < nbytes:
         buf = torch.zeros(max(int(nbytes), 1 << 20), dtype=torch.uint8, device=device)

@@ -46,7 +46,7 @@ def compute_mask(flow_bwd_tensor, flow_fwd_tensor):
         mask = torch.empty((n, 1, h, w), dtype=a.dtype, device=dev)
         need = lib.dcb_occlusion_mask_workspace_bytes(n, h, w)
         ws = _lib.workspace(dev, need, "acc")
-        with torch.cuda.device(dev):
+        with _lib.on_device(dev):
             rc = lib.dcb_occlusion_mask(_lib.desc(a), _lib.desc(b), _lib.desc(mask), ws.data_ptr(), ws.numel(),
                                         _lib.FLAG_WS_CLEAN, _lib.stream_ptr(dev))
         if rc != 0:

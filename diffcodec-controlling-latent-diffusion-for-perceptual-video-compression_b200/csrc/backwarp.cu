@@ -74,24 +74,38 @@ __global__ void __launch_bounds__(256) k_backwarp_fwd(const WarpArgs a) {
     const unsigned n = p / a.HW, r = p - n * a.HW;
     const int y = (int)(r / (unsigned)a.W), x = (int)(r - (unsigned)y * (unsigned)a.W);
     const TF* fp = (const TF*)a.flow.p + n * a.flow.sN + y * a.flow.sH + x * a.flow.sW;
-    const Tap<A> t = make_tap<A>(x, y, ld<A>(fp), ld<A>(fp + a.flow.sC), a.W, a.H, a.align);
+    const Tap<A> t = make_tap<A>(x, y, (A)ld_stream(fp), (A)ld_stream(fp + a.flow.sC), a.W, a.H, a.align);
 
-    const T* im = (const T*)a.image.p + n * a.image.sN + (long long)t.y0 * a.image.sH + (long long)t.x0 * a.image.sW;
-    const long long o1 = a.image.sW, o2 = a.image.sH, o3 = a.image.sH + a.image.sW;
+    // tap offsets inside one (n, c) plane; an out-of-range tap reads element 0 and is zeroed by its weight
+    const long long o0 = (long long)t.y0 * a.image.sH + (long long)t.x0 * a.image.sW;
+    const long long to[4] = {t.b[0] ? o0 : 0, t.b[1] ? o0 + a.image.sW : 0, t.b[2] ? o0 + a.image.sH : 0,
+                             t.b[3] ? o0 + a.image.sH + a.image.sW : 0};
+    const A tw[4] = {t.wnw, t.wne, t.wsw, t.wse};
+    const T* im = (const T*)a.image.p + n * a.image.sN;
     const T* gt = a.gt.p ? (const T*)a.gt.p + n * a.gt.sN + y * a.gt.sH + x * a.gt.sW : nullptr;
     T* wp = (T*)a.warped + (long long)n * a.C * a.HW + r;
     T* rp = a.residual ? (T*)a.residual + (long long)n * a.C * a.HW + r : nullptr;
-    for (int c = 0; c < a.C; ++c, im += a.image.sC) {
-        A acc = (A)0;
-        if (t.b[0]) acc = fma_rn(ld<A>(im), t.wnw, acc);
-        if (t.b[1]) acc = fma_rn(ld<A>(im + o1), t.wne, acc);
-        if (t.b[2]) acc = fma_rn(ld<A>(im + o2), t.wsw, acc);
-        if (t.b[3]) acc = fma_rn(ld<A>(im + o3), t.wse, acc);
-        st<T, A>(wp + (long long)c * a.HW, acc);
-        if (rp) {
-            // residual of the value as stored (rounded to T), like `gt - warped` on the stored tensor
-            const A stored = ld<A>(wp + (long long)c * a.HW);
-            st<T, A>(rp + (long long)c * a.HW, sub_rn(ld<A>(gt + c * a.gt.sC), stored));
+    constexpr int U = 4;                                  // channels in flight: 16 taps + 4 gt loads
+    for (int c0 = 0; c0 < a.C; c0 += U) {
+        A v[U][4], gv[U];
+#pragma unroll
+        for (int j = 0; j < U; ++j) {
+            const int c = c0 + j < a.C ? c0 + j : a.C - 1;
+            const T* pl = im + (long long)c * a.image.sC;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) v[j][k] = ld<A>(pl + to[k]);      // the image is re-read by neighbours: keep it cached
+            gv[j] = gt ? (A)ld_stream(gt + (long long)c * a.gt.sC) : (A)0;
+        }
+#pragma unroll
+        for (int j = 0; j < U; ++j) {
+            if (c0 + j < a.C) {
+                A acc = (A)0;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) acc = t.b[k] ? fma_rn(v[j][k], tw[k], acc) : acc;   // grid_sample's tap order and fma chain
+                st_stream(wp + (long long)(c0 + j) * a.HW, acc);
+                // residual of the value as stored (rounded to T), like `gt - warped` on the stored tensor
+                if (rp) st_stream(rp + (long long)(c0 + j) * a.HW, sub_rn(gv[j], round_as<T>(acc)));
+            }
         }
     }
 }

@@ -88,6 +88,12 @@ template <> __device__ __forceinline__ void st<__nv_bfloat16, float>(__nv_bfloat
 // streaming variants (ld.global.cs / st.global.cs: evict-first in L1 and L2) for data touched once:
 // they keep the inputs / outputs from pushing the fp32 accumulators out of L2
 __device__ __forceinline__ float ld_stream(const float* p) { return __ldcs(p); }
+__device__ __forceinline__ double ld_stream(const double* p) { return __ldcs(p); }
+__device__ __forceinline__ void st_stream(double* p, double v) { __stcs(p, v); }
+// the value a store of `v` into a T would leave behind
+template <class T> __device__ __forceinline__ float round_as(float v) { return v; }
+template <> __device__ __forceinline__ float round_as<__nv_bfloat16>(float v) { return __bfloat162float(__float2bfloat16_rn(v)); }
+template <class T> __device__ __forceinline__ double round_as(double v) { return v; }
 __device__ __forceinline__ float ld_stream(const __nv_bfloat16* p) { return __bfloat162float(__ldcs(p)); }
 __device__ __forceinline__ void st_stream(float* p, float v) { __stcs(p, v); }
 __device__ __forceinline__ void st_stream(__nv_bfloat16* p, float v) { __stcs(p, __float2bfloat16_rn(v)); }

@@ -67,7 +67,7 @@ def residual_conditioning(image1, flow1, flow2, gt, variant: str = "dataset", re
         occ_bwd = torch.empty_like(occ_fwd)
         need = lib.dcb_residual_workspace_bytes(n, c, h, w)
         ws = _lib.workspace(dev, need, "acc")
-        with torch.cuda.device(dev):
+        with _lib.on_device(dev):
             rc = lib.dcb_residual_fused(_lib.desc(image1), _lib.desc(flow1), _lib.desc(flow2), _lib.desc(gt),
                                         _lib.desc(fused), _lib.desc(residual), _lib.desc(occ_fwd), _lib.desc(occ_bwd),
                                         ws.data_ptr(), ws.numel(), _VARIANTS[variant], _lib.FLAG_WS_CLEAN,

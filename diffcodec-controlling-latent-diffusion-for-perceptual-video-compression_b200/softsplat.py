@@ -33,6 +33,7 @@ _MODES = {"sum": _lib.MODE_SUM, "avg": _lib.MODE_AVG, "linear": _lib.MODE_LINEAR
 _EPS = {"addeps": _lib.EPS_ADD, "zeroeps": _lib.EPS_ZERO, "clipeps": _lib.EPS_CLIP}
 
 _state = threading.local()
+_ws_sizes: dict = {}
 
 
 def is_deterministic() -> bool:
@@ -80,19 +81,23 @@ def _forward(tenIn, tenFlow, tenMetric, mask, mode: int, eps: int, det: bool, wa
     dt = _lib._DTYPES.get(tenIn.dtype)
     if dt is None:
         raise ValueError(f"softsplat: unsupported dtype {tenIn.dtype} (float32, bfloat16, float64)")
-    need = lib.dcb_splat_fwd_workspace_bytes(n, c, h, w, dt, mode, flags)
+    key = (n, c, h, w, dt, mode, flags)
+    need = _ws_sizes.get(key)
+    if need is None:
+        need = _ws_sizes[key] = lib.dcb_splat_fwd_workspace_bytes(n, c, h, w, dt, mode, flags)
+    stream = _lib.stream_ptr(dev)
     ws, ws_ptr = None, None
     if need > 0:
         if det:
-            ws = _lib.workspace(dev, need, "scratch")
+            ws = _lib.workspace(dev, need, "scratch", stream)
         else:
-            ws = _lib.workspace(dev, need, "acc")
+            ws = _lib.workspace(dev, need, "acc", stream)
             flags |= _lib.FLAG_WS_CLEAN
         ws_ptr = ws.data_ptr()
-    with torch.cuda.device(dev):
+    with _lib.on_device(dev):
         rc = lib.dcb_splat_fwd(_lib.desc(tenIn), _lib.desc(tenFlow), _lib.desc(tenMetric), _lib.desc(out),
                                _lib.desc(norm), _lib.desc(mask), ws_ptr, ws.numel() if ws is not None else 0,
-                               mode, eps, flags, _lib.stream_ptr(dev))
+                               mode, eps, flags, stream)
     if rc != 0:
         _lib.invalidate_acc(dev)
     _lib.check(rc, "dcb_splat_fwd")
@@ -108,7 +113,7 @@ def _backward(gout, tenIn, tenFlow, tenMetric, out, norm, mask, mode: int, eps: 
     gmetric = torch.empty((n, 1, h, w), dtype=tenIn.dtype, device=dev) if (need[2] and tenMetric is not None) else None
     nbytes = lib.dcb_splat_bwd_workspace_bytes(n, c, h, w, _lib._DTYPES[tenIn.dtype], mode, 0)
     ws = _lib.workspace(dev, nbytes, "scratch") if (mode != _lib.MODE_SUM and nbytes > 0) else None
-    with torch.cuda.device(dev):
+    with _lib.on_device(dev):
         rc = lib.dcb_splat_bwd(_lib.desc(gout), _lib.desc(tenIn), _lib.desc(tenFlow), _lib.desc(tenMetric),
                                _lib.desc(out), _lib.desc(norm), _lib.desc(mask), _lib.desc(gin), _lib.desc(gflow),
                                _lib.desc(gmetric), ws.data_ptr() if ws is not None else None,
@@ -179,8 +184,23 @@ class _splat_mode_func(torch.autograd.Function):
         return gin, gflow, gmetric, None, None, None
 
 
+def _needs_autograd(*tensors) -> bool:
+    return torch.is_grad_enabled() and any(t is not None and t.requires_grad for t in tensors)
+
+
 def _splat_normalised(tenIn, tenFlow, tenMetric, mode: int, eps: int, mask=None):
-    return _splat_mode_func.apply(tenIn, tenFlow, tenMetric, mask, mode, eps)
+    if _needs_autograd(tenIn, tenFlow, tenMetric) or torch.is_autocast_enabled("cuda"):
+        return _splat_mode_func.apply(tenIn, tenFlow, tenMetric, mask, mode, eps)
+    # inference fast path: same kernels, no autograd.Function / custom_fwd bookkeeping (~15 us per call)
+    _check_inputs(tenIn, tenFlow)
+    tenFlow = _match_flow(tenIn, tenFlow)
+    if tenMetric is not None:
+        assert tenMetric.shape == (tenIn.shape[0], 1, tenIn.shape[2], tenIn.shape[3]), "tenMetric must be [N,1,H,W]"
+        if tenMetric.dtype != tenIn.dtype:
+            tenMetric = tenMetric.to(tenIn.dtype)
+    if mask is not None and mask.dtype != tenIn.dtype:
+        mask = mask.to(tenIn.dtype)
+    return _forward(tenIn, tenFlow, tenMetric, mask, mode, eps, is_deterministic(), False)[0]
 
 
 def softsplat(tenIn: torch.Tensor, tenFlow: torch.Tensor, tenMetric: torch.Tensor, strMode: str):
@@ -196,7 +216,10 @@ def softsplat(tenIn: torch.Tensor, tenFlow: torch.Tensor, tenMetric: torch.Tenso
     if parts[0] == "soft": assert tenMetric is not None                        # softsplat.py:238
 
     if strMode == "sum":
-        return softsplat_func.apply(tenIn, tenFlow)
+        if _needs_autograd(tenIn, tenFlow) or torch.is_autocast_enabled("cuda"):
+            return softsplat_func.apply(tenIn, tenFlow)
+        _check_inputs(tenIn, tenFlow)
+        return _forward(tenIn, _match_flow(tenIn, tenFlow), None, None, _lib.MODE_SUM, _lib.EPS_ADD, is_deterministic(), False)[0]
 
     if parts[0] in ("sum", "avg") and strMode != parts[0]:
         # Reference quirk kept on purpose: 'avg-<eps>' / 'sum-<eps>' fail the exact-match tests of

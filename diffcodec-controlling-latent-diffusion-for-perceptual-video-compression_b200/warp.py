@@ -32,7 +32,7 @@ class _backwarp_func(torch.autograd.Function):
         dev = image.device
         warped = torch.empty(image.shape, dtype=image.dtype, device=dev)
         residual = torch.empty_like(warped) if gt is not None else None
-        with torch.cuda.device(dev):
+        with _lib.on_device(dev):
             rc = lib.dcb_backwarp_fwd(_lib.desc(image), _lib.desc(flow), _lib.desc(gt), _lib.desc(warped),
                                       _lib.desc(residual), int(bool(align_corners)), _lib.stream_ptr(dev))
         _lib.check(rc, "dcb_backwarp_fwd")
@@ -56,7 +56,7 @@ class _backwarp_func(torch.autograd.Function):
         gflow = torch.empty((n, 2, h, w), dtype=flow.dtype, device=dev) if ctx.needs_input_grad[1] else None
         need = lib.dcb_backwarp_bwd_workspace_bytes(n, c, h, w, _lib._DTYPES[image.dtype]) if gimage is not None else 0
         ws = _lib.workspace(dev, need, "scratch") if need > 0 else None
-        with torch.cuda.device(dev):
+        with _lib.on_device(dev):
             rc = lib.dcb_backwarp_bwd(_lib.desc(g), _lib.desc(image), _lib.desc(flow), _lib.desc(gimage),
                                       _lib.desc(gflow), ctx.align, ws.data_ptr() if ws is not None else None,
                                       ws.numel() if ws is not None else 0, _lib.stream_ptr(dev))

@@ -235,6 +235,33 @@ def _extras(torch, d, dev, gen, peak):
     return ex
 
 
+def _uvg_sweep(torch, d, dev, rank, world, peak, gops_per_chunk=16):
+    """C5: the UVG-shaped synthetic 1080p sweep (7 sequences, 3900 frames, 975 GOP-4 units, 2925 inter
+    frames), GOPs sharded round-robin over the ranks, the conditioning recipe (a-7) per inter frame.
+    Inputs are generated on the device per chunk from the GOP seed (untimed); only the recipe is timed."""
+    units = d.shard_units(d.enumerate_gops(), rank, world)
+    ev_a, ev_b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    total_ms, frames, digest = 0.0, 0, 0.0
+    for i in range(0, len(units), gops_per_chunk):
+        chunk = units[i:i + gops_per_chunk]
+        n = sum(u.inter_frames for u in chunk)
+        gen = torch.Generator(device=dev).manual_seed(chunk[0].seed())
+        img = torch.rand(n, 3, H, W, device=dev, generator=gen); gt = torch.rand(n, 3, H, W, device=dev, generator=gen)
+        f1 = _smooth_flow(torch, n, H, W, 8.0, dev, gen); f2 = -f1 + 0.5 * _smooth_flow(torch, n, H, W, 1.0, dev, gen)
+        if i == 0:
+            d.residual_conditioning(img, f1, f2, gt, "dataset")          # warm-up, untimed
+        torch.cuda.synchronize()
+        ev_a.record()
+        fused, res = d.residual_conditioning(img, f1, f2, gt, "dataset")
+        ev_b.record(); torch.cuda.synchronize()
+        total_ms += ev_a.elapsed_time(ev_b); frames += n
+        digest += float(res[:, :, ::64, ::64].double().sum())
+        del img, gt, f1, f2, fused, res
+    return {"gops": len(units), "inter_frames": frames, "ms": round(total_ms, 2), "frames_per_s": round(frames / total_ms * 1e3, 1),
+            "mpixel_s": round(frames * H * W / total_ms / 1e3, 1), "alg_gbs": round(64 * frames * H * W / total_ms / 1e6, 1),
+            "frac_of_peak": round(64 * frames * H * W / total_ms / 1e6 / peak, 3), "digest": round(digest, 3)}
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -338,6 +365,10 @@ def run_ours(args):
             del tin, metric, flow, out
             torch.cuda.empty_cache()
             line["extra"] = _extras(torch, d, dev, gen, peak)
+            try:
+                line["extra"]["C5_uvg_sweep_recipe_2925x1080p_f32"] = _uvg_sweep(torch, d, dev, 0, 1, peak)
+            except Exception as e:
+                line["extra"]["C5_uvg_sweep_recipe_2925x1080p_f32"] = {"error": repr(e)}
         print(json.dumps(line))
     if world > 1:
         dist.barrier()

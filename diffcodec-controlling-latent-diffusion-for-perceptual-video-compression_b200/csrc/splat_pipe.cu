@@ -31,7 +31,7 @@
 
 namespace dcb {
 
-constexpr int kPipeThreads = 128;           // 4 independent warps per CTA
+constexpr int kPipeThreads = 32;            // one warp per CTA: the item index is blockIdx-uniform, so every shuffle is provably convergent
 constexpr int kWarpsPerCta = kPipeThreads / 32;
 #ifndef DCB_KROWS
 #define DCB_KROWS 4
@@ -40,14 +40,23 @@ constexpr int kWarpsPerCta = kPipeThreads / 32;
 #define DCB_KPASSES 1
 #endif
 #ifndef DCB_MINCTAS
-#define DCB_MINCTAS 8
+#define DCB_MINCTAS 32
 #endif
 constexpr int kRows = DCB_KROWS;            // rows loaded at once by a warp
 constexpr int kPasses = DCB_KPASSES;        // consecutive row groups per strip (the vertical carry spans them)
 constexpr int kMinCtas = DCB_MINCTAS;       // register budget: 64 per thread -> 32 warps per SM
 constexpr int kStripH = kRows * kPasses;    // a scatter item: 32 columns x 16 rows
-constexpr int kNPer = 8;                    // normalise: pixels per lane per batch
-constexpr int kNBatches = 2;
+#ifndef DCB_NPER
+#define DCB_NPER 8
+#endif
+#ifndef DCB_NBATCH
+#define DCB_NBATCH 2
+#endif
+#ifndef DCB_INTERLEAVE
+#define DCB_INTERLEAVE 0
+#endif
+constexpr int kNPer = DCB_NPER;             // normalise: pixels per lane per batch
+constexpr int kNBatches = DCB_NBATCH;
 constexpr int kChunk = 32 * kNPer * kNBatches;   // a normalise item: 512 target pixels
 constexpr float kExp1 = 2.7182817459106445f;     // expf(1.0f): what tenMetric.exp() yields for an all-ones metric
 constexpr long long kGroupBytes = 34ll << 20;    // accumulator bytes per ring slot (one 1080p frame = 31.6 MiB)
@@ -286,19 +295,29 @@ __device__ __forceinline__ void mask_chunk(const PipeArgs& a, int frame, int chu
 // ---------------------------------------------------------------------------------------------
 template <class T, class TF, int MODE, int CA>
 __global__ void __launch_bounds__(kPipeThreads, kMinCtas) k_splat_step(const __grid_constant__ PipeArgs a) {
-    const int lane = threadIdx.x & 31;
-    const unsigned item = blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5);
-    const unsigned n_items = (unsigned)a.n_frames * a.tn;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const unsigned n_items = (unsigned)a.n_frames * a.tn, s_items = (unsigned)a.s_frames * a.ts;
+    const unsigned n_ctas = (n_items + kWarpsPerCta - 1) / kWarpsPerCta;      // grid = n_ctas + s_ctas
+    unsigned b = blockIdx.x;
+#if DCB_INTERLEAVE
+    {   // alternate normalise and scatter CTAs so that both kinds of work run from the first wave on
+        const unsigned s_ctas = gridDim.x - n_ctas;
+        const unsigned pairs = n_ctas < s_ctas ? n_ctas : s_ctas;
+        if (b < 2 * pairs) b = (b & 1) ? n_ctas + (b >> 1) : (b >> 1);
+        else b = (n_ctas > s_ctas ? 0u : n_ctas) + pairs + (b - 2 * pairs);   // the longer list's tail
+    }
+#endif
     const size_t slot_floats = (size_t)a.G * a.HW * 4;
-    if (item < n_items) {
-        if (a.dbg & 4) return;
+    if (b < n_ctas) {
+        const unsigned item = b * kWarpsPerCta + warp;
+        if (item >= n_items || (a.dbg & 4)) return;
         const int f = a.n_frame0 + item / a.tn, chunk = item % a.tn;
         float* acc = a.acc + (size_t)((f / a.G) & 1) * slot_floats + (size_t)(f % a.G) * a.HW * 4;
         if (a.epi == 1) mask_chunk<T>(a, f, chunk, acc, lane);
         else normalize_chunk<T, MODE, CA>(a, f, chunk, acc, lane);
     } else {
-        const unsigned s = item - n_items;
-        if (s >= (unsigned)a.s_frames * a.ts || (a.dbg & 8)) return;
+        const unsigned s = (b - n_ctas) * kWarpsPerCta + warp;
+        if (s >= s_items || (a.dbg & 8)) return;
         const int f = a.s_frame0 + s / a.ts, strip = s % a.ts;
         float* acc = a.acc + (size_t)((f / a.G) & 1) * slot_floats + (size_t)(f % a.G) * a.HW * 4;
         scatter_strip<T, TF, MODE, CA>(a, f, strip, acc, lane);
@@ -322,17 +341,59 @@ long long pipe_acc_bytes(long long N, long long H, long long W) {
 
 long long pipe_workspace(long long N, long long H, long long W) { return pipe_acc_bytes(N, H, W); }
 
+// Optional (DCB_L2_PERSIST=1): reserve part of L2 for persisting lines, once per process. This is
+// device-wide state, so it is opt-in; without it the kernels rely on the streaming hints alone.
+static long long persisting_budget() {
+    static long long budget = -1;
+    if (budget < 0) {
+        budget = 0;
+        const char* e = getenv("DCB_L2_PERSIST");
+        if (e && atoi(e) > 0) {
+            int dev = 0, max_persist = 0;
+            if (cudaGetDevice(&dev) == cudaSuccess &&
+                cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, dev) == cudaSuccess && max_persist > 0 &&
+                cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, (size_t)max_persist) == cudaSuccess)
+                budget = max_persist;
+            (void)cudaGetLastError();
+        }
+    }
+    return budget;
+}
+
 template <class T, class TF, int MODE, int CA> static int launch_steps(PipeArgs& a, cudaStream_t st) {
     const int groups = (a.N + a.G - 1) / a.G;
+    long long persist_bytes = 0;
+    if (groups > 1 && persisting_budget() > 0) {
+        persist_bytes = 2ll * a.G * a.HW * 16;
+        if (persist_bytes > persisting_budget()) persist_bytes = persisting_budget();
+    }
     for (int k = 0; k <= groups; ++k) {
         a.s_frame0 = k * a.G;
         a.s_frames = k < groups ? (a.N - a.s_frame0 < a.G ? a.N - a.s_frame0 : a.G) : 0;
         a.n_frame0 = (k - 1) * a.G;
         a.n_frames = k > 0 ? (a.N - a.n_frame0 < a.G ? a.N - a.n_frame0 : a.G) : 0;
-        const long long items = (long long)a.n_frames * a.tn + (long long)a.s_frames * a.ts;
-        const unsigned grid = (unsigned)((items + kWarpsPerCta - 1) / kWarpsPerCta);
-        k_splat_step<T, TF, MODE, CA><<<grid, kPipeThreads, 0, st>>>(a);
-        DCB_CHECK_LAUNCH("k_splat_step");
+        const long long n_ctas = ((long long)a.n_frames * a.tn + kWarpsPerCta - 1) / kWarpsPerCta;
+        const long long s_ctas = ((long long)a.s_frames * a.ts + kWarpsPerCta - 1) / kWarpsPerCta;
+        const unsigned grid = (unsigned)(n_ctas + s_ctas);
+        if (persist_bytes > 0) {
+            // per-launch L2 access-policy window over the accumulator ring: those lines are the only
+            // data of the step that is reused, everything else streams through once
+            cudaLaunchConfig_t cfg = {};
+            cfg.gridDim = dim3(grid); cfg.blockDim = dim3(kPipeThreads); cfg.dynamicSmemBytes = 0; cfg.stream = st;
+            cudaLaunchAttribute attr[1];
+            attr[0].id = cudaLaunchAttributeAccessPolicyWindow;
+            attr[0].val.accessPolicyWindow.base_ptr = a.acc;
+            attr[0].val.accessPolicyWindow.num_bytes = (size_t)persist_bytes;
+            attr[0].val.accessPolicyWindow.hitRatio = 1.0f;
+            attr[0].val.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+            attr[0].val.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+            cfg.attrs = attr; cfg.numAttrs = 1;
+            DCB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, k_splat_step<T, TF, MODE, CA>, a));
+            count_launch();
+        } else {
+            k_splat_step<T, TF, MODE, CA><<<grid, kPipeThreads, 0, st>>>(a);
+            DCB_CHECK_LAUNCH("k_splat_step");
+        }
     }
     return DCB_OK;
 }

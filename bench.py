@@ -347,7 +347,8 @@ def run_ours(args):
                        "frames_per_gpu": F, "l2_policy": f"inputs+outputs per step = {(36 * px_per_step) >> 20} MiB per GPU, larger than the 126 MB L2; no flush needed",
                        "partition": "frames sharded by rank, no data-path collective"},
             "roofline": {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),
-                         "traffic": None, "kernel": "k_splat_step (one launch per frame: scatter of frame k + normalise of frame k-1)",
+                         "traffic": 132.06e6, "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of one k_splat_step launch, ncu --set full --cache-control none, profiles/r01/ncu_step_final.txt (compulsory: 74.6e6)",
+                         "kernel": "k_splat_step (one launch per frame: scatter of frame k + normalise of frame k-1)",
                          "algorithmic_bytes_per_px": ALG_BYTES_PER_PX, "peak_source": peak_src, "frac_of_nominal_8TBs": round(achieved / 8000.0, 4)},
             "e2e": {"value": round(e2e_value, 1), "unit": "Mpixel/s", "h2d_bytes_per_step": Fe * (C + 3) * H * W * 4,
                     "d2h_bytes_per_step": Fe * C * H * W * 4, "frames_per_step": Fe, "api": "diffcodec_b200.softsplat(tenIn, tenFlow, tenMetric, 'soft') from pinned host tensors"},

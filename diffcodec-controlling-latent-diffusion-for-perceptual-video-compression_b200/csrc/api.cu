@@ -50,6 +50,11 @@ long long recipe_workspace(long long N, long long H, long long W);
 int occlusion_mask_impl(const DcbTensor*, const DcbTensor*, const DcbTensor*, void*, long long, int, cudaStream_t);
 int residual_fused_impl(const DcbTensor*, const DcbTensor*, const DcbTensor*, const DcbTensor*, const DcbTensor*,
                         const DcbTensor*, const DcbTensor*, const DcbTensor*, void*, long long, int, int, cudaStream_t);
+int bidir_fuse_fwd_impl(const DcbTensor*, const DcbTensor*, const DcbTensor*, const DcbTensor*, const DcbTensor*,
+                        const DcbTensor*, const DcbTensor*, cudaStream_t);
+int bidir_fuse_bwd_impl(const DcbTensor*, const DcbTensor*, const DcbTensor*, const DcbTensor*, const DcbTensor*,
+                        const DcbTensor*, const DcbTensor*, const DcbTensor*, const DcbTensor*, const DcbTensor*,
+                        const DcbTensor*, cudaStream_t);
 
 // ---------------------------------------------------------------------------------------------
 // validation helpers
@@ -121,8 +126,8 @@ int64_t dcb_launch_count(void) { return (int64_t)g_launches.load(); }
 const char* dcb_build_info(void) {
     return "libdiffcodec_b200 " __DATE__ " nvcc " DCB_STR(__CUDACC_VER_MAJOR__) "." DCB_STR(__CUDACC_VER_MINOR__)
            " target sm_100a; kernels: k_scatter_planar k_scatter_vec4 k_normalize k_bwd_target k_bwd_source "
-           "k_splat_pipe k_backwarp_fwd k_backwarp_bwd k_mask_scatter k_mask_epilogue k_recipe_scatter k_recipe_epilogue "
-           "k_det_count k_det_scan k_det_fill k_det_reduce";
+           "k_backwarp_fwd k_backwarp_bwd k_mask_scatter k_mask_epilogue k_recipe_scatter k_recipe_epilogue "
+           "k_planar_step k_splat_step k_recipe_fuse k_bidir_fuse_fwd k_bidir_fuse_bwd k_det_emit k_det_reduce";
 }
 
 int64_t dcb_splat_fwd_workspace_bytes(int64_t N, int64_t C, int64_t H, int64_t W, int32_t dtype, int32_t mode, int32_t flags) {
@@ -325,6 +330,57 @@ int dcb_residual_fused(const DcbTensor* image1, const DcbTensor* flow1, const Dc
     TRY(check_out(fn, "occ_bwd", occ_bwd, dt, elem_size(dt)));
     return residual_fused_impl(image1, flow1, flow2, gt, fused, residual, occ_fwd, occ_bwd, ws, ws_bytes, variant, flags,
                                (cudaStream_t)stream);
+}
+
+static int check_fuse_common(const char* fn, const DcbTensor* A, const DcbTensor* B, const DcbTensor* ca, const DcbTensor* cb,
+                             const DcbTensor* oa, const DcbTensor* ob) {
+    TRY(check_tensor(fn, "A", A, true));
+    TRY(check_tensor(fn, "B", B, true));
+    TRY(check_tensor(fn, "conf_a", ca, true));
+    TRY(check_tensor(fn, "conf_b", cb, true));
+    TRY(check_tensor(fn, "occ_a", oa, false));
+    TRY(check_tensor(fn, "occ_b", ob, false));
+    if ((oa == nullptr) != (ob == nullptr)) return set_error(DCB_E_NULL, "%s: occ_a and occ_b go together", fn);
+    const long long N = A->size[0], C = A->size[1], H = A->size[2], W = A->size[3];
+    TRY(check_limits(fn, A));
+    TRY(check_shape(fn, "B", B, N, C, H, W));
+    TRY(check_shape(fn, "conf_a", ca, N, 1, H, W));
+    TRY(check_shape(fn, "conf_b", cb, N, 1, H, W));
+    TRY(check_shape(fn, "occ_a", oa, N, 1, H, W));
+    TRY(check_shape(fn, "occ_b", ob, N, 1, H, W));
+    const int dt = A->dtype;
+    if (B->dtype != dt || ca->dtype != dt || cb->dtype != dt || (oa && (oa->dtype != dt || ob->dtype != dt)))
+        return set_error(DCB_E_DTYPE, "%s: all tensors must share one dtype", fn);
+    return DCB_OK;
+}
+
+int dcb_bidir_fuse_fwd(const DcbTensor* A, const DcbTensor* B, const DcbTensor* ca, const DcbTensor* cb,
+                       const DcbTensor* oa, const DcbTensor* ob, const DcbTensor* fused, void* stream) {
+    const char* fn = "dcb_bidir_fuse_fwd";
+    TRY(check_fuse_common(fn, A, B, ca, cb, oa, ob));
+    TRY(check_tensor(fn, "fused", fused, true));
+    TRY(check_shape(fn, "fused", fused, A->size[0], A->size[1], A->size[2], A->size[3]));
+    TRY(check_out(fn, "fused", fused, A->dtype, elem_size(A->dtype)));
+    return bidir_fuse_fwd_impl(A, B, ca, cb, oa, ob, fused, (cudaStream_t)stream);
+}
+
+int dcb_bidir_fuse_bwd(const DcbTensor* g, const DcbTensor* A, const DcbTensor* B, const DcbTensor* ca, const DcbTensor* cb,
+                       const DcbTensor* oa, const DcbTensor* ob, const DcbTensor* gA, const DcbTensor* gB,
+                       const DcbTensor* gca, const DcbTensor* gcb, void* stream) {
+    const char* fn = "dcb_bidir_fuse_bwd";
+    TRY(check_fuse_common(fn, A, B, ca, cb, oa, ob));
+    TRY(check_tensor(fn, "grad_fused", g, true));
+    const long long N = A->size[0], C = A->size[1], H = A->size[2], W = A->size[3];
+    TRY(check_shape(fn, "grad_fused", g, N, C, H, W));
+    if (g->dtype != A->dtype) return set_error(DCB_E_DTYPE, "%s: grad_fused dtype differs", fn);
+    const DcbTensor* outs[4] = {gA, gB, gca, gcb};
+    const char* names[4] = {"grad_A", "grad_B", "grad_conf_a", "grad_conf_b"};
+    for (int i = 0; i < 4; ++i) {
+        TRY(check_tensor(fn, names[i], outs[i], false));
+        TRY(check_shape(fn, names[i], outs[i], N, i < 2 ? C : 1, H, W));
+        TRY(check_out(fn, names[i], outs[i], A->dtype, elem_size(A->dtype)));
+    }
+    return bidir_fuse_bwd_impl(g, A, B, ca, cb, oa, ob, gA, gB, gca, gcb, (cudaStream_t)stream);
 }
 
 }  // extern "C"

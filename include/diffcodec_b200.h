@@ -181,6 +181,21 @@ int dcb_residual_fused(const DcbTensor* image1, const DcbTensor* flow1, const Dc
                        void* workspace, int64_t workspace_bytes,
                        int32_t variant, int32_t flags, void* stream);
 
+/*
+ * Confidence fusion of the two warped maps of a bi-directional block, without the host sync.
+ * Replaces controlnet/extractors.py:298-310 (also :193-205 and controlnet/residual_utils.py:181-193):
+ *   conf = clamp(cat(conf_a, conf_b), min=0); w = conf / (conf.sum(1) + 1e-6);
+ *   fused = w0 * A + w1 * B;  where (occ_a + occ_b) > 1.5: fused = 0.5 * (A + B)
+ * A, B [N,C,H,W]; conf_a, conf_b, occ_a, occ_b [N,1,H,W] (occ_* both NULL = no hole branch);
+ * fused [N,C,H,W] contiguous. The backward fills grad_A, grad_B, grad_conf_a, grad_conf_b (any NULL).
+ */
+int dcb_bidir_fuse_fwd(const DcbTensor* A, const DcbTensor* B, const DcbTensor* conf_a, const DcbTensor* conf_b,
+                       const DcbTensor* occ_a, const DcbTensor* occ_b, const DcbTensor* fused, void* stream);
+int dcb_bidir_fuse_bwd(const DcbTensor* grad_fused, const DcbTensor* A, const DcbTensor* B,
+                       const DcbTensor* conf_a, const DcbTensor* conf_b, const DcbTensor* occ_a, const DcbTensor* occ_b,
+                       const DcbTensor* grad_A, const DcbTensor* grad_B, const DcbTensor* grad_conf_a,
+                       const DcbTensor* grad_conf_b, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

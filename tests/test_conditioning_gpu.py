@@ -176,3 +176,40 @@ def test_backwarp_identity_and_layer(dcb):
     b = dcb.backwarp(img.bfloat16(), zero.bfloat16(), align_corners=True)
     assert b.dtype == torch.bfloat16
     assert_close(b.float(), img, 1e-2, "bf16 identity")
+
+
+def test_bidir_fuse_forward_backward(dcb, orc):
+    """extractors.py:298-310 without the host sync: values and all four gradients vs the CPU composition."""
+    g = torch.Generator().manual_seed(41)
+    n, c, h, w = 2, 12, 20, 28
+    A = torch.randn(n, c, h, w, generator=g); B = torch.randn(n, c, h, w, generator=g)
+    ca = torch.randn(n, 1, h, w, generator=g); cb = torch.randn(n, 1, h, w, generator=g)     # negative values exercise the clamp
+    oa = (torch.rand(n, 1, h, w, generator=g) > 0.5).float(); ob = (torch.rand(n, 1, h, w, generator=g) > 0.5).float()
+    go = torch.randn(n, c, h, w, generator=g)
+    for with_occ in (True, False):
+        cpu = [t.clone().requires_grad_(True) for t in (A, B, ca, cb)]
+        ref = orc.fuse(cpu[0], cpu[1], cpu[2], cpu[3], oa if with_occ else None, ob if with_occ else None)
+        ref.backward(go)
+        gpu = [t.cuda().requires_grad_(True) for t in (A, B, ca, cb)]
+        got = dcb.bidir_fuse(gpu[0], gpu[1], gpu[2], gpu[3], oa.cuda() if with_occ else None, ob.cuda() if with_occ else None)
+        got.backward(go.cuda())
+        assert_close(got, ref, 1e-5, "bidir fused")
+        for name, a, b in zip(("gA", "gB", "gconf_a", "gconf_b"), gpu, cpu):
+            assert_close(a.grad, b.grad, 1e-5, f"bidir {name} occ={with_occ}")
+
+
+def test_bidirectional_block(dcb, orc):
+    """Masks + both masked soft splats + fusion, as one scale of Bi_Dir_FeatureExtractor (extractors.py:289-310)."""
+    g = torch.Generator().manual_seed(43)
+    n, c, r = 2, 16, 32
+    f1 = torch.randn(n, c, r, r, generator=g); f2 = torch.randn(n, c, r, r, generator=g)
+    ff, fb = _flows(7, n, r, r, 0.6)
+    warper = dcb.FeatureWarperSoftsplat(with_learnable_metric=False)
+    got = dcb.bidirectional_warp_fuse(f1.cuda(), f2.cuda(), ff.cuda(), fb.cuda(), warper)
+    of, ob = orc.compute_mask(ff, fb), orc.compute_mask(fb, ff)
+    wa, ca = orc.feature_warper(f1, ff, None, of)
+    wb, cb = orc.feature_warper(f2, fb, None, ob)
+    ref = orc.fuse(wa, wb, ca, cb, of, ob)
+    same = (dcb.compute_mask(ff.cuda(), fb.cuda()).cpu() == of) & (dcb.compute_mask(fb.cuda(), ff.cuda()).cpu() == ob)
+    assert same.float().mean() > 0.999
+    assert_close(got.cpu()[same.expand_as(ref)], ref[same.expand_as(ref)], 1e-5, "bidirectional block")

@@ -299,3 +299,14 @@ def test_multi_frame_pipeline_many_frames(dcb, orc):
         for k in ("out", "gin", "gflow", "gmetric"):
             assert_close(got[k], ref[k], 1e-5, f"7 frames {k}", truth=truth[k])
     assert_close(dcb.softsplat(tin[:2].cuda(), flow[:2].cuda(), None, "avg"), orc.softsplat(tin[:2], flow[:2], None, "avg"), 1e-5, "2 frames avg")
+
+
+def test_softsplat_host_matches_device(dcb):
+    """Host-buffer entry point (chunked, three streams) == the device op on the same frames."""
+    tin, flow, metric, _ = make_inputs(51, 7, 3, 60, 90, flow_scale=3.0)
+    for mode, me in (("soft", metric), ("avg", None)):
+        ref = dcb.softsplat(tin.cuda(), flow.cuda(), None if me is None else me.cuda(), mode).cpu()
+        got = dcb.softsplat_host(tin.pin_memory(), flow.pin_memory(), None if me is None else me.pin_memory(), mode, chunk_frames=3)
+        torch.cuda.synchronize()
+        assert not got.is_cuda and got.shape == ref.shape
+        assert_close(got, ref, 1e-5, f"host {mode}")

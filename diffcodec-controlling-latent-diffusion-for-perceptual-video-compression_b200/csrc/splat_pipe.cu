@@ -52,9 +52,6 @@ constexpr int kStripH = kRows * kPasses;    // a scatter item: 32 columns x 16 r
 #ifndef DCB_NBATCH
 #define DCB_NBATCH 2
 #endif
-#ifndef DCB_INTERLEAVE
-#define DCB_INTERLEAVE 0
-#endif
 constexpr int kNPer = DCB_NPER;             // normalise: pixels per lane per batch
 constexpr int kNBatches = DCB_NBATCH;
 constexpr int kChunk = 32 * kNPer * kNBatches;   // a normalise item: 512 target pixels
@@ -77,7 +74,6 @@ struct PipeArgs {
     void* mask_out;          // epilogue 1: [N,1,H,W] in T
     int epi;                 // 0 = normalise (softsplat), 1 = occlusion mask (control_utils.py:15-16)
     int ones;                // metric is all-ones and not materialised (compute_mask, dataset wrappers)
-    int dbg;                 // experiments only (DCB_DBG): 1 = no reds, 2 = no input loads, 4 = skip normalise items, 8 = skip scatter items
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -126,7 +122,7 @@ __device__ __forceinline__ void scatter_strip(const PipeArgs& a, int frame, int 
         float flx[kRows], fly[kRows], mv[kRows], iv[kRows][C > 0 ? C : 1];
 #pragma unroll
         for (int r = 0; r < kRows; ++r) {
-            const bool on = xin && r < rows && !(a.dbg & 2);
+            const bool on = xin && r < rows;
             const int y = yb + r;
             flx[r] = fly[r] = 0.f; mv[r] = 0.f;
 #pragma unroll
@@ -142,7 +138,7 @@ __device__ __forceinline__ void scatter_strip(const PipeArgs& a, int frame, int 
         }
 #pragma unroll
         for (int r = 0; r < kRows; ++r) {
-            const bool in_img = xin && r < rows && !(a.dbg & 1);
+            const bool in_img = xin && r < rows;
             const float fx = add_rn((float)x, flx[r]), fy = add_rn((float)(yb + r), fly[r]);   // softsplat.py:298-299
             const float x0f = floorf(fx), y0f = floorf(fy);
             const int x0 = __float2int_rz(x0f), y0 = __float2int_rz(y0f);
@@ -298,26 +294,18 @@ __global__ void __launch_bounds__(kPipeThreads, kMinCtas) k_splat_step(const __g
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const unsigned n_items = (unsigned)a.n_frames * a.tn, s_items = (unsigned)a.s_frames * a.ts;
     const unsigned n_ctas = (n_items + kWarpsPerCta - 1) / kWarpsPerCta;      // grid = n_ctas + s_ctas
-    unsigned b = blockIdx.x;
-#if DCB_INTERLEAVE
-    {   // alternate normalise and scatter CTAs so that both kinds of work run from the first wave on
-        const unsigned s_ctas = gridDim.x - n_ctas;
-        const unsigned pairs = n_ctas < s_ctas ? n_ctas : s_ctas;
-        if (b < 2 * pairs) b = (b & 1) ? n_ctas + (b >> 1) : (b >> 1);
-        else b = (n_ctas > s_ctas ? 0u : n_ctas) + pairs + (b - 2 * pairs);   // the longer list's tail
-    }
-#endif
+    const unsigned b = blockIdx.x;
     const size_t slot_floats = (size_t)a.G * a.HW * 4;
     if (b < n_ctas) {
         const unsigned item = b * kWarpsPerCta + warp;
-        if (item >= n_items || (a.dbg & 4)) return;
+        if (item >= n_items) return;
         const int f = a.n_frame0 + item / a.tn, chunk = item % a.tn;
         float* acc = a.acc + (size_t)((f / a.G) & 1) * slot_floats + (size_t)(f % a.G) * a.HW * 4;
         if (a.epi == 1) mask_chunk<T>(a, f, chunk, acc, lane);
         else normalize_chunk<T, MODE, CA>(a, f, chunk, acc, lane);
     } else {
         const unsigned s = (b - n_ctas) * kWarpsPerCta + warp;
-        if (s >= s_items || (a.dbg & 8)) return;
+        if (s >= s_items) return;
         const int f = a.s_frame0 + s / a.ts, strip = s % a.ts;
         float* acc = a.acc + (size_t)((f / a.G) & 1) * slot_floats + (size_t)(f % a.G) * a.HW * 4;
         scatter_strip<T, TF, MODE, CA>(a, f, strip, acc, lane);
@@ -341,32 +329,8 @@ long long pipe_acc_bytes(long long N, long long H, long long W) {
 
 long long pipe_workspace(long long N, long long H, long long W) { return pipe_acc_bytes(N, H, W); }
 
-// Optional (DCB_L2_PERSIST=1): reserve part of L2 for persisting lines, once per process. This is
-// device-wide state, so it is opt-in; without it the kernels rely on the streaming hints alone.
-static long long persisting_budget() {
-    static long long budget = -1;
-    if (budget < 0) {
-        budget = 0;
-        const char* e = getenv("DCB_L2_PERSIST");
-        if (e && atoi(e) > 0) {
-            int dev = 0, max_persist = 0;
-            if (cudaGetDevice(&dev) == cudaSuccess &&
-                cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, dev) == cudaSuccess && max_persist > 0 &&
-                cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, (size_t)max_persist) == cudaSuccess)
-                budget = max_persist;
-            (void)cudaGetLastError();
-        }
-    }
-    return budget;
-}
-
 template <class T, class TF, int MODE, int CA> static int launch_steps(PipeArgs& a, cudaStream_t st) {
     const int groups = (a.N + a.G - 1) / a.G;
-    long long persist_bytes = 0;
-    if (groups > 1 && persisting_budget() > 0) {
-        persist_bytes = 2ll * a.G * a.HW * 16;
-        if (persist_bytes > persisting_budget()) persist_bytes = persisting_budget();
-    }
     for (int k = 0; k <= groups; ++k) {
         a.s_frame0 = k * a.G;
         a.s_frames = k < groups ? (a.N - a.s_frame0 < a.G ? a.N - a.s_frame0 : a.G) : 0;
@@ -375,25 +339,8 @@ template <class T, class TF, int MODE, int CA> static int launch_steps(PipeArgs&
         const long long n_ctas = ((long long)a.n_frames * a.tn + kWarpsPerCta - 1) / kWarpsPerCta;
         const long long s_ctas = ((long long)a.s_frames * a.ts + kWarpsPerCta - 1) / kWarpsPerCta;
         const unsigned grid = (unsigned)(n_ctas + s_ctas);
-        if (persist_bytes > 0) {
-            // per-launch L2 access-policy window over the accumulator ring: those lines are the only
-            // data of the step that is reused, everything else streams through once
-            cudaLaunchConfig_t cfg = {};
-            cfg.gridDim = dim3(grid); cfg.blockDim = dim3(kPipeThreads); cfg.dynamicSmemBytes = 0; cfg.stream = st;
-            cudaLaunchAttribute attr[1];
-            attr[0].id = cudaLaunchAttributeAccessPolicyWindow;
-            attr[0].val.accessPolicyWindow.base_ptr = a.acc;
-            attr[0].val.accessPolicyWindow.num_bytes = (size_t)persist_bytes;
-            attr[0].val.accessPolicyWindow.hitRatio = 1.0f;
-            attr[0].val.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
-            attr[0].val.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
-            cfg.attrs = attr; cfg.numAttrs = 1;
-            DCB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, k_splat_step<T, TF, MODE, CA>, a));
-            count_launch();
-        } else {
-            k_splat_step<T, TF, MODE, CA><<<grid, kPipeThreads, 0, st>>>(a);
-            DCB_CHECK_LAUNCH("k_splat_step");
-        }
+        k_splat_step<T, TF, MODE, CA><<<grid, kPipeThreads, 0, st>>>(a);
+        DCB_CHECK_LAUNCH("k_splat_step");
     }
     return DCB_OK;
 }
@@ -449,7 +396,6 @@ int splat_pipe_impl(const DcbTensor* in, const DcbTensor* flow, const DcbTensor*
     a.out = out ? out->ptr : nullptr;
     a.norm = norm ? norm->ptr : nullptr;
     a.acc = (float*)ws;
-    { static int dbg = -1; if (dbg < 0) { const char* e = getenv("DCB_DBG"); dbg = e ? atoi(e) : 0; } a.dbg = dbg; }
     if (!ws_clean) DCB_CHECK_CUDA(cudaMemsetAsync(ws, 0, (size_t)pipe_workspace(a.N, a.H, a.W), st));
     const bool ff = flow->dtype == DCB_F32;
     if (in->dtype == DCB_F32) return launch_pipe<float, float>(a, mode, st);

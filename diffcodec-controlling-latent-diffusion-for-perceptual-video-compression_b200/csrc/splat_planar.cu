@@ -23,7 +23,7 @@ constexpr int kPWarps = kPThreads / 32;
 constexpr int kPRows = 4;                         // strip: 32 columns x 4 rows
 constexpr int kPChunk = 128;                      // normalise item: 128 target pixels (4 per lane)
 constexpr long long kPGroupBytes = 34ll << 20;    // accumulator bytes per ring slot
-constexpr float kExp1p = 2.7182817459106445f;
+
 
 struct PlanarArgs {
     View in, flow, metric, mask;

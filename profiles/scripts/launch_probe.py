@@ -1,5 +1,4 @@
-"""Is the step pipeline host-launch-bound? Times the same 64-frame call (a) eagerly, (b) with all
-device work disabled (DCB_DBG=12 set by the caller), (c) replayed from a CUDA graph."""
+"""Is the step pipeline host-launch-bound? Times the same 64-frame call (a) eagerly, (b) replayed from a CUDA graph."""
 import os, sys, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import torch

@@ -162,6 +162,18 @@ def _extras(torch, d, dev, gen, peak):
     """Secondary BASELINE.json configs; each a few hundred ms. Never part of the timed region."""
     ex = {}
     try:
+        # the headline workload again on flow as smooth as real optical flow (same ~8 px amplitude, noise cell
+        # 256 px instead of 32 px): register merging then removes most L2 reduction sectors
+        F2 = 32
+        t_ = torch.rand(F2, 3, H, W, device=dev, generator=gen); m_ = -torch.rand(F2, 1, H, W, device=dev, generator=gen)
+        low = torch.randn(F2, 2, 4, 7, device=dev, generator=gen)
+        fs = torch.nn.functional.interpolate(low, size=(H, W), mode="bicubic", align_corners=False) * 8.0
+        ms = _time_cuda(torch, lambda: d.softsplat(t_, fs, m_, "soft"), 5, 3)
+        ex["headline_on_smooth_flow_32x3x1080x1920_f32"] = {
+            "mean_abs_dflow_dx": round(float((fs[:, :, :, 1:] - fs[:, :, :, :-1]).abs().mean()), 4), "us_per_frame": round(ms * 1e3 / F2, 2),
+            "mpixel_s": round(F2 * H * W / ms / 1e3, 1), "alg_gbs": round(36 * F2 * H * W / ms / 1e6, 1),
+            "frac_of_peak": round(36 * F2 * H * W / ms / 1e6 / peak, 3)}
+        del t_, m_, fs, low
         # C1: avg forward of single 1x3x1080x1920 frames, rotating pool of 16 distinct frames (> L2)
         pool = [(torch.rand(1, 3, H, W, device=dev, generator=gen), _smooth_flow(torch, 1, H, W, 8.0, dev, gen)) for _ in range(16)]
         it = [0]

@@ -173,7 +173,19 @@ def _extras(torch, d, dev, gen, peak):
             "mean_abs_dflow_dx": round(float((fs[:, :, :, 1:] - fs[:, :, :, :-1]).abs().mean()), 4), "us_per_frame": round(ms * 1e3 / F2, 2),
             "mpixel_s": round(F2 * H * W / ms / 1e3, 1), "alg_gbs": round(36 * F2 * H * W / ms / 1e6, 1),
             "frac_of_peak": round(36 * F2 * H * W / ms / 1e6 / peak, 3)}
-        del t_, m_, fs, low
+        # BASELINE.md's wording read literally: gaussian_blur(randn * 8 px, sigma = 16 px), no re-scaling
+        # (sub-pixel, very coherent motion)
+        k = torch.arange(-48, 49, device=dev, dtype=torch.float32)
+        k = torch.exp(-0.5 * (k / 16.0) ** 2); k = (k / k.sum()).view(1, 1, 1, -1)
+        fl_ = torch.randn(F2 * 2, 1, H, W, device=dev, generator=gen) * 8.0
+        fl_ = torch.nn.functional.conv2d(torch.nn.functional.pad(fl_, (48, 48, 0, 0), mode="replicate"), k)
+        fl_ = torch.nn.functional.conv2d(torch.nn.functional.pad(fl_, (0, 0, 48, 48), mode="replicate"), k.transpose(2, 3))
+        fl_ = fl_.view(F2, 2, H, W).contiguous()
+        ms = _time_cuda(torch, lambda: d.softsplat(t_, fl_, m_, "soft"), 5, 3)
+        ex["headline_on_literal_blurred_flow_32x3x1080x1920_f32"] = {
+            "flow_std_px": round(float(fl_.std()), 3), "us_per_frame": round(ms * 1e3 / F2, 2), "mpixel_s": round(F2 * H * W / ms / 1e3, 1),
+            "frac_of_peak": round(36 * F2 * H * W / ms / 1e6 / peak, 3)}
+        del t_, m_, fs, low, fl_
         # C1: avg forward of single 1x3x1080x1920 frames, rotating pool of 16 distinct frames (> L2)
         pool = [(torch.rand(1, 3, H, W, device=dev, generator=gen), _smooth_flow(torch, 1, H, W, 8.0, dev, gen)) for _ in range(16)]
         it = [0]

@@ -18,11 +18,20 @@
 
 namespace dcb {
 
-constexpr int kPThreads = 128;
+#ifndef DCB_PTHREADS
+#define DCB_PTHREADS 32
+#endif
+#ifndef DCB_PGROUP_MB
+#define DCB_PGROUP_MB 34
+#endif
+#ifndef DCB_PMINCTAS
+#define DCB_PMINCTAS 24
+#endif
+constexpr int kPThreads = DCB_PTHREADS;
 constexpr int kPWarps = kPThreads / 32;
 constexpr int kPRows = 4;                         // strip: 32 columns x 4 rows
 constexpr int kPChunk = 128;                      // normalise item: 128 target pixels (4 per lane)
-constexpr long long kPGroupBytes = 34ll << 20;    // accumulator bytes per ring slot
+constexpr long long kPGroupBytes = (long long)DCB_PGROUP_MB << 20;    // accumulator bytes per ring slot
 
 
 struct PlanarArgs {
@@ -207,7 +216,7 @@ __device__ __forceinline__ void planar_normalize_chunk(const PlanarArgs& a, int 
 }
 
 template <class T, class TF>
-__global__ void __launch_bounds__(kPThreads, 6) k_planar_step(const __grid_constant__ PlanarArgs a) {
+__global__ void __launch_bounds__(kPThreads, DCB_PMINCTAS) k_planar_step(const __grid_constant__ PlanarArgs a) {
     const int lane = threadIdx.x & 31;
     unsigned item = blockIdx.x * kPWarps + (threadIdx.x >> 5);
     const size_t frame_floats = (size_t)a.C * a.HW, slot_floats = (size_t)a.G * frame_floats;

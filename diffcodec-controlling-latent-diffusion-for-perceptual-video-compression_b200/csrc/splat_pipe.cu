@@ -291,6 +291,11 @@ __device__ __forceinline__ void mask_chunk(const PipeArgs& a, int frame, int chu
 // ---------------------------------------------------------------------------------------------
 template <class T, class TF, int MODE, int CA>
 __global__ void __launch_bounds__(kPipeThreads, kMinCtas) k_splat_step(const __grid_constant__ PipeArgs a) {
+    // Programmatic dependent launch: let the next step's grid start being scheduled while this one
+    // drains, and wait here until the previous step has completed and flushed (both steps touch
+    // the same accumulator ring). The launch latency of 65 dependent launches is thereby hidden.
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const unsigned n_items = (unsigned)a.n_frames * a.tn, s_items = (unsigned)a.s_frames * a.ts;
     const unsigned n_ctas = (n_items + kWarpsPerCta - 1) / kWarpsPerCta;      // grid = n_ctas + s_ctas
@@ -339,8 +344,14 @@ template <class T, class TF, int MODE, int CA> static int launch_steps(PipeArgs&
         const long long n_ctas = ((long long)a.n_frames * a.tn + kWarpsPerCta - 1) / kWarpsPerCta;
         const long long s_ctas = ((long long)a.s_frames * a.ts + kWarpsPerCta - 1) / kWarpsPerCta;
         const unsigned grid = (unsigned)(n_ctas + s_ctas);
-        k_splat_step<T, TF, MODE, CA><<<grid, kPipeThreads, 0, st>>>(a);
-        DCB_CHECK_LAUNCH("k_splat_step");
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(grid); cfg.blockDim = dim3(kPipeThreads); cfg.dynamicSmemBytes = 0; cfg.stream = st;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = attr; cfg.numAttrs = 1;
+        DCB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, k_splat_step<T, TF, MODE, CA>, a));
+        count_launch();
     }
     return DCB_OK;
 }

@@ -217,6 +217,9 @@ __device__ __forceinline__ void planar_normalize_chunk(const PlanarArgs& a, int 
 
 template <class T, class TF>
 __global__ void __launch_bounds__(kPThreads, DCB_PMINCTAS) k_planar_step(const __grid_constant__ PlanarArgs a) {
+    // programmatic dependent launch: see k_splat_step
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
     const int lane = threadIdx.x & 31;
     unsigned item = blockIdx.x * kPWarps + (threadIdx.x >> 5);
     const size_t frame_floats = (size_t)a.C * a.HW, slot_floats = (size_t)a.G * frame_floats;
@@ -303,8 +306,14 @@ template <class T, class TF> static int launch_planar(PlanarArgs& a, cudaStream_
         a.n_frames = k > 0 ? (a.N - a.n_frame0 < a.G ? a.N - a.n_frame0 : a.G) : 0;
         const long long items = (long long)a.n_frames * a.tn * a.ncg_n + (normalised ? (long long)a.G * a.tz : 0) +
                                 (long long)a.s_frames * a.ts * a.ncg_s;
-        k_planar_step<T, TF><<<(unsigned)((items + kPWarps - 1) / kPWarps), kPThreads, 0, st>>>(a);
-        DCB_CHECK_LAUNCH("k_planar_step");
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3((unsigned)((items + kPWarps - 1) / kPWarps)); cfg.blockDim = dim3(kPThreads); cfg.dynamicSmemBytes = 0; cfg.stream = st;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = attr; cfg.numAttrs = 1;
+        DCB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, k_planar_step<T, TF>, a));
+        count_launch();
     }
     // the normaliser slot read by the last step is the only part of the workspace left non-zero
     if (normalised)

@@ -5,6 +5,7 @@ Tolerances (BASELINE.json north_star): 1e-5 relative in fp32 (atomic order is no
 1e-2 in bf16, bit-exact in deterministic mode."""
 import glob
 import os
+import zlib
 
 import numpy as np
 import pytest
@@ -34,7 +35,8 @@ def orc():
 @pytest.mark.parametrize("mode", MODES)
 @pytest.mark.parametrize("shape", SHAPES, ids=lambda s: "x".join(map(str, s)))
 def test_forward_backward_fp32(dcb, orc, mode, shape):
-    tin, flow, metric, gout = make_inputs(hash((mode, shape)) % 1000, *shape, flow_scale=2.5)
+    seed = zlib.crc32(repr((mode, shape)).encode()) % 1000          # stable across processes (str hash is salted)
+    tin, flow, metric, gout = make_inputs(seed, *shape, flow_scale=2.5)
     if mode.startswith("linear"):
         metric = metric.abs() + 0.1          # keep the normaliser away from cancellation (tolerance is relative)
     ref = oracle_run(orc, tin, flow, metric, gout, mode)

@@ -17,6 +17,7 @@ from .extractors import bidir_fuse, bidirectional_warp_fuse
 from .residual_utils import residual_conditioning, ResidueDataset, WarpingDatasetWrapper
 from .sharding import UVG_SEQUENCES, GopUnit, enumerate_gops, shard_units, gather_checksums, gather_outputs, checksum
 from .host import softsplat_host
+from . import flow_io
 from .dropin import install
 
 __version__ = "0.1.0"

@@ -128,3 +128,30 @@ def test_gather_over_gloo_world2(tmp_path):
     procs = [subprocess.Popen([sys.executable, str(script)], env=dict(env, RANK=str(r)), stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True) for r in range(2)]
     outs = [p.communicate(timeout=240)[0] for p in procs]
     assert all(p.returncode == 0 for p in procs), "\n".join(outs)
+
+
+def test_flow_ingest(tmp_path):
+    """f-2: .flo round trip (interleaved), the dataset's planar mis-reshape, and both resize conventions."""
+    import numpy as np
+    import diffcodec_b200 as d
+    fio = d.flow_io
+    rng = np.random.default_rng(3)
+    flow = rng.standard_normal((6, 10, 2)).astype(np.float32) * 5
+    path = str(tmp_path / "flow_0000_0003.flo")
+    fio.write_flo(path, flow)
+    assert os.path.getsize(path) == 12 + 6 * 10 * 2 * 4                      # header + payload (512x512 -> 2,097,164 B)
+    back = fio.read_flo(path)
+    assert back.shape == (6, 10, 2) and np.array_equal(back, flow)
+    quirk = fio.read_flo(path, planar_quirk=True)                            # dataset.py:15-24
+    assert quirk.shape == (2, 6, 10) and np.array_equal(quirk.ravel(), flow.ravel()) and not np.array_equal(quirk[0], flow[..., 0])
+    with open(path, "r+b") as f:
+        f.write(b"\x00\x00\x00\x00")
+    with pytest.raises(ValueError):
+        fio.read_flo(path)
+    up = fio.resize_flow_to(flow, 12, 20)                                    # utils.py:21-28: rescaled vectors
+    ref = torch.nn.functional.interpolate(torch.from_numpy(flow).permute(2, 0, 1)[None], size=(12, 20), mode="bilinear", align_corners=True)
+    assert torch.allclose(up[:, 0], ref[:, 0] * 2.0) and torch.allclose(up[:, 1], ref[:, 1] * 2.0)
+    down = fio.fast_downsample_flow(flow.transpose(2, 0, 1), 3, 5)           # dataset.py:43-50: no rescale
+    assert down.shape == (2, 3, 5) and np.allclose(down[0, 0, 0], flow[:2, :2, 0].mean(), atol=1e-6)
+    np.save(str(tmp_path / "cached.npy"), flow.transpose(2, 0, 1))
+    assert np.allclose(fio.load_flow_cached(str(tmp_path / "cached.flo"), 3, 5), down)

@@ -11,7 +11,10 @@
 //   * per channel the east column is handed to lane+1 by shuffle and the south row is carried to
 //     the next row when footprints abut, so smooth flow costs ~1.2-2 scalar reds per element
 //     instead of 4; a warp's reds of one channel fall on one or two 128-byte lines of one plane;
-//   * accumulators are planar fp32 [frame][C+1][H][W] in a ring of two L2-sized slots; step k
+//   * accumulators hold FOUR channels per cell, fp32 [frame][C/4][H*W][4]: one 16-byte
+//     `red.global.add.v4.f32` per corner and channel quad instead of four scalar reds (on rough flow
+//     a scalar red costs ~0.44 L2 sectors, a v4 red ~0.6 for four times the payload); the weight
+//     channel has its own plane; both live in a ring of two L2-sized slots; step k
 //     normalises frame group k-1 (and re-zeroes it) while it scatters group k; the kernel boundary
 //     is the only synchronisation; inputs/outputs use streaming loads/stores.
 #include "dcb_common.cuh"
@@ -36,21 +39,20 @@ constexpr long long kPGroupBytes = (long long)DCB_PGROUP_MB << 20;    // accumul
 
 struct PlanarArgs {
     View in, flow, metric, mask;
-    float* acc;              // channel planes: 2 slots x G frames x C x HW floats (or `out` when acc_is_out)
+    float* acc;              // channel quads: 2 slots x G frames x Cq x HW float4
     float* dacc;             // normaliser planes: 3 slots x G frames x HW floats (read by several warps, re-zeroed one step later)
     void* out;               // [N,C,H,W]
     void* norm;              // [N,1,H,W] fp32 or null
-    int N, C, Cacc, H, W;
+    int N, C, Cq, H, W;      // Cq = ceil(C / 4) channel quads
     unsigned HW;
     int mode, eps;
     int G;
     int tiles_x, ts, tn;
-    int cg_s, ncg_s;         // scatter: channels per item, items per strip
-    int cg_n, ncg_n;         // normalise: channels per item, items per chunk
+    int cg_s, ncg_s;         // scatter: channel quads per item, items per strip
+    int cg_n, ncg_n;         // normalise: channel quads per item, items per chunk
     int tz;                  // re-zero items per frame (1024 normaliser cells each)
     int step;                // pipeline step k: scatter group k, normalise group k-1, re-zero normaliser slot (k+1) % 3
     int s_frame0, s_frames, n_frame0, n_frames;
-    int acc_is_out;          // SUM in fp32: reds go straight into `out`, no normalise items
 };
 
 __device__ __forceinline__ void red1_if(bool p, float* addr, float v) {
@@ -61,9 +63,17 @@ __device__ __forceinline__ void red1_if(bool p, float* addr, float v) {
         ::"r"((int)p), "l"(addr), "f"(v) : "memory");
 }
 
+__device__ __forceinline__ void red4p_if(bool p, float4* addr, const float (&v)[4]) {
+    asm volatile(
+        "{\n\t.reg .pred q;\n\t"
+        "setp.ne.s32 q, %0, 0;\n\t"
+        "@q red.global.add.v4.f32 [%1], {%2, %3, %4, %5};\n\t}"
+        ::"r"((int)p), "l"(addr), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]) : "memory");
+}
+
 template <class T, class TF>
-__device__ __forceinline__ void planar_scatter_strip(const PlanarArgs& a, int frame, int tile, int c_begin, int c_end,
-                                                     float* acc, float* dplane, int lane) {
+__device__ __forceinline__ void planar_scatter_strip(const PlanarArgs& a, int frame, int tile, int q_begin, int q_end,
+                                                     bool with_weight, float* acc, float* dplane, int lane) {
     const int tx = tile % a.tiles_x, ty = tile / a.tiles_x;
     const int x = tx * 32 + lane, yb = ty * kPRows;
     const int W = a.W, H = a.H, C = a.C;
@@ -122,45 +132,70 @@ __device__ __forceinline__ void planar_scatter_strip(const PlanarArgs& a, int fr
         last_off = off[kPRows - 1] + W;
     }
 
-    // ---- stream the channels through the footprints ----
+    // ---- stream the channel quads through the footprints ----
     const T* ibase = (const T*)a.in.p + frame * a.in.sN + (long long)xs * a.in.sW + (long long)yb * a.in.sH;
-    for (int c = c_begin; c < c_end; ++c) {
-        float v[kPRows];
-        if (c < C) {
-            const T* ip = ibase + (long long)c * a.in.sC;
+    for (int q = q_begin; q < q_end; ++q) {
+        float v[kPRows][4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int c = 4 * q + j;
+            const T* ip = ibase + (long long)(c < C ? c : 0) * a.in.sC;
 #pragma unroll
             for (int r = 0; r < kPRows; ++r) {
-                v[r] = 0.f;
-                if (xin && r < rows) v[r] = ld_stream(ip + (long long)r * a.in.sH);
+                v[r][j] = 0.f;
+                if (c < C && xin && r < rows) v[r][j] = ld_stream(ip + (long long)r * a.in.sH);
+            }
+        }
+        float4* plane = (float4*)acc + (size_t)q * a.HW;
+        float pend[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int r = 0; r < kPRows; ++r) {
+            float nw[4], ne[4], sw[4], se[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const float t = (a.mode >= DCB_MODE_LINEAR) ? mul_rn(v[r][j], g[r]) : v[r][j];        // softsplat.py:244,247
+                nw[j] = mul_rn(t, wnw[r]); ne[j] = mul_rn(t, wne[r]); sw[j] = mul_rn(t, wsw[r]); se[j] = mul_rn(t, wse[r]);
             }
 #pragma unroll
-            for (int r = 0; r < kPRows; ++r) v[r] = (a.mode >= DCB_MODE_LINEAR) ? mul_rn(v[r], g[r]) : v[r];   // softsplat.py:244,247
-        } else {
+            for (int j = 0; j < 4; ++j) {
+                const float en = __shfl_up_sync(full, ne[j], 1), es = __shfl_up_sync(full, se[j], 1);
+                nw[j] = take[r] ? add_rn(nw[j], en) : nw[j];
+                sw[j] = take[r] ? add_rn(sw[j], es) : sw[j];
+            }
+            red4p_if(e_n[r], plane + off[r] + 1, ne);
+            red4p_if(e_s[r], plane + off[r] + W + 1, se);
+            if (r > 0) red4p_if(flush_prev[r], plane + off[r - 1] + W, pend);
 #pragma unroll
-            for (int r = 0; r < kPRows; ++r) v[r] = g[r];                                                       // appended channel
+            for (int j = 0; j < 4; ++j) nw[j] = join[r] ? add_rn(nw[j], pend[j]) : nw[j];
+            red4p_if(n_ok[r], plane + off[r], nw);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) pend[j] = sw[j];
         }
-        float* plane = c < C ? acc + (size_t)c * a.HW : dplane;
+        red4p_if(last_ok, plane + last_off, pend);
+    }
+    // ---- the appended weight channel (1 | m | exp(m)): its own plane, scalar reds ----
+    if (with_weight) {
         float pend = 0.f;
 #pragma unroll
         for (int r = 0; r < kPRows; ++r) {
-            float nw = mul_rn(v[r], wnw[r]), sw = mul_rn(v[r], wsw[r]);
-            const float ne = mul_rn(v[r], wne[r]), se = mul_rn(v[r], wse[r]);
+            float nw = mul_rn(g[r], wnw[r]), sw = mul_rn(g[r], wsw[r]);
+            const float ne = mul_rn(g[r], wne[r]), se = mul_rn(g[r], wse[r]);
             const float en = __shfl_up_sync(full, ne, 1), es = __shfl_up_sync(full, se, 1);
             nw = take[r] ? add_rn(nw, en) : nw;
             sw = take[r] ? add_rn(sw, es) : sw;
-            red1_if(e_n[r], plane + off[r] + 1, ne);
-            red1_if(e_s[r], plane + off[r] + W + 1, se);
-            if (r > 0) red1_if(flush_prev[r], plane + off[r - 1] + W, pend);
+            red1_if(e_n[r], dplane + off[r] + 1, ne);
+            red1_if(e_s[r], dplane + off[r] + W + 1, se);
+            if (r > 0) red1_if(flush_prev[r], dplane + off[r - 1] + W, pend);
             nw = join[r] ? add_rn(nw, pend) : nw;
-            red1_if(n_ok[r], plane + off[r], nw);
+            red1_if(n_ok[r], dplane + off[r], nw);
             pend = sw;
         }
-        red1_if(last_ok, plane + last_off, pend);
+        red1_if(last_ok, dplane + last_off, pend);
     }
 }
 
 template <class T>
-__device__ __forceinline__ void planar_normalize_chunk(const PlanarArgs& a, int frame, int chunk, int c_begin, int c_end,
+__device__ __forceinline__ void planar_normalize_chunk(const PlanarArgs& a, int frame, int chunk, int q_begin, int q_end,
                                                        float* acc, const float* dplane, int lane) {
     const int C = a.C;
     T* out = (T*)a.out + (long long)frame * C * a.HW;
@@ -179,7 +214,7 @@ __device__ __forceinline__ void planar_normalize_chunk(const PlanarArgs& a, int 
                 if (a.eps == DCB_EPS_ADD) d = add_rn(d, 0.0000001f);
                 else if (a.eps == DCB_EPS_ZERO) d = (d == 0.f) ? 1.f : d;
                 else d = (d < 0.0000001f) ? 0.0000001f : d;
-                if (a.norm && c_begin == 0) __stcs((float*)a.norm + (long long)frame * a.HW + r, d);
+                if (a.norm && q_begin == 0) __stcs((float*)a.norm + (long long)frame * a.HW + r, d);
                 scale[i] = __frcp_rn(d);          // <= 1 ulp from the true quotient of softsplat.py:270
             }
             if (a.mask.p) {
@@ -190,28 +225,26 @@ __device__ __forceinline__ void planar_normalize_chunk(const PlanarArgs& a, int 
         }
     }
     const bool scaled = normalised || a.mask.p != nullptr;
-    constexpr int kCU = 4;                           // channels in flight
-    (void)C;
-    for (int c0 = c_begin; c0 < c_end; c0 += kCU) {
-        float s[kCU][kPer];
+    for (int q = q_begin; q < q_end; ++q) {
+        float4* plane = (float4*)acc + (size_t)q * a.HW;
+        float4 s[kPer];
 #pragma unroll
-        for (int j = 0; j < kCU; ++j)
+        for (int i = 0; i < kPer; ++i) {
+            const unsigned r = base + i * 32;
+            s[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (r < a.HW) s[i] = __ldcg(plane + r);
+        }
 #pragma unroll
-            for (int i = 0; i < kPer; ++i) {
-                const unsigned r = base + i * 32;
-                s[j][i] = 0.f;
-                if (c0 + j < c_end && r < a.HW) s[j][i] = __ldcg(acc + (size_t)(c0 + j) * a.HW + r);
+        for (int i = 0; i < kPer; ++i) {
+            const unsigned r = base + i * 32;
+            if (r < a.HW) {
+                __stcg(plane + r, make_float4(0.f, 0.f, 0.f, 0.f));
+                const float sv[4] = {s[i].x, s[i].y, s[i].z, s[i].w};
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    if (4 * q + j < C) st_stream(out + (size_t)(4 * q + j) * a.HW + r, scaled ? mul_rn(sv[j], scale[i]) : sv[j]);
             }
-#pragma unroll
-        for (int j = 0; j < kCU; ++j)
-#pragma unroll
-            for (int i = 0; i < kPer; ++i) {
-                const unsigned r = base + i * 32;
-                if (c0 + j < c_end && r < a.HW) {
-                    __stcg(acc + (size_t)(c0 + j) * a.HW + r, 0.f);
-                    st_stream(out + (size_t)(c0 + j) * a.HW + r, scaled ? mul_rn(s[j][i], scale[i]) : s[j][i]);
-                }
-            }
+        }
     }
 }
 
@@ -222,10 +255,10 @@ __global__ void __launch_bounds__(kPThreads, DCB_PMINCTAS) k_planar_step(const _
     asm volatile("griddepcontrol.wait;" ::: "memory");
     const int lane = threadIdx.x & 31;
     unsigned item = blockIdx.x * kPWarps + (threadIdx.x >> 5);
-    const size_t frame_floats = (size_t)a.C * a.HW, slot_floats = (size_t)a.G * frame_floats;
+    const size_t frame_floats = (size_t)a.Cq * a.HW * 4, slot_floats = (size_t)a.G * frame_floats;
     const size_t dslot = (size_t)a.G * a.HW;
     const unsigned n_items = (unsigned)a.n_frames * a.tn * a.ncg_n;
-    const unsigned z_items = a.acc_is_out || a.mode == DCB_MODE_SUM ? 0u : (unsigned)a.G * a.tz;
+    const unsigned z_items = a.mode == DCB_MODE_SUM ? 0u : (unsigned)a.G * a.tz;
     if (item < n_items) {                                                 // normalise group step-1
         const unsigned per = (unsigned)a.tn * a.ncg_n;
         const int fi = item / per, q = item % per;
@@ -233,7 +266,7 @@ __global__ void __launch_bounds__(kPThreads, DCB_PMINCTAS) k_planar_step(const _
         const int f = a.n_frame0 + fi, g = a.step - 1;
         float* acc = a.acc + (size_t)(g & 1) * slot_floats + (size_t)fi * frame_floats;
         const float* dplane = a.dacc + (size_t)(g % 3) * dslot + (size_t)fi * a.HW;
-        planar_normalize_chunk<T>(a, f, chunk, cgi * a.cg_n, min(a.C, (cgi + 1) * a.cg_n), acc, dplane, lane);
+        planar_normalize_chunk<T>(a, f, chunk, cgi * a.cg_n, min(a.Cq, (cgi + 1) * a.cg_n), acc, dplane, lane);
         return;
     }
     item -= n_items;
@@ -249,17 +282,17 @@ __global__ void __launch_bounds__(kPThreads, DCB_PMINCTAS) k_planar_step(const _
     const int fi = item / per, q = item % per;                            // scatter group step
     const int strip = q % a.ts, cgi = q / a.ts;
     const int f = a.s_frame0 + fi;
-    float* acc = a.acc_is_out ? a.acc + (size_t)f * frame_floats
-                              : a.acc + (size_t)(a.step & 1) * slot_floats + (size_t)fi * frame_floats;
-    float* dplane = a.acc_is_out ? nullptr : a.dacc + (size_t)(a.step % 3) * dslot + (size_t)fi * a.HW;
-    planar_scatter_strip<T, TF>(a, f, strip, cgi * a.cg_s, min(a.Cacc, (cgi + 1) * a.cg_s), acc, dplane, lane);
+    float* acc = a.acc + (size_t)(a.step & 1) * slot_floats + (size_t)fi * frame_floats;
+    float* dplane = a.dacc + (size_t)(a.step % 3) * dslot + (size_t)fi * a.HW;
+    planar_scatter_strip<T, TF>(a, f, strip, cgi * a.cg_s, min(a.Cq, (cgi + 1) * a.cg_s), cgi == 0 && a.mode != DCB_MODE_SUM,
+                                acc, dplane, lane);
 }
 
 // ---------------------------------------------------------------------------------------------
 // host
 // ---------------------------------------------------------------------------------------------
 static long long planar_group_frames(long long N, long long C, long long H, long long W) {
-    const long long per = C * H * W * 4;
+    const long long per = (C + 3) / 4 * 16 * H * W;
     long long g = kPGroupBytes / (per > 0 ? per : 1);
     if (g < 1) g = 1;
     return g > N ? (N < 1 ? 1 : N) : g;
@@ -267,11 +300,11 @@ static long long planar_group_frames(long long N, long long C, long long H, long
 
 static long long planar_chan_bytes(long long N, long long C, long long H, long long W) {
     const long long G = planar_group_frames(N, C, H, W);
-    return align_up((N > G ? 2 : 1) * G * C * H * W * 4, 256);
+    return align_up((N > G ? 2 : 1) * G * ((C + 3) / 4) * 16 * H * W, 256);
 }
 
 long long planar_workspace(long long N, long long C, long long H, long long W, int dtype, int mode) {
-    if (mode == DCB_MODE_SUM && dtype == DCB_F32) return 0;               // reds go straight into `out`
+    (void)dtype;
     const long long G = planar_group_frames(N, C, H, W);
     const long long dbytes = mode == DCB_MODE_SUM ? 0 : align_up(3 * G * H * W * 4, 256);
     return planar_chan_bytes(N, C, H, W) + dbytes;
@@ -289,13 +322,6 @@ static void split_channels(long long items, int channels, int min_cg, int* cg, i
 }
 
 template <class T, class TF> static int launch_planar(PlanarArgs& a, cudaStream_t st) {
-    if (a.acc_is_out) {
-        a.step = 0; a.s_frame0 = 0; a.s_frames = a.N; a.n_frame0 = 0; a.n_frames = 0;
-        const long long items = (long long)a.N * a.ts * a.ncg_s;
-        k_planar_step<T, TF><<<(unsigned)((items + kPWarps - 1) / kPWarps), kPThreads, 0, st>>>(a);
-        DCB_CHECK_LAUNCH("k_planar_step");
-        return DCB_OK;
-    }
     const int groups = (a.N + a.G - 1) / a.G;
     const bool normalised = a.mode != DCB_MODE_SUM;
     for (int k = 0; k <= groups; ++k) {
@@ -328,7 +354,7 @@ int splat_planar_impl(const DcbTensor* in, const DcbTensor* flow, const DcbTenso
     PlanarArgs a;
     a.in = make_view(in); a.flow = make_view(flow); a.metric = make_view(metric); a.mask = make_view(mask);
     a.N = (int)in->size[0]; a.C = (int)in->size[1]; a.H = (int)in->size[2]; a.W = (int)in->size[3];
-    a.Cacc = a.C + (mode == DCB_MODE_SUM ? 0 : 1);
+    a.Cq = (a.C + 3) / 4;
     a.HW = (unsigned)(in->size[2] * in->size[3]);
     a.mode = mode; a.eps = eps;
     a.G = (int)planar_group_frames(a.N, a.C, a.H, a.W);
@@ -337,21 +363,13 @@ int splat_planar_impl(const DcbTensor* in, const DcbTensor* flow, const DcbTenso
     a.tn = (int)((a.HW + kPChunk - 1) / kPChunk);
     a.tz = (int)((a.HW + 1023) / 1024);
     const int frames_per_step = a.N < a.G ? a.N : a.G;
-    split_channels((long long)frames_per_step * a.ts, a.Cacc, 8, &a.cg_s, &a.ncg_s);
-    split_channels((long long)frames_per_step * a.tn, a.C, 8, &a.cg_n, &a.ncg_n);
+    split_channels((long long)frames_per_step * a.ts, a.Cq, 2, &a.cg_s, &a.ncg_s);
+    split_channels((long long)frames_per_step * a.tn, a.Cq, 2, &a.cg_n, &a.ncg_n);
     a.out = out->ptr;
     a.norm = norm ? norm->ptr : nullptr;
-    a.acc_is_out = (mode == DCB_MODE_SUM && in->dtype == DCB_F32 && !mask) ? 1 : 0;
-    a.dacc = nullptr;
-    if (a.acc_is_out) {
-        a.acc = (float*)out->ptr;
-        split_channels((long long)a.N * a.ts, a.Cacc, 8, &a.cg_s, &a.ncg_s);
-        DCB_CHECK_CUDA(cudaMemsetAsync(out->ptr, 0, (size_t)a.N * a.C * a.HW * 4, st));
-    } else {
-        a.acc = (float*)ws;
-        a.dacc = (float*)((char*)ws + planar_chan_bytes(a.N, a.C, a.H, a.W));
-        if (!ws_clean) DCB_CHECK_CUDA(cudaMemsetAsync(ws, 0, (size_t)planar_workspace(a.N, a.C, a.H, a.W, in->dtype, mode), st));
-    }
+    a.acc = (float*)ws;
+    a.dacc = (float*)((char*)ws + planar_chan_bytes(a.N, a.C, a.H, a.W));
+    if (!ws_clean) DCB_CHECK_CUDA(cudaMemsetAsync(ws, 0, (size_t)planar_workspace(a.N, a.C, a.H, a.W, in->dtype, mode), st));
     const bool ff = flow->dtype == DCB_F32;
     if (in->dtype == DCB_F32) return launch_planar<float, float>(a, st);
     if (in->dtype == DCB_BF16)

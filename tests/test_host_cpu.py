@@ -39,7 +39,8 @@ def test_workspace_queries_need_no_gpu():
     # C+1 <= 4: one or two L2-sized slots of float4 accumulators (a slot = one 1080p frame)
     assert lib.dcb_splat_fwd_workspace_bytes(1, 3, 1080, 1920, L.DCB_F32, L.MODE_SOFT, 0) == 1080 * 1920 * 16
     assert lib.dcb_splat_fwd_workspace_bytes(64, 3, 1080, 1920, L.DCB_F32, L.MODE_SOFT, 0) == 2 * 1080 * 1920 * 16
-    assert lib.dcb_splat_workspace_bytes(1, 8, 64, 64, L.DCB_F32, L.MODE_SUM, 0) == 0        # planar reds straight into out
+    assert lib.dcb_splat_workspace_bytes(1, 8, 64, 64, L.DCB_F32, L.MODE_SUM, 0) == 2 * 64 * 64 * 16   # two channel quads
+    assert lib.dcb_splat_workspace_bytes(1, 8, 64, 64, L.DCB_F64, L.MODE_SUM, 0) == 0        # fp64 reds go straight into out
     # many channels: planar accumulators, 2 slots x 2 frames x 64 planes + 3 slots x 2 normaliser planes
     assert lib.dcb_splat_workspace_bytes(8, 64, 256, 256, L.DCB_F32, L.MODE_SOFT, 0) == (2 * 2 * 64 + 3 * 2) * 256 * 256 * 4
     assert lib.dcb_splat_bwd_workspace_bytes(64, 3, 1080, 1920, L.DCB_F32, L.MODE_SOFT, 0) == 64 * 1080 * 1920 * 8

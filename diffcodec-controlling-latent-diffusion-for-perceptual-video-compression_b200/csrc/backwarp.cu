@@ -33,9 +33,24 @@ template <class A> struct Tap {
     bool b[4];
 };
 
-template <class A> __device__ __forceinline__ A linspace_pm1(int i, int n) {
+// Per-launch constants of the grid arithmetic, evaluated once on the host with the same IEEE
+// operations (a division per pixel costs ~10 instructions plus a range check on the device).
+template <class A> struct TapConst {
+    A stepx, stepy;      // linspace step 2 / (n - 1)
+    A divx, divy;        // (n - 1) / 2, the divisor of warp.py:11-12
+};
+
+template <class A> static TapConst<A> make_tap_const(int W, int H) {
+    TapConst<A> k;
+    k.stepx = W > 1 ? (A)2 / (A)(W - 1) : (A)0;
+    k.stepy = H > 1 ? (A)2 / (A)(H - 1) : (A)0;
+    k.divx = (A)((W - 1.0) / 2.0);
+    k.divy = (A)((H - 1.0) / 2.0);
+    return k;
+}
+
+template <class A> __device__ __forceinline__ A linspace_pm1(int i, int n, A step) {
     if (n == 1) return (A)-1;
-    const A step = (A)2 / (A)(n - 1);
     return i < n / 2 ? fma_rn(step, (A)i, (A)-1) : fma_rn(-step, (A)(n - 1 - i), (A)1);
 }
 
@@ -45,10 +60,10 @@ template <class A> __device__ __forceinline__ A unnormalize(A g, int size, int a
 }
 
 template <class A>
-__device__ __forceinline__ Tap<A> make_tap(int x, int y, A flow_x, A flow_y, int W, int H, int align) {
+__device__ __forceinline__ Tap<A> make_tap(int x, int y, A flow_x, A flow_y, int W, int H, int align, const TapConst<A>& k) {
     Tap<A> t;
-    const A gx = linspace_pm1<A>(x, W) + flow_x / (A)((W - 1.0) / 2.0);
-    const A gy = linspace_pm1<A>(y, H) + flow_y / (A)((H - 1.0) / 2.0);
+    const A gx = linspace_pm1<A>(x, W, k.stepx) + flow_x / k.divx;
+    const A gy = linspace_pm1<A>(y, H, k.stepy) + flow_y / k.divy;
     const A sx = unnormalize<A>(gx, W, align), sy = unnormalize<A>(gy, H, align);
     const A x0f = floor_t(sx), y0f = floor_t(sy);
     t.x0 = to_int_sat(x0f);
@@ -67,14 +82,14 @@ __device__ __forceinline__ Tap<A> make_tap(int x, int y, A flow_x, A flow_y, int
 
 // K4: one thread per OUTPUT pixel, loop over channels (gather, coalesced for smooth flow).
 template <class T, class TF>
-__global__ void __launch_bounds__(256) k_backwarp_fwd(const WarpArgs a) {
+__global__ void __launch_bounds__(256) k_backwarp_fwd(const WarpArgs a, const TapConst<typename Acc<T>::type> kc) {
     using A = typename Acc<T>::type;
     const unsigned p = blockIdx.x * 256 + threadIdx.x;
     if (p >= a.total) return;
     const unsigned n = p / a.HW, r = p - n * a.HW;
     const int y = (int)(r / (unsigned)a.W), x = (int)(r - (unsigned)y * (unsigned)a.W);
     const TF* fp = (const TF*)a.flow.p + n * a.flow.sN + y * a.flow.sH + x * a.flow.sW;
-    const Tap<A> t = make_tap<A>(x, y, (A)ld_stream(fp), (A)ld_stream(fp + a.flow.sC), a.W, a.H, a.align);
+    const Tap<A> t = make_tap<A>(x, y, (A)ld_stream(fp), (A)ld_stream(fp + a.flow.sC), a.W, a.H, a.align, kc);
 
     // tap offsets inside one (n, c) plane; an out-of-range tap reads element 0 and is zeroed by its weight
     const long long o0 = (long long)t.y0 * a.image.sH + (long long)t.x0 * a.image.sW;
@@ -110,16 +125,84 @@ __global__ void __launch_bounds__(256) k_backwarp_fwd(const WarpArgs a) {
     }
 }
 
+// K4, fp32 fast path: four consecutive output pixels per thread, 16-byte loads of flow / gt and
+// 16-byte stores of warped / residual, 32-bit element offsets. The per-pixel arithmetic is the
+// same sequence as above, so the results are bit-identical to the generic kernel.
+struct Warp4Args {
+    const float *image, *flow, *gt;
+    float *warped, *residual;
+    int isN, isC, isH, isW;      // image strides (elements)
+    int fsN, fsC, fsH;           // flow strides; sW == 1
+    int gsN, gsC, gsH;           // gt strides; sW == 1
+    unsigned total4, W4;
+    int C, H, W, HW, align;
+};
+
+__global__ void __launch_bounds__(256) k_backwarp_fwd4(const Warp4Args a, const TapConst<float> kc) {
+    const unsigned q = blockIdx.x * 256 + threadIdx.x;
+    if (q >= a.total4) return;
+    const unsigned row = q / a.W4;                         // n * H + y
+    const int x = (int)(q - row * a.W4) * 4;
+    const unsigned n = row / (unsigned)a.H;
+    const int y = (int)(row - n * (unsigned)a.H);
+    const float* fp = a.flow + (int)n * a.fsN + y * a.fsH + x;
+    const float4 fx4 = __ldcs((const float4*)fp), fy4 = __ldcs((const float4*)(fp + a.fsC));
+    const float fx[4] = {fx4.x, fx4.y, fx4.z, fx4.w}, fy[4] = {fy4.x, fy4.y, fy4.z, fy4.w};
+
+    int to[4][4];
+    float tw[4][4];
+    unsigned valid = 0;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const Tap<float> t = make_tap<float>(x + j, y, fx[j], fy[j], a.W, a.H, a.align, kc);
+        const int o0 = t.y0 * a.isH + t.x0 * a.isW;        // only used when the tap is valid
+        to[j][0] = t.b[0] ? o0 : 0;
+        to[j][1] = t.b[1] ? o0 + a.isW : 0;
+        to[j][2] = t.b[2] ? o0 + a.isH : 0;
+        to[j][3] = t.b[3] ? o0 + a.isH + a.isW : 0;
+        tw[j][0] = t.wnw; tw[j][1] = t.wne; tw[j][2] = t.wsw; tw[j][3] = t.wse;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) valid |= (t.b[k] ? 1u : 0u) << (j * 4 + k);
+    }
+    const float* im = a.image + (int)n * a.isN;
+    const float* gt = a.gt ? a.gt + (int)n * a.gsN + y * a.gsH + x : nullptr;
+    const int oo = ((int)n * a.C) * a.HW + y * a.W + x;
+    float* wp = a.warped + oo;
+    float* rp = a.residual ? a.residual + oo : nullptr;
+    for (int c = 0; c < a.C; ++c, im += a.isC, wp += a.HW) {
+        float v[4][4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+#pragma unroll
+            for (int k = 0; k < 4; ++k) v[j][k] = im[to[j][k]];
+        float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (gt) g = __ldcs((const float4*)(gt + c * a.gsC));
+        float acc[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            acc[j] = 0.f;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) acc[j] = (valid >> (j * 4 + k)) & 1u ? fma_rn(v[j][k], tw[j][k], acc[j]) : acc[j];
+        }
+        __stcs((float4*)wp, make_float4(acc[0], acc[1], acc[2], acc[3]));
+        if (rp) {
+            __stcs((float4*)rp, make_float4(sub_rn(g.x, acc[0]), sub_rn(g.y, acc[1]), sub_rn(g.z, acc[2]), sub_rn(g.w, acc[3])));
+            rp += a.HW;
+        }
+    }
+}
+
 // K4b: gradImage by scatter (reds into the zeroed planar buffer), gradFlow by gather.
 template <class T, class TF>
-__global__ void __launch_bounds__(256) k_backwarp_bwd(const WarpArgs a, typename Acc<T>::type* gimage_acc) {
+__global__ void __launch_bounds__(256) k_backwarp_bwd(const WarpArgs a, const TapConst<typename Acc<T>::type> kc,
+                                                      typename Acc<T>::type* gimage_acc) {
     using A = typename Acc<T>::type;
     const unsigned p = blockIdx.x * 256 + threadIdx.x;
     if (p >= a.total) return;
     const unsigned n = p / a.HW, r = p - n * a.HW;
     const int y = (int)(r / (unsigned)a.W), x = (int)(r - (unsigned)y * (unsigned)a.W);
     const TF* fp = (const TF*)a.flow.p + n * a.flow.sN + y * a.flow.sH + x * a.flow.sW;
-    const Tap<A> t = make_tap<A>(x, y, ld<A>(fp), ld<A>(fp + a.flow.sC), a.W, a.H, a.align);
+    const Tap<A> t = make_tap<A>(x, y, ld<A>(fp), ld<A>(fp + a.flow.sC), a.W, a.H, a.align, kc);
 
     const T* im = (const T*)a.image.p + n * a.image.sN + (long long)t.y0 * a.image.sH + (long long)t.x0 * a.image.sW;
     const long long o1 = a.image.sW, o2 = a.image.sH, o3 = a.image.sH + a.image.sW;
@@ -165,8 +248,51 @@ static void fill(WarpArgs& a, const DcbTensor* image) {
 }
 
 template <class T, class TF> static int launch_warp_fwd(const WarpArgs& a, cudaStream_t st) {
-    k_backwarp_fwd<T, TF><<<(a.total + 255) / 256, 256, 0, st>>>(a);
+    k_backwarp_fwd<T, TF><<<(a.total + 255) / 256, 256, 0, st>>>(a, make_tap_const<typename Acc<T>::type>(a.W, a.H));
     DCB_CHECK_LAUNCH("k_backwarp_fwd");
+    return DCB_OK;
+}
+
+// largest element offset a [N,C,H,W] view can address, or -1 when it does not fit 31 bits
+static long long max_offset31(const DcbTensor* t) {
+    long long m = 0;
+    for (int d = 0; d < 4; ++d) {
+        if (t->size[d] == 0) return 0;
+        const long long s = t->stride[d];
+        if (s < 0) return -1;
+        m += (t->size[d] - 1) * s;
+    }
+    return m < (1ll << 31) ? m : -1;
+}
+
+static bool rows_vec4(const DcbTensor* t) {      // 16-byte loads along x are legal
+    return t->dtype == DCB_F32 && t->stride[3] == 1 && t->stride[0] % 4 == 0 && t->stride[1] % 4 == 0 &&
+           t->stride[2] % 4 == 0 && ((uintptr_t)t->ptr & 15) == 0 && max_offset31(t) >= 0;
+}
+
+static bool fwd4_supported(const DcbTensor* image, const DcbTensor* flow, const DcbTensor* gt, const DcbTensor* warped,
+                           const DcbTensor* residual) {
+    if (image->dtype != DCB_F32 || image->size[3] % 4 != 0 || max_offset31(image) < 0) return false;
+    if (image->size[0] * image->size[1] * image->size[2] * image->size[3] >= (1ll << 31)) return false;
+    if (!rows_vec4(flow) || (gt && !rows_vec4(gt))) return false;
+    if (((uintptr_t)warped->ptr & 15) || (residual && ((uintptr_t)residual->ptr & 15))) return false;
+    return true;
+}
+
+static int launch_warp_fwd4(const DcbTensor* image, const DcbTensor* flow, const DcbTensor* gt, const DcbTensor* warped,
+                            const DcbTensor* residual, int align, cudaStream_t st) {
+    Warp4Args a{};
+    a.image = (const float*)image->ptr; a.flow = (const float*)flow->ptr; a.gt = gt ? (const float*)gt->ptr : nullptr;
+    a.warped = (float*)warped->ptr; a.residual = residual ? (float*)residual->ptr : nullptr;
+    a.isN = (int)image->stride[0]; a.isC = (int)image->stride[1]; a.isH = (int)image->stride[2]; a.isW = (int)image->stride[3];
+    a.fsN = (int)flow->stride[0]; a.fsC = (int)flow->stride[1]; a.fsH = (int)flow->stride[2];
+    if (gt) { a.gsN = (int)gt->stride[0]; a.gsC = (int)gt->stride[1]; a.gsH = (int)gt->stride[2]; }
+    a.C = (int)image->size[1]; a.H = (int)image->size[2]; a.W = (int)image->size[3];
+    a.HW = a.H * a.W; a.align = align;
+    a.W4 = (unsigned)(a.W / 4);
+    a.total4 = (unsigned)(image->size[0] * a.H) * a.W4;
+    k_backwarp_fwd4<<<(a.total4 + 255) / 256, 256, 0, st>>>(a, make_tap_const<float>(a.W, a.H));
+    DCB_CHECK_LAUNCH("k_backwarp_fwd4");
     return DCB_OK;
 }
 
@@ -178,6 +304,7 @@ int backwarp_fwd_impl(const DcbTensor* image, const DcbTensor* flow, const DcbTe
     a.align = align;
     fill(a, image);
     if (a.total == 0 || a.C == 0) return DCB_OK;
+    if (fwd4_supported(image, flow, gt, warped, residual)) return launch_warp_fwd4(image, flow, gt, warped, residual, align, st);
     const bool ff = flow->dtype == DCB_F32;
     switch (image->dtype) {
         case DCB_F32: return launch_warp_fwd<float, float>(a, st);
@@ -189,7 +316,7 @@ int backwarp_fwd_impl(const DcbTensor* image, const DcbTensor* flow, const DcbTe
 
 template <class T, class TF> static int launch_warp_bwd(const WarpArgs& a, void* acc, cudaStream_t st) {
     using A = typename Acc<T>::type;
-    k_backwarp_bwd<T, TF><<<(a.total + 255) / 256, 256, 0, st>>>(a, (A*)acc);
+    k_backwarp_bwd<T, TF><<<(a.total + 255) / 256, 256, 0, st>>>(a, make_tap_const<A>(a.W, a.H), (A*)acc);
     DCB_CHECK_LAUNCH("k_backwarp_bwd");
     return DCB_OK;
 }

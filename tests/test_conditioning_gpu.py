@@ -166,6 +166,30 @@ def test_backwarp_matches_grid_sample(dcb, orc, align, shape):
     assert_close(fc.grad, ref_gflow, 1e-4, "backwarp grad flow")
 
 
+@pytest.mark.parametrize("align", [False, True])
+def test_backwarp_vector_path_is_bit_identical(dcb, align):
+    """The 4-pixel fp32 kernel (W % 4 == 0, unit-stride rows) and the generic strided kernel
+    run the same per-pixel arithmetic: identical bits, including out-of-frame taps."""
+    g = torch.Generator().manual_seed(11)
+    img = torch.randn(2, 3, 36, 64, generator=g).cuda()
+    flow = (torch.randn(2, 2, 36, 64, generator=g) * 9).cuda()
+    flow[0, :, 0, 0] = 1e9
+    flow[1, :, 5, 7] = float("nan")
+    gt = torch.randn(2, 3, 36, 64, generator=g).cuda()
+    w_fast, r_fast = dcb.backwarp_residual(img, flow, gt, align_corners=align)
+    # a flow whose x stride is 2 forces the generic kernel
+    wide = torch.zeros(2, 2, 36, 128, device="cuda")
+    wide[..., ::2] = flow
+    w_gen, r_gen = dcb.backwarp_residual(img, wide[..., ::2], gt, align_corners=align)
+    assert torch.equal(torch.nan_to_num(w_fast, nan=7.0), torch.nan_to_num(w_gen, nan=7.0))
+    assert torch.equal(torch.nan_to_num(r_fast, nan=7.0), torch.nan_to_num(r_gen, nan=7.0))
+    # channel-sliced image (non-contiguous, strides still fit): vector kernel again
+    big = torch.randn(2, 5, 36, 64, generator=g).cuda()
+    w_a = dcb.backwarp(big[:, 1:4], flow, align_corners=align)
+    w_b = dcb.backwarp(big[:, 1:4].contiguous(), flow, align_corners=align)
+    assert torch.equal(torch.nan_to_num(w_a, nan=7.0), torch.nan_to_num(w_b, nan=7.0))
+
+
 def test_backwarp_identity_and_layer(dcb):
     img = torch.rand(1, 3, 16, 20, device="cuda")
     zero = torch.zeros(1, 2, 16, 20, device="cuda")

@@ -125,35 +125,99 @@ __global__ void __launch_bounds__(256) k_backwarp_fwd(const WarpArgs a, const Ta
     }
 }
 
-// K4, fp32 fast path: four consecutive output pixels per thread, 16-byte loads of flow / gt and
-// 16-byte stores of warped / residual, 32-bit element offsets. The per-pixel arithmetic is the
-// same sequence as above, so the results are bit-identical to the generic kernel.
-struct Warp4Args {
+// K4, fp32 fast path: PX consecutive output pixels per thread, vector loads of flow / gt and
+// vector stores of warped / residual, 32-bit element offsets, CU channels in flight. The per-pixel
+// arithmetic is the same sequence as above, so the results are bit-identical to the generic kernel.
+#ifndef DCB_BW_PX
+#define DCB_BW_PX 2          // 2 or 4 pixels per thread
+#endif
+#ifndef DCB_BW_CU
+#define DCB_BW_CU 1          // channels in flight per thread: 4 * PX * CU tap loads + CU gt loads
+#endif
+#ifndef DCB_BW_MINCTAS
+#define DCB_BW_MINCTAS 5
+#endif
+#ifndef DCB_BW_TILE
+#define DCB_BW_TILE 1
+#endif
+#ifndef DCB_BW_PF
+#define DCB_BW_PF 1          // L2 prefetch one wave of CTAs ahead (0 = off)
+#endif
+
+struct WarpRowsArgs {
     const float *image, *flow, *gt;
     float *warped, *residual;
     int isN, isC, isH, isW;      // image strides (elements)
     int fsN, fsC, fsH;           // flow strides; sW == 1
     int gsN, gsC, gsH;           // gt strides; sW == 1
-    unsigned total4, W4;
+    unsigned totalv, Wv;         // threads in all, threads per row
+    unsigned tiles_x, pf_dist;   // CTAs per tile row; prefetch distance = resident CTAs
     int C, H, W, HW, align;
 };
 
-__global__ void __launch_bounds__(256) k_backwarp_fwd4(const Warp4Args a, const TapConst<float> kc) {
+template <int PX> struct VecOf;
+template <> struct VecOf<2> { using type = float2; };
+template <> struct VecOf<4> { using type = float4; };
+__device__ __forceinline__ void unpack(const float2& v, float* o) { o[0] = v.x; o[1] = v.y; }
+__device__ __forceinline__ void unpack(const float4& v, float* o) { o[0] = v.x; o[1] = v.y; o[2] = v.z; o[3] = v.w; }
+__device__ __forceinline__ void pack(float2& v, const float* o) { v = make_float2(o[0], o[1]); }
+__device__ __forceinline__ void pack(float4& v, const float* o) { v = make_float4(o[0], o[1], o[2], o[3]); }
+
+__global__ void __launch_bounds__(256, DCB_BW_MINCTAS) k_backwarp_rows(const WarpRowsArgs a, const TapConst<float> kc) {
+    constexpr int CU = DCB_BW_CU, PX = DCB_BW_PX;
+    using V = typename VecOf<PX>::type;
+#if DCB_BW_TILE
+    // a CTA covers 8 rows x (32 * PX) columns: the two image rows a warp gathers from are the rows
+    // its neighbours in the CTA gather from too, so they are served by this SM's L1
+    const unsigned tx = blockIdx.x % a.tiles_x, ty = blockIdx.x / a.tiles_x;
+    const unsigned n = blockIdx.y;
+    const int y = (int)(ty * 8 + (threadIdx.x >> 5));
+    const int x = (int)((tx * 32 + (threadIdx.x & 31)) * PX);
+#if DCB_BW_PF
+    {   // L2 prefetch of the rows a CTA one wave ahead will stream: one 128-byte line per lane
+        unsigned pb = blockIdx.x + a.pf_dist, pn = n;
+        if (pb >= gridDim.x) { pb -= gridDim.x; ++pn; }
+        if (pn < gridDim.y && pb < gridDim.x) {
+            const int px0 = (int)((pb % a.tiles_x) * 32 * PX), py = (int)((pb / a.tiles_x) * 8 + (threadIdx.x >> 5));
+            const int lane = threadIdx.x & 31;
+            constexpr int LPR = PX * 32 * 4 / 128;                  // lines per row segment
+            const int plane = lane / LPR, line = lane % LPR;
+            const int pxl = px0 + line * 32;
+            if (py < a.H && pxl < a.W) {
+                const float* q = nullptr;
+                if (plane < 2) q = a.flow + (int)pn * a.fsN + plane * a.fsC + py * a.fsH + pxl;
+                else if (plane < 2 + a.C && a.gt) q = a.gt + (int)pn * a.gsN + (plane - 2) * a.gsC + py * a.gsH + pxl;
+                else if (plane >= 8 && plane < 8 + a.C) q = a.image + (int)pn * a.isN + (plane - 8) * a.isC + py * a.isH + pxl * a.isW;
+                if (q) asm volatile("prefetch.global.L2 [%0];" ::"l"(q));
+            }
+        }
+    }
+#endif
+    if (y >= a.H || x >= a.W) return;
+#else
     const unsigned q = blockIdx.x * 256 + threadIdx.x;
-    if (q >= a.total4) return;
-    const unsigned row = q / a.W4;                         // n * H + y
-    const int x = (int)(q - row * a.W4) * 4;
+    if (q >= a.totalv) return;
+    const unsigned row = q / a.Wv;                         // n * H + y
+    const int x = (int)(q - row * a.Wv) * PX;
     const unsigned n = row / (unsigned)a.H;
     const int y = (int)(row - n * (unsigned)a.H);
+#endif
     const float* fp = a.flow + (int)n * a.fsN + y * a.fsH + x;
-    const float4 fx4 = __ldcs((const float4*)fp), fy4 = __ldcs((const float4*)(fp + a.fsC));
-    const float fx[4] = {fx4.x, fx4.y, fx4.z, fx4.w}, fy[4] = {fy4.x, fy4.y, fy4.z, fy4.w};
+    const V fxv = __ldcs((const V*)fp), fyv = __ldcs((const V*)(fp + a.fsC));
+    // the gt rows do not depend on the flow: put the first block's loads in flight before the taps
+    const float* gt = a.gt ? a.gt + (int)n * a.gsN + y * a.gsH + x : nullptr;
+    V g[CU];
+#pragma unroll
+    for (int u = 0; u < CU; ++u)
+        if (gt) g[u] = __ldcs((const V*)(gt + (u < a.C ? u : a.C - 1) * a.gsC));
+    float fx[PX], fy[PX];
+    unpack(fxv, fx); unpack(fyv, fy);
 
-    int to[4][4];
-    float tw[4][4];
+    int to[PX][4];
+    float tw[PX][4];
     unsigned valid = 0;
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
+    for (int j = 0; j < PX; ++j) {
         const Tap<float> t = make_tap<float>(x + j, y, fx[j], fy[j], a.W, a.H, a.align, kc);
         const int o0 = t.y0 * a.isH + t.x0 * a.isW;        // only used when the tap is valid
         to[j][0] = t.b[0] ? o0 : 0;
@@ -165,29 +229,45 @@ __global__ void __launch_bounds__(256) k_backwarp_fwd4(const Warp4Args a, const 
         for (int k = 0; k < 4; ++k) valid |= (t.b[k] ? 1u : 0u) << (j * 4 + k);
     }
     const float* im = a.image + (int)n * a.isN;
-    const float* gt = a.gt ? a.gt + (int)n * a.gsN + y * a.gsH + x : nullptr;
     const int oo = ((int)n * a.C) * a.HW + y * a.W + x;
     float* wp = a.warped + oo;
     float* rp = a.residual ? a.residual + oo : nullptr;
-    for (int c = 0; c < a.C; ++c, im += a.isC, wp += a.HW) {
-        float v[4][4];
+    for (int c0 = 0; c0 < a.C; c0 += CU) {
+        float v[CU][PX][4];
 #pragma unroll
-        for (int j = 0; j < 4; ++j)
+        for (int u = 0; u < CU; ++u) {
+            const float* pl = im + (c0 + u < a.C ? c0 + u : a.C - 1) * a.isC;
 #pragma unroll
-            for (int k = 0; k < 4; ++k) v[j][k] = im[to[j][k]];
-        float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (gt) g = __ldcs((const float4*)(gt + c * a.gsC));
-        float acc[4];
+            for (int j = 0; j < PX; ++j)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            acc[j] = 0.f;
-#pragma unroll
-            for (int k = 0; k < 4; ++k) acc[j] = (valid >> (j * 4 + k)) & 1u ? fma_rn(v[j][k], tw[j][k], acc[j]) : acc[j];
+                for (int k = 0; k < 4; ++k) v[u][j][k] = pl[to[j][k]];
         }
-        __stcs((float4*)wp, make_float4(acc[0], acc[1], acc[2], acc[3]));
-        if (rp) {
-            __stcs((float4*)rp, make_float4(sub_rn(g.x, acc[0]), sub_rn(g.y, acc[1]), sub_rn(g.z, acc[2]), sub_rn(g.w, acc[3])));
-            rp += a.HW;
+        if (c0 > 0 && gt) {
+#pragma unroll
+            for (int u = 0; u < CU; ++u) g[u] = __ldcs((const V*)(gt + (c0 + u < a.C ? c0 + u : a.C - 1) * a.gsC));
+        }
+#pragma unroll
+        for (int u = 0; u < CU; ++u) {
+            if (c0 + u < a.C) {
+                float acc[PX], gv[PX];
+#pragma unroll
+                for (int j = 0; j < PX; ++j) {
+                    acc[j] = 0.f;
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                        acc[j] = (valid >> (j * 4 + k)) & 1u ? fma_rn(v[u][j][k], tw[j][k], acc[j]) : acc[j];
+                }
+                V o;
+                pack(o, acc);
+                __stcs((V*)(wp + (c0 + u) * a.HW), o);
+                if (rp) {
+                    unpack(g[u], gv);
+#pragma unroll
+                    for (int j = 0; j < PX; ++j) gv[j] = sub_rn(gv[j], acc[j]);
+                    pack(o, gv);
+                    __stcs((V*)(rp + (c0 + u) * a.HW), o);
+                }
+            }
         }
     }
 }
@@ -265,23 +345,24 @@ static long long max_offset31(const DcbTensor* t) {
     return m < (1ll << 31) ? m : -1;
 }
 
-static bool rows_vec4(const DcbTensor* t) {      // 16-byte loads along x are legal
-    return t->dtype == DCB_F32 && t->stride[3] == 1 && t->stride[0] % 4 == 0 && t->stride[1] % 4 == 0 &&
-           t->stride[2] % 4 == 0 && ((uintptr_t)t->ptr & 15) == 0 && max_offset31(t) >= 0;
+static bool rows_vec(const DcbTensor* t) {      // vector loads along x are legal
+    constexpr int V = DCB_BW_PX;
+    return t->dtype == DCB_F32 && t->stride[3] == 1 && t->stride[0] % V == 0 && t->stride[1] % V == 0 &&
+           t->stride[2] % V == 0 && ((uintptr_t)t->ptr & (V * 4 - 1)) == 0 && max_offset31(t) >= 0;
 }
 
-static bool fwd4_supported(const DcbTensor* image, const DcbTensor* flow, const DcbTensor* gt, const DcbTensor* warped,
+static bool rows_supported(const DcbTensor* image, const DcbTensor* flow, const DcbTensor* gt, const DcbTensor* warped,
                            const DcbTensor* residual) {
-    if (image->dtype != DCB_F32 || image->size[3] % 4 != 0 || max_offset31(image) < 0) return false;
+    if (image->size[0] > 65535 || image->dtype != DCB_F32 || image->size[3] % DCB_BW_PX != 0 || max_offset31(image) < 0) return false;
     if (image->size[0] * image->size[1] * image->size[2] * image->size[3] >= (1ll << 31)) return false;
-    if (!rows_vec4(flow) || (gt && !rows_vec4(gt))) return false;
-    if (((uintptr_t)warped->ptr & 15) || (residual && ((uintptr_t)residual->ptr & 15))) return false;
+    if (!rows_vec(flow) || (gt && !rows_vec(gt))) return false;
+    if (((uintptr_t)warped->ptr & (DCB_BW_PX * 4 - 1)) || (residual && ((uintptr_t)residual->ptr & (DCB_BW_PX * 4 - 1)))) return false;
     return true;
 }
 
-static int launch_warp_fwd4(const DcbTensor* image, const DcbTensor* flow, const DcbTensor* gt, const DcbTensor* warped,
+static int launch_warp_rows(const DcbTensor* image, const DcbTensor* flow, const DcbTensor* gt, const DcbTensor* warped,
                             const DcbTensor* residual, int align, cudaStream_t st) {
-    Warp4Args a{};
+    WarpRowsArgs a{};
     a.image = (const float*)image->ptr; a.flow = (const float*)flow->ptr; a.gt = gt ? (const float*)gt->ptr : nullptr;
     a.warped = (float*)warped->ptr; a.residual = residual ? (float*)residual->ptr : nullptr;
     a.isN = (int)image->stride[0]; a.isC = (int)image->stride[1]; a.isH = (int)image->stride[2]; a.isW = (int)image->stride[3];
@@ -289,10 +370,17 @@ static int launch_warp_fwd4(const DcbTensor* image, const DcbTensor* flow, const
     if (gt) { a.gsN = (int)gt->stride[0]; a.gsC = (int)gt->stride[1]; a.gsH = (int)gt->stride[2]; }
     a.C = (int)image->size[1]; a.H = (int)image->size[2]; a.W = (int)image->size[3];
     a.HW = a.H * a.W; a.align = align;
-    a.W4 = (unsigned)(a.W / 4);
-    a.total4 = (unsigned)(image->size[0] * a.H) * a.W4;
-    k_backwarp_fwd4<<<(a.total4 + 255) / 256, 256, 0, st>>>(a, make_tap_const<float>(a.W, a.H));
-    DCB_CHECK_LAUNCH("k_backwarp_fwd4");
+    a.Wv = (unsigned)(a.W / DCB_BW_PX);
+    a.totalv = (unsigned)(image->size[0] * a.H) * a.Wv;
+#if DCB_BW_TILE
+    a.tiles_x = (a.Wv + 31) / 32;
+    a.pf_dist = (unsigned)(device_sm_count() * DCB_BW_MINCTAS);
+    const dim3 grid(a.tiles_x * (unsigned)((a.H + 7) / 8), (unsigned)image->size[0]);
+    k_backwarp_rows<<<grid, 256, 0, st>>>(a, make_tap_const<float>(a.W, a.H));
+#else
+    k_backwarp_rows<<<(a.totalv + 255) / 256, 256, 0, st>>>(a, make_tap_const<float>(a.W, a.H));
+#endif
+    DCB_CHECK_LAUNCH("k_backwarp_rows");
     return DCB_OK;
 }
 
@@ -304,7 +392,7 @@ int backwarp_fwd_impl(const DcbTensor* image, const DcbTensor* flow, const DcbTe
     a.align = align;
     fill(a, image);
     if (a.total == 0 || a.C == 0) return DCB_OK;
-    if (fwd4_supported(image, flow, gt, warped, residual)) return launch_warp_fwd4(image, flow, gt, warped, residual, align, st);
+    if (rows_supported(image, flow, gt, warped, residual)) return launch_warp_rows(image, flow, gt, warped, residual, align, st);
     const bool ff = flow->dtype == DCB_F32;
     switch (image->dtype) {
         case DCB_F32: return launch_warp_fwd<float, float>(a, st);

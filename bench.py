@@ -345,7 +345,7 @@ def run_ours(args):
     h_fl = flow[:Fe].cpu().pin_memory(); h_out = torch.empty(Fe, C, H, W).pin_memory()
     def e2e_step():
         # public host-buffer API: chunked H2D / kernels / D2H over three streams, result back in h_out
-        d.softsplat_host(h_in, h_fl, h_me, "soft", out=h_out, device=dev, chunk_frames=2)
+        d.softsplat_host(h_in, h_fl, h_me, "soft", out=h_out, device=dev, chunk_frames=8)
     for _ in range(2):
         e2e_step()
     barrier()
@@ -407,7 +407,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--frames", type=int, default=64, help="1080p frames per GPU per step")
-    ap.add_argument("--e2e-frames", type=int, default=16)
+    ap.add_argument("--e2e-frames", type=int, default=64)
     ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-extra", action="store_true")

@@ -156,3 +156,14 @@ def test_flow_ingest(tmp_path):
     assert down.shape == (2, 3, 5) and np.allclose(down[0, 0, 0], flow[:2, :2, 0].mean(), atol=1e-6)
     np.save(str(tmp_path / "cached.npy"), flow.transpose(2, 0, 1))
     assert np.allclose(fio.load_flow_cached(str(tmp_path / "cached.flo"), 3, 5), down)
+
+
+def test_host_chunk_schedule():
+    """softsplat_host's chunk plan covers every frame once, never exceeds the steady chunk, and
+    starts / ends with single frames when the batch is long enough to ramp."""
+    from diffcodec_b200.host import _chunk_schedule
+    for n in range(1, 80):
+        for k in (1, 2, 3, 4, 8, 16):
+            plan = _chunk_schedule(n, min(k, n))
+            assert sum(plan) == n and min(plan) >= 1 and max(plan) <= max(1, min(k, n)), (n, k, plan)
+    assert _chunk_schedule(64, 8)[:4] == [1, 2, 4, 8] and _chunk_schedule(64, 8)[-1] == 1

@@ -312,3 +312,10 @@ def test_softsplat_host_matches_device(dcb):
         torch.cuda.synchronize()
         assert not got.is_cuda and got.shape == ref.shape
         assert_close(got, ref, 1e-5, f"host {mode}")
+    # ramped schedule (1, 2, 4, 4 ..., 2, 1), staging buffers reused by a second call with new data
+    for seed in (52, 53):
+        tin, flow, metric, _ = make_inputs(seed, 23, 3, 24, 40, flow_scale=3.0)
+        ref = dcb.softsplat(tin.cuda(), flow.cuda(), metric.cuda(), "soft").cpu()
+        got = dcb.softsplat_host(tin.pin_memory(), flow.pin_memory(), metric.pin_memory(), "soft", chunk_frames=4)
+        torch.cuda.synchronize()
+        assert_close(got, ref, 1e-5, "host ramped")

@@ -125,7 +125,7 @@ int64_t dcb_launch_count(void) { return (int64_t)g_launches.load(); }
 
 const char* dcb_build_info(void) {
     return "libdiffcodec_b200 " __DATE__ " nvcc " DCB_STR(__CUDACC_VER_MAJOR__) "." DCB_STR(__CUDACC_VER_MINOR__)
-           " target sm_100a; kernels: k_splat_step k_planar_step k_scatter_planar k_normalize k_bwd_target k_bwd_source "
+           " target sm_100a; kernels: k_splat_step k_planar_step k_list_count k_list_alloc k_list_fill k_list_gather k_scatter_planar k_normalize k_bwd_target k_bwd_source "
            "k_backwarp_rows k_backwarp_fwd k_backwarp_bwd k_cast_f32_bf16 k_recipe_fuse k_bidir_fuse_fwd k_bidir_fuse_bwd "
            "k_det_emit k_det_reduce";
 }

@@ -76,10 +76,18 @@ __global__ void __launch_bounds__(256) k_bwd_target(const BwdArgs a) {
 
 // K3b -- source-side gather. blockDim = (px, cs): px source pixels, cs channel slices per pixel.
 // Loads are unconditional from always-valid addresses (an out-of-range corner reads element 0 of
-// its plane and is then zeroed by a select): no branches in the channel loop, 4 channels = 20
+// its plane and is then zeroed by a select): no branches in the channel loop, 2 channels = 10
 // loads in flight per thread.
-template <class T, class TF>
-__global__ void __launch_bounds__(256) k_bwd_source(const BwdArgs a) {
+#ifndef DCB_BS_U
+#define DCB_BS_U 2           // channels in flight per thread (5 loads each); 64 registers -> 4 CTAs per SM
+#endif
+#ifndef DCB_BS_MINCTAS
+#define DCB_BS_MINCTAS 4
+#endif
+// IX: type of the element offsets inside one gradOut plane (int when they fit 31 bits: one
+// IMAD.WIDE per load instead of a 64-bit multiply-add chain).
+template <class T, class TF, class IX>
+__global__ void __launch_bounds__(256, DCB_BS_MINCTAS) k_bwd_source(const BwdArgs a) {
     using A = typename Acc<T>::type;
     extern __shared__ unsigned char smem_raw[];
     A* red = (A*)smem_raw;                                        // [cs][px][4] when cs > 1
@@ -103,13 +111,14 @@ __global__ void __launch_bounds__(256) k_bwd_source(const BwdArgs a) {
     const bool any = b[0] || b[1] || b[2] || b[3];
     const A w[4] = {f.wnw, f.wne, f.wsw, f.wse};
     // gradOut element offsets of the four corners inside one (n, c) plane; 0 when out of range
-    long long go[4];
+    IX go[4];
     {
-        const long long o0 = (long long)f.y0 * a.gout.sH + (long long)f.x0 * a.gout.sW;
-        go[0] = b[0] ? o0 : 0;
-        go[1] = b[1] ? o0 + a.gout.sW : 0;
-        go[2] = b[2] ? o0 + a.gout.sH : 0;
-        go[3] = b[3] ? o0 + a.gout.sH + a.gout.sW : 0;
+        const IX sH = (IX)a.gout.sH, sW = (IX)a.gout.sW;
+        const IX o0 = (IX)f.y0 * sH + (IX)f.x0 * sW;              // only used when the corner is in range
+        go[0] = b[0] ? o0 : (IX)0;
+        go[1] = b[1] ? o0 + sW : (IX)0;
+        go[2] = b[2] ? o0 + sH : (IX)0;
+        go[3] = b[3] ? o0 + sH + sW : (IX)0;
     }
 
     A g = (A)1, gprime = (A)1;
@@ -132,23 +141,27 @@ __global__ void __launch_bounds__(256) k_bwd_source(const BwdArgs a) {
 #pragma unroll
     for (int k = 0; k < 4; ++k) wa[k] = b[k] ? w[k] * ak[k] : (A)0;
 
-    const T* gp = (const T*)a.gout.p + n * a.gout.sN;
-    const T* ip = (const T*)a.in.p + n * a.in.sN + y * a.in.sH + x * a.in.sW;
-    T* gi = (a.gin && live) ? (T*)a.gin + (long long)n * a.C * a.HW + r : nullptr;
     const bool need_A = (a.gflow != nullptr) || (a.gmetric != nullptr);
+    // moving plane pointers: one 64-bit add per channel, corner loads are base + 32-bit offset
+    const long long gstep = (long long)a.cs * a.gout.sC, istep = (long long)a.cs * a.in.sC, ostep = (long long)a.cs * a.HW;
+    const T* gc = (const T*)a.gout.p + n * a.gout.sN + (long long)ty * a.gout.sC;
+    const T* ic = (const T*)a.in.p + n * a.in.sN + y * a.in.sH + x * a.in.sW + (long long)ty * a.in.sC;
+    T* gi = (a.gin && live) ? (T*)a.gin + (long long)n * a.C * a.HW + r + (long long)ty * a.HW : nullptr;
 
     A Ak[4] = {(A)0, (A)0, (A)0, (A)0};
-    constexpr int U = 4;
+    constexpr int U = DCB_BS_U;
     int c = ty;
     for (; c + (U - 1) * a.cs < a.C; c += U * a.cs) {
         A gk[U][4], v[U];
+        const T* gcj = gc;
+        const T* icj = ic;
 #pragma unroll
-        for (int j = 0; j < U; ++j) {
-            const T* gc = gp + (long long)(c + j * a.cs) * a.gout.sC;
+        for (int j = 0; j < U; ++j, gcj += gstep, icj += istep) {
 #pragma unroll
-            for (int k = 0; k < 4; ++k) gk[j][k] = ld<A>(gc + go[k]);
-            v[j] = need_A ? ld<A>(ip + (long long)(c + j * a.cs) * a.in.sC) : (A)0;
+            for (int k = 0; k < 4; ++k) gk[j][k] = ld<A>(gcj + go[k]);
+            v[j] = need_A ? ld<A>(icj) : (A)0;
         }
+        gc = gcj; ic = icj;
 #pragma unroll
         for (int j = 0; j < U; ++j) {
 #pragma unroll
@@ -157,14 +170,14 @@ __global__ void __launch_bounds__(256) k_bwd_source(const BwdArgs a) {
                 A s = (A)0;
 #pragma unroll
                 for (int k = 0; k < 4; ++k) s = fma_rn(gk[j][k], wa[k], s);
-                st<T, A>(gi + (long long)(c + j * a.cs) * a.HW, s * g);
+                st<T, A>(gi, s * g);
+                gi += ostep;
             }
 #pragma unroll
             for (int k = 0; k < 4; ++k) Ak[k] = fma_rn(gk[j][k], v[j], Ak[k]);
         }
     }
-    for (; c < a.C; c += a.cs) {
-        const T* gc = gp + (long long)c * a.gout.sC;
+    for (; c < a.C; c += a.cs, gc += gstep, ic += istep) {
         A gk[4];
 #pragma unroll
         for (int k = 0; k < 4; ++k) { gk[k] = ld<A>(gc + go[k]); gk[k] = b[k] ? gk[k] : (A)0; }
@@ -172,10 +185,11 @@ __global__ void __launch_bounds__(256) k_bwd_source(const BwdArgs a) {
             A s = (A)0;
 #pragma unroll
             for (int k = 0; k < 4; ++k) s = fma_rn(gk[k], wa[k], s);
-            st<T, A>(gi + (long long)c * a.HW, s * g);
+            st<T, A>(gi, s * g);
+            gi += ostep;
         }
         if (need_A) {
-            const A v = ld<A>(ip + (long long)c * a.in.sC);
+            const A v = ld<A>(ic);
 #pragma unroll
             for (int k = 0; k < 4; ++k) Ak[k] = fma_rn(gk[k], v, Ak[k]);
         }
@@ -240,7 +254,13 @@ static int launch_bwd(BwdArgs& a, cudaStream_t st) {
     dim3 block(a.px, cs);
     const unsigned blocks = (a.total + a.px - 1) / a.px;
     const size_t smem = cs > 1 ? (size_t)256 * 4 * sizeof(A) : 0;
-    k_bwd_source<T, TF><<<blocks, block, smem, st>>>(a);
+    // plane-relative gradOut offsets in 32 bits whenever the view allows it
+    const long long span = (long long)(a.H - 1) * (a.gout.sH < 0 ? -a.gout.sH : a.gout.sH) +
+                           (long long)(a.W - 1) * (a.gout.sW < 0 ? -a.gout.sW : a.gout.sW);
+    if (span < (1ll << 30))
+        k_bwd_source<T, TF, int><<<blocks, block, smem, st>>>(a);
+    else
+        k_bwd_source<T, TF, long long><<<blocks, block, smem, st>>>(a);
     DCB_CHECK_LAUNCH("k_bwd_source");
     return DCB_OK;
 }

@@ -5,7 +5,8 @@
 // post-ops) and :277-355 (softsplat_func.forward, kernel `softsplat_out`) of the reference.
 //
 //   fp32 / bf16, C + 1 <= 4 (frames, flows, SD latents)  -> splat_pipe.cu   (float4 accumulators)
-//   fp32 / bf16, more channels (feature maps)             -> splat_planar.cu (planar accumulators)
+//   fp32 / bf16, more channels (feature maps)             -> splat_planar.cu (channel-quad accumulators),
+//                                      and >= 16 MB of them -> splat_lists.cu  (per-target lists + gather)
 //   fp64 (the reference supports double; gradcheck uses it) -> this file
 //
 // The plain path: one thread per SOURCE PIXEL (flow read once, weights computed once per pixel;
@@ -139,6 +140,22 @@ int splat_planar_impl(const DcbTensor* in, const DcbTensor* flow, const DcbTenso
                       const DcbTensor* norm, const DcbTensor* mask, void* ws, int mode, int eps, bool ws_clean,
                       cudaStream_t st);
 
+// implemented in splat_lists.cu
+long long lists_workspace(long long N, long long H, long long W);
+bool lists_supported(const DcbTensor* in, const DcbTensor* flow, const DcbTensor* metric, int mode);
+int splat_lists_impl(const DcbTensor* in, const DcbTensor* flow, const DcbTensor* metric, const DcbTensor* out,
+                     const DcbTensor* norm, const DcbTensor* mask, void* ws, int mode, int eps, bool leave_clean,
+                     cudaStream_t st);
+
+// the shape-only part of lists_supported (the workspace query has no strides)
+static bool lists_shape(int dtype, int mode, long long N, long long C, long long H, long long W) {
+    DcbTensor t{};
+    t.dtype = dtype;
+    t.size[0] = N; t.size[1] = C; t.size[2] = H; t.size[3] = W;
+    t.stride[3] = 1; t.stride[2] = W; t.stride[1] = H * W; t.stride[0] = C * H * W;
+    return lists_supported(&t, nullptr, nullptr, mode);
+}
+
 // C+1 <= 4 channels in fp32 / bf16: float4 accumulators (splat_pipe.cu)
 static bool use_pipe(int dtype, int mode, long long C) {
     return dtype != DCB_F64 && C + (mode == DCB_MODE_SUM ? 0 : 1) <= 4;
@@ -146,7 +163,12 @@ static bool use_pipe(int dtype, int mode, long long C) {
 
 long long splat_fwd_workspace(long long N, long long C, long long H, long long W, int dtype, int mode) {
     if (use_pipe(dtype, mode, C)) return pipe_workspace(N, H, W);
-    if (dtype != DCB_F64) return planar_workspace(N, C, H, W, dtype, mode);
+    if (dtype != DCB_F64) {
+        const long long planar = planar_workspace(N, C, H, W, dtype, mode);
+        if (!lists_shape(dtype, mode, N, C, H, W)) return planar;
+        const long long lists = lists_workspace(N, H, W);         // strides may still send the call to the planar path
+        return lists > planar ? lists : planar;
+    }
     if (mode == DCB_MODE_SUM) return 0;                           // fp64 reds go straight into `out`
     return align_up(N * (C + 1) * H * W * 8, 256);
 }
@@ -226,10 +248,11 @@ int splat_fwd_impl(const DcbTensor* in, const DcbTensor* flow, const DcbTensor* 
     const bool pipe = use_pipe(in->dtype, mode, C);
     if (pipe && !pipe_supported(in, flow, metric))
         return set_error(DCB_E_LIMIT, "splat_fwd: tensor spans beyond 2^31 elements are not supported by the float4 path");
-    const long long need = pipe ? pipe_workspace(N, H, W) : planar_workspace(N, C, H, W, in->dtype, mode);
+    const long long need = splat_fwd_workspace(N, C, H, W, in->dtype, mode);
     if (need > 0 && (!ws || ws_bytes < need || ((uintptr_t)ws & 255)))
         return set_error(DCB_E_WORKSPACE, "splat_fwd: workspace of %lld bytes (256 B aligned) required, got %lld", need, ws_bytes);
     if (pipe) return splat_pipe_impl(in, flow, metric, out, norm, mask, ws, mode, eps, ws_clean, st);
+    if (lists_supported(in, flow, metric, mode)) return splat_lists_impl(in, flow, metric, out, norm, mask, ws, mode, eps, ws_clean, st);
     return splat_planar_impl(in, flow, metric, out, norm, mask, ws, mode, eps, ws_clean, st);
 }
 

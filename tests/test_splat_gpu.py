@@ -280,6 +280,38 @@ def test_small_spatial_many_channels(dcb, orc):
             assert_close(got[k], ref[k], 2e-5, f"pyramid {c}x{r} {k}", truth=truth[k])
 
 
+@pytest.mark.parametrize("mode", ["sum", "avg", "linear", "soft", "avg-zeroeps", "soft-clipeps"])
+def test_large_many_channel_tensors(dcb, orc, mode):
+    """>= 16 MB with C + 1 > 4: the per-target list path (count / scan / fill / gather). Collisions,
+    holes and out-of-frame corners from a rough flow; forward and all gradients vs the oracle."""
+    tin, flow, metric, gout = make_inputs(77, 2, 35, 192, 320, flow_scale=4.0)
+    flow[0, :, 3, 5] = float("nan"); flow[1, 0, 7, 9] = 1e9; flow[1, :, 100:110, 200:210] = -500.0
+    ref = oracle_run(orc, tin, flow, metric, gout, mode)
+    truth = oracle_run(orc, tin.double(), flow.double(), metric.double(), gout.double(), mode)
+    got = cuda_run(dcb.softsplat, tin, flow, metric, gout, mode)
+    for k in ("out", "gin", "gflow", "gmetric"):
+        if ref[k] is not None:
+            assert_close(got[k], ref[k], 2e-5, f"lists {mode} {k}", truth=truth[k])
+    # the shared all-zero workspace must still be clean for the accumulator paths
+    small = make_inputs(78, 1, 3, 24, 40, flow_scale=2.0)
+    assert_close(dcb.softsplat(small[0].cuda(), small[1].cuda(), small[2].cuda(), "soft"),
+                 orc.softsplat(small[0], small[1], small[2], "soft"), 1e-5, "pipe after lists")
+    assert_close(dcb.softsplat(tin[:1, :9, :32, :32].cuda(), flow[:1, :, :32, :32].cuda(), None, "avg"),
+                 orc.softsplat(tin[:1, :9, :32, :32], flow[:1, :, :32, :32], None, "avg"), 1e-5, "planar after lists")
+
+
+def test_large_many_channel_bf16_and_frame_groups(dcb, orc):
+    """bf16 through the list path, and more frames than one 64 MB list group (two groups at 512 x 768)."""
+    tin, flow, metric, _ = make_inputs(79, 2, 70, 192, 320, flow_scale=3.0)
+    tb, mb = tin.bfloat16(), metric.bfloat16()
+    ref = orc.softsplat(tb.float(), flow, mb.float(), "soft")
+    got = dcb.softsplat(tb.cuda(), flow.cuda(), mb.cuda(), "soft")
+    assert got.dtype == torch.bfloat16
+    assert_close(got.float(), ref, 1e-2, "lists bf16 (fp32 flow)")
+    tin, flow, metric, _ = make_inputs(80, 3, 5, 512, 768, flow_scale=3.0)
+    assert_close(dcb.softsplat(tin.cuda(), flow.cuda(), metric.cuda(), "soft"), orc.softsplat(tin, flow, metric, "soft"), 1e-5, "lists groups")
+
+
 def test_bf16_forward_wild_flows(dcb, orc):
     """bf16 forward on large flows (holes, collisions): values within 1e-2 of the fp32 reference."""
     tin, flow, metric, _ = make_inputs(8, 2, 3, 40, 56, flow_scale=6.0)

@@ -42,6 +42,19 @@ inline void count_launch(int n = 1) { g_launches.fetch_add(n, std::memory_order_
             return dcb::set_error((int)e__, "%s: %s", #expr, cudaGetErrorString(e__)); \
     } while (0)
 
+// Programmatic dependent launch: the kernel may be scheduled while its predecessor in the stream
+// drains; it must call pdl_wait() (device side) before it touches anything the predecessor wrote.
+template <class... KArgs, class... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 // Strided 4-d view handed to kernels by value (strides in elements).
 struct View {
     const void* p;
@@ -76,6 +89,13 @@ int device_sm_count();
 // ------------------------------------------------------------------------------------------------
 // device side
 // ------------------------------------------------------------------------------------------------
+// let the next kernel of the stream start its launch now; wait until the previous one has completed
+// and its writes are visible (both are no-ops for a kernel launched without the PDL attribute)
+__device__ __forceinline__ void pdl_wait() {
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+
 template <class T> struct Acc { using type = float; };
 template <> struct Acc<double> { using type = double; };
 

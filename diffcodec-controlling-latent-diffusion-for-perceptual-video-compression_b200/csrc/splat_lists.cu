@@ -87,6 +87,7 @@ __device__ __forceinline__ void corners(const ListArgs& a, unsigned p, unsigned&
 
 template <class TF>
 __global__ void __launch_bounds__(256) k_list_count(const ListArgs a) {
+    pdl_wait();
     const unsigned p = blockIdx.x * 256 + threadIdx.x;
     if (p >= a.gtotal) return;
     unsigned n, tgt[4]; int y, x; float w[4]; bool ok[4];
@@ -100,6 +101,7 @@ __global__ void __launch_bounds__(256) k_list_count(const ListArgs a) {
 __global__ void __launch_bounds__(256) k_list_alloc(const ListArgs a) {
     __shared__ int warp_sum[8];
     __shared__ int cta_base;
+    pdl_wait();
     const unsigned t = blockIdx.x * 256 + threadIdx.x;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const int cnt = t < a.gtotal ? __ldcg(a.cursor + t) : 0;
@@ -127,6 +129,7 @@ __global__ void __launch_bounds__(256) k_list_alloc(const ListArgs a) {
 
 template <class T, class TF>
 __global__ void __launch_bounds__(256) k_list_fill(const ListArgs a) {
+    pdl_wait();
     const unsigned p = blockIdx.x * 256 + threadIdx.x;
     if (p >= a.gtotal) return;
     unsigned n, tgt[4]; int y, x; float w[4]; bool ok[4];
@@ -150,6 +153,7 @@ __global__ void __launch_bounds__(256) k_list_fill(const ListArgs a) {
 template <class T>
 __global__ void __launch_bounds__(256, DCB_LMINCTAS) k_list_gather(const ListArgs a) {
     constexpr int CB = DCB_LCB;
+    pdl_wait();
     // a CTA owns a 32 x 8 tile of targets: the sources of vertically adjacent targets are the same
     // rows of `in`, so they are served by this SM's L1 instead of L2
     const unsigned tile = blockIdx.x % a.tiles, n = blockIdx.x / a.tiles;
@@ -271,14 +275,12 @@ static int launch_lists(ListArgs& a, const ListLayout& L, char* ws, int N, bool 
         const unsigned blocks = (a.gtotal + 255) / 256;
         if (!clean)
             DCB_CHECK_CUDA(cudaMemsetAsync(ws + L.total_off, 0, (size_t)(L.cursor_off - L.total_off) + (size_t)a.gtotal * 4, st));
-        k_list_count<TF><<<blocks, 256, 0, st>>>(a);
-        DCB_CHECK_LAUNCH("k_list_count");
-        k_list_alloc<<<blocks, 256, 0, st>>>(a);
-        DCB_CHECK_LAUNCH("k_list_alloc");
-        k_list_fill<T, TF><<<blocks, 256, 0, st>>>(a);
-        DCB_CHECK_LAUNCH("k_list_fill");
-        k_list_gather<T><<<a.tiles * (unsigned)frames, 256, 0, st>>>(a);
-        DCB_CHECK_LAUNCH("k_list_gather");
+        // programmatic dependent launches: each kernel's launch overlaps its predecessor's drain
+        DCB_CHECK_CUDA(launch_pdl(k_list_count<TF>, blocks, 256, 0, st, a));
+        DCB_CHECK_CUDA(launch_pdl(k_list_alloc, blocks, 256, 0, st, a));
+        DCB_CHECK_CUDA(launch_pdl(k_list_fill<T, TF>, blocks, 256, 0, st, a));
+        DCB_CHECK_CUDA(launch_pdl(k_list_gather<T>, a.tiles * (unsigned)frames, 256, 0, st, a));
+        count_launch(4);
         // a shared all-zero workspace is handed back all-zero: one memset behind the gather (zeroing
         // the cells inside the kernel that reads them cost 10-60 % of its speed: the stores order
         // the loads behind them)

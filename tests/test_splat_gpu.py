@@ -208,7 +208,7 @@ def test_mass_conservation_1080p(dcb):
     # avg: where anything landed, a constant image stays constant
     ones = torch.full_like(tin, 3.0)
     avg = dcb.softsplat(ones, flow, None, "avg")
-    hit = dcb.softsplat(torch.ones_like(tin[:, :1]), flow, None, "sum") > 1e-3
+    hit = dcb.softsplat(torch.ones_like(tin[:, :1]), flow, None, "sum") > 0.05   # the 1e-7 of the normaliser is a 2e-6 relative effect there
     assert_close(avg[:, :1][hit], torch.full_like(avg[:, :1][hit], 3.0), 1e-4, "avg of constant")
 
 
@@ -310,6 +310,38 @@ def test_large_many_channel_bf16_and_frame_groups(dcb, orc):
     assert_close(got.float(), ref, 1e-2, "lists bf16 (fp32 flow)")
     tin, flow, metric, _ = make_inputs(80, 3, 5, 512, 768, flow_scale=3.0)
     assert_close(dcb.softsplat(tin.cuda(), flow.cuda(), metric.cuda(), "soft"), orc.softsplat(tin, flow, metric, "soft"), 1e-5, "lists groups")
+
+
+def test_list_path_agrees_with_accumulator_path(dcb):
+    """Two independent GPU implementations of the many-channel forward: the whole batch goes through the
+    per-target lists (>= 16 MB), single frames of it through the channel-quad accumulators."""
+    g = torch.Generator().manual_seed(81)
+    tin = torch.randn(4, 24, 192, 256, generator=g).cuda()
+    flow = (torch.randn(4, 2, 192, 256, generator=g) * 5).cuda()
+    metric = (torch.randn(4, 1, 192, 256, generator=g) * 0.5).cuda()
+    for mode in ("sum", "avg", "soft"):
+        me = metric if mode == "soft" else None
+        whole = dcb.softsplat(tin, flow, me, mode)
+        for n in range(4):
+            part = dcb.softsplat(tin[n:n + 1], flow[n:n + 1], None if me is None else me[n:n + 1], mode)
+            assert_close(whole[n:n + 1], part, 1e-5, f"lists vs accumulators {mode} frame {n}")
+
+
+def test_mass_conservation_c4_shape(dcb):
+    """BASELINE config C4 (8 x 64 x 256 x 256) through the list path: a 'sum' splat whose footprints all stay
+    inside the frame moves mass without creating or losing any; 'avg' of a constant is that constant."""
+    g = torch.Generator(device="cuda").manual_seed(82)
+    tin = torch.rand(8, 64, 256, 256, device="cuda", generator=g)
+    low = torch.randn(8, 2, 8, 8, device="cuda", generator=g)
+    flow = torch.nn.functional.interpolate(low, size=(256, 256), mode="bicubic") * 3
+    border = torch.zeros(1, 1, 256, 256, device="cuda"); border[..., 12:-12, 12:-12] = 1
+    flow = flow * border                                   # nothing leaves the frame
+    out = dcb.softsplat(tin, flow, None, "sum")
+    assert_close(out.double().sum(dim=(2, 3)), tin.double().sum(dim=(2, 3)), 1e-6, "mass per (frame, channel)")
+    const = torch.full_like(tin, 0.75)
+    avg = dcb.softsplat(const, flow, None, "avg")
+    covered = dcb.softsplat(torch.ones(8, 1, 256, 256, device="cuda"), flow, None, "sum") > 0.05   # the 1e-7 of the normaliser is a 2e-6 relative effect there
+    assert_close(avg[covered.expand_as(avg)], const[covered.expand_as(avg)], 1e-5, "avg of a constant")
 
 
 def test_bf16_forward_wild_flows(dcb, orc):

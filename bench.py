@@ -95,12 +95,16 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+WORKLOAD = "soft (softmax) forward splat, fp32, {F}x3x1080x1920 frames per GPU per step, smooth synthetic flow ~8 px"
+
+
 def _cpu_port_mpixel_s(frames, threads, repeats=1):
     """Soft-mode forward on the host: the oracle's C kernel (frame-parallel pthreads) + the mode
     wrapper's pre/post ops in torch CPU, exactly the reference composition (softsplat.py:246-270)."""
     import torch
     from oracle import oracle as orc
 
+    torch.set_num_threads(max(1, threads))      # torchrun exports OMP_NUM_THREADS=1: give the pre/post ops the cores too
     torch.manual_seed(0)
     tin = torch.rand(frames, C, H, W)
     metric = -torch.rand(frames, 1, H, W)
@@ -138,7 +142,8 @@ def run_reference(args):
         "unit": "Mpixel/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": round(dt / max(args.steps, 1) * 1e3, 2), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"soft fwd fp32 {frames}x3x1080x1920 on host cores", "frames_per_step": frames},
+        "config": {"workload": WORKLOAD.format(F=args.frames), "frames_per_gpu": args.frames,
+                   "sample": f"each step = {frames} of the workload's frames on rank 0's host cores"},
         "cpu_baseline": {"value": round(v, 2), "unit": "Mpixel/s", "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": round(v, 2), "unit": "Mpixel/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "note": "the reference has no CPU path and CuPy is absent: this is the committed CPU port of its kernel (oracle/)",
@@ -367,7 +372,7 @@ def run_ours(args):
             "metric": "softsplat soft-mode forward throughput, 1080p fp32 frames", "value": round(value, 1), "unit": "Mpixel/s",
             "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": round(ms_step, 4),
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"soft (softmax) forward splat, fp32, {F}x3x1080x1920 frames per GPU per step, smooth synthetic flow ~8 px",
+            "config": {"workload": WORKLOAD.format(F=F),
                        "frames_per_gpu": F, "l2_policy": f"inputs+outputs per step = {(36 * px_per_step) >> 20} MiB per GPU, larger than the 126 MB L2; no flush needed",
                        "partition": "frames sharded by rank, no data-path collective"},
             "roofline": {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),

@@ -308,7 +308,7 @@ def test_large_many_channel_bf16_and_frame_groups(dcb, orc):
     got = dcb.softsplat(tb.cuda(), flow.cuda(), mb.cuda(), "soft")
     assert got.dtype == torch.bfloat16
     assert_close(got.float(), ref, 1e-2, "lists bf16 (fp32 flow)")
-    tin, flow, metric, _ = make_inputs(80, 3, 5, 512, 768, flow_scale=3.0)
+    tin, flow, metric, _ = make_inputs(80, 3, 16, 512, 768, flow_scale=3.0)
     assert_close(dcb.softsplat(tin.cuda(), flow.cuda(), metric.cuda(), "soft"), orc.softsplat(tin, flow, metric, "soft"), 1e-5, "lists groups")
 
 

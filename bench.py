@@ -259,6 +259,28 @@ def _extras(torch, d, dev, gen, peak):
         ms = _time_cuda(torch, lambda: d.softsplat(ti.detach(), fl.detach(), me.detach(), "soft"), 10, 3)
         ex["C4_soft_fwd_only_8x64x256x256_f32"] = {"us": round(ms * 1e3, 1), "mpixel_s": round(px / ms / 1e3, 1),
                                                    "alg_gbs": round(131 * 4 * px / ms / 1e6, 1), "frac_of_peak": round(131 * 4 * px / ms / 1e6 / peak, 3)}
+        del ti, me, fl, go
+        # f-3: Hann-window tile merge (patch_utils.py:83-174): a 1080p canvas from 512^2 tiles with 64 px overlap
+        # (patch_exp.ipynb cell 3), at pixel scale (3 channels) and at latent scale (4 channels, 8x smaller)
+        def torch_eager_merge(tiles, rects, full):
+            # the reference's composition as executed by torch on the same GPU (exact-fit tiles: no resize)
+            out = torch.zeros(full, device=dev); weight = torch.zeros_like(out)
+            for t, (y1, y2, x1, x2) in zip(tiles, rects):
+                wy = torch.hann_window(y2 - y1, periodic=False, device=dev); wx = torch.hann_window(x2 - x1, periodic=False, device=dev)
+                m = wy.unsqueeze(1) * wx.unsqueeze(0); m = (m / (m.max() + 1e-12)).expand(1, t.size(1), y2 - y1, x2 - x1)
+                out[:, :, y1:y2, x1:x2] += t * m; weight[:, :, y1:y2, x1:x2] += m
+            return out / torch.maximum(weight, torch.tensor(1e-8, device=dev))
+        for tag, ch, div in (("pixel_3x1080x1920", 3, 1), ("latent_4x135x240", 4, 8)):
+            hh, ww, ts, ov = H // div, W // div, 512 // div, 64 // div
+            rects = [(y, min(y + ts, hh), x, min(x + ts, ww)) for y in range(0, hh, ts - ov) for x in range(0, ww, ts - ov)]
+            tiles = [torch.randn(1, ch, y2 - y1, x2 - x1, device=dev, generator=gen) for (y1, y2, x1, x2) in rects]
+            as_read = [(x1, x2, y1, y2) for (y1, y2, x1, x2) in rects]
+            ms = _time_cuda(torch, lambda: d.merge_latent_tiles_from_pixel_coords(tiles, as_read, (1, ch, hh, ww), (hh, ww)), 20, 3)
+            ms_ref = _time_cuda(torch, lambda: torch_eager_merge(tiles, rects, (1, ch, hh, ww)), 5, 2)
+            byts = 4 * (sum(t.numel() for t in tiles) + ch * hh * ww)
+            ex[f"f3_tile_merge_{tag}_{len(tiles)}tiles_f32"] = {"us": round(ms * 1e3, 1), "alg_gbs": round(byts / ms / 1e6, 1),
+                                                               "frac_of_peak": round(byts / ms / 1e6 / peak, 3),
+                                                               "torch_eager_same_gpu_us": round(ms_ref * 1e3, 1)}
     except Exception as e:  # extras must never take the headline line down
         ex["error"] = repr(e)
     return ex

@@ -17,6 +17,7 @@ from .extractors import bidir_fuse, bidirectional_warp_fuse
 from .residual_utils import residual_conditioning, ResidueDataset, WarpingDatasetWrapper
 from .sharding import UVG_SEQUENCES, GopUnit, enumerate_gops, shard_units, gather_checksums, gather_outputs, checksum
 from .host import softsplat_host
+from .patch_utils import merge_latent_tiles_from_pixel_coords, crop_into_tiles
 from . import flow_io
 from .dropin import install
 

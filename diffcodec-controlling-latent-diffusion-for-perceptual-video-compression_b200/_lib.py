@@ -42,7 +42,9 @@ class DcbTensor(ctypes.Structure):
 # ctypes.Structure costs ~6.5 us per tensor, struct.pack ~1.5 us -- it matters for latent-sized calls.
 _P = ctypes.c_void_p
 _I64x4 = ctypes.c_int64 * 4
-_pack_desc = struct.Struct("Pii4q4q").pack
+_DESC_STRUCT = struct.Struct("Pii4q4q")
+_pack_desc = _DESC_STRUCT.pack
+_pack_desc_into = _DESC_STRUCT.pack_into
 assert struct.calcsize("Pii4q4q") == ctypes.sizeof(DcbTensor)
 _lib = None
 _lock = threading.Lock()
@@ -66,6 +68,9 @@ SYMBOLS = {
     "dcb_residual_workspace_bytes": (ctypes.c_int64, [ctypes.c_int64] * 4),
     "dcb_bidir_fuse_fwd": (ctypes.c_int, [_P] * 7 + [ctypes.c_void_p]),
     "dcb_bidir_fuse_bwd": (ctypes.c_int, [_P] * 11 + [ctypes.c_void_p]),
+    "dcb_tile_merge_workspace_bytes": (ctypes.c_int64, [ctypes.c_int64] * 3 + [ctypes.c_int32]),
+    "dcb_tile_merge": (ctypes.c_int, [_P, ctypes.c_void_p, ctypes.c_int32, _P, ctypes.c_int64, ctypes.c_int64, ctypes.c_double,
+                                      ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p]),
     "dcb_residual_fused": (ctypes.c_int, [_P] * 8 + [ctypes.c_void_p, ctypes.c_int64, ctypes.c_int32, ctypes.c_int32, ctypes.c_void_p]),
 }
 

@@ -56,6 +56,10 @@ int bidir_fuse_bwd_impl(const DcbTensor*, const DcbTensor*, const DcbTensor*, co
                         const DcbTensor*, const DcbTensor*, const DcbTensor*, const DcbTensor*, const DcbTensor*,
                         const DcbTensor*, cudaStream_t);
 
+long long tile_merge_workspace(long long C, long long H, long long W, int n_tiles);
+int tile_merge_impl(const DcbTensor*, const long long*, int, const DcbTensor*, long long, long long, double, void*, long long,
+                    cudaStream_t);
+
 // ---------------------------------------------------------------------------------------------
 // validation helpers
 // ---------------------------------------------------------------------------------------------
@@ -127,7 +131,7 @@ const char* dcb_build_info(void) {
     return "libdiffcodec_b200 " __DATE__ " nvcc " DCB_STR(__CUDACC_VER_MAJOR__) "." DCB_STR(__CUDACC_VER_MINOR__)
            " target sm_100a; kernels: k_splat_step k_planar_step k_list_count k_list_alloc k_list_fill k_list_gather k_scatter_planar k_normalize k_bwd_target k_bwd_source "
            "k_backwarp_rows k_backwarp_fwd k_backwarp_bwd k_cast_f32_bf16 k_recipe_fuse k_bidir_fuse_fwd k_bidir_fuse_bwd "
-           "k_det_emit k_det_reduce";
+           "k_det_emit k_det_reduce k_tile_merge";
 }
 
 int64_t dcb_splat_fwd_workspace_bytes(int64_t N, int64_t C, int64_t H, int64_t W, int32_t dtype, int32_t mode, int32_t flags) {
@@ -381,6 +385,35 @@ int dcb_bidir_fuse_bwd(const DcbTensor* g, const DcbTensor* A, const DcbTensor* 
         TRY(check_out(fn, names[i], outs[i], A->dtype, elem_size(A->dtype)));
     }
     return bidir_fuse_bwd_impl(g, A, B, ca, cb, oa, ob, gA, gB, gca, gcb, (cudaStream_t)stream);
+}
+
+int64_t dcb_tile_merge_workspace_bytes(int64_t C, int64_t H, int64_t W, int32_t n_tiles) {
+    if (C < 0 || H < 0 || W < 0 || n_tiles < 0) return 0;
+    return (int64_t)tile_merge_workspace(C, H, W, n_tiles);
+}
+
+int dcb_tile_merge(const DcbTensor* tiles, const int64_t* pixel_coords, int32_t n_tiles, const DcbTensor* out, int64_t H_px,
+                   int64_t W_px, double eps, void* ws, int64_t ws_bytes, void* stream) {
+    const char* fn = "dcb_tile_merge";
+    TRY(check_tensor(fn, "out", out, true));
+    if (out->dtype != DCB_F32 && out->dtype != DCB_BF16) return set_error(DCB_E_DTYPE, "%s: F32 or BF16 only, got %d", fn, out->dtype);
+    TRY(check_out(fn, "out", out, out->dtype, elem_size(out->dtype)));
+    TRY(check_limits(fn, out));
+    if (n_tiles < 0) return set_error(DCB_E_SHAPE, "%s: n_tiles = %d", fn, n_tiles);
+    if (n_tiles > 0 && (!tiles || !pixel_coords)) return set_error(DCB_E_NULL, "%s: tiles and pixel_coords are required", fn);
+    if (H_px <= 0 || W_px <= 0) return set_error(DCB_E_SHAPE, "%s: original image size %lld x %lld", fn, (long long)H_px, (long long)W_px);
+    for (int i = 0; i < n_tiles; ++i) {
+        const DcbTensor* t = tiles + i;
+        TRY(check_tensor(fn, "tile", t, true));
+        if (t->dtype != out->dtype) return set_error(DCB_E_DTYPE, "%s: tile %d has dtype %d, canvas %d", fn, i, t->dtype, out->dtype);
+        if (t->size[0] != 1 || t->size[1] != out->size[1])                                  // patch_utils.py:155
+            return set_error(DCB_E_SHAPE, "%s: tile %d is [%lld,%lld,..], expected [1,%lld,h,w]", fn, i, (long long)t->size[0],
+                             (long long)t->size[1], (long long)out->size[1]);
+        if (t->size[2] <= 0 || t->size[3] <= 0 || t->size[2] >= (1 << 24) || t->size[3] >= (1 << 24))
+            return set_error(DCB_E_SHAPE, "%s: tile %d has an empty or oversized plane", fn, i);
+    }
+    static_assert(sizeof(long long) == sizeof(int64_t), "int64_t coordinates");
+    return tile_merge_impl(tiles, (const long long*)pixel_coords, n_tiles, out, H_px, W_px, eps, ws, ws_bytes, (cudaStream_t)stream);
 }
 
 }  // extern "C"

@@ -35,3 +35,7 @@ def install(force: bool = True) -> None:
     full = "cmp.models.modules.warp"
     if full in sys.modules:
         sys.modules[full].WarpingLayerBWFlow = warp.WarpingLayerBWFlow
+    # patch_utils.py is a top-level script module of the reference (cv2 / PIL imports): patch it if it is loaded
+    if "patch_utils" in sys.modules:
+        tiles = importlib.import_module(__package__ + ".patch_utils")
+        sys.modules["patch_utils"].merge_latent_tiles_from_pixel_coords = tiles.merge_latent_tiles_from_pixel_coords

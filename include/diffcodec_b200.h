@@ -196,6 +196,23 @@ int dcb_bidir_fuse_bwd(const DcbTensor* grad_fused, const DcbTensor* A, const Dc
                        const DcbTensor* grad_A, const DcbTensor* grad_B, const DcbTensor* grad_conf_a,
                        const DcbTensor* grad_conf_b, void* stream);
 
+/*
+ * Hann-window merge of overlapping latent tiles into one canvas, in one gather kernel.
+ * Replaces merge_latent_tiles_from_pixel_coords(), patch_utils.py:83-174:
+ *   per tile (list order): pixel rectangle -> latent rectangle (int(round()), clamped; the 4-tuple is
+ *   read as (x1, x2, y1, y2), i.e. entries 2,3 scale with H / H_px and entries 0,1 with W / W_px, as the
+ *   reference executes it); bilinear resize (align_corners = 0) if the stored tile size differs;
+ *   mask = hann(h) x hann(w) / (max + 1e-12); out[rect] += tile * mask; weight[rect] += mask;
+ *   merged = out / max(weight, eps).
+ * tiles: array of n_tiles descriptors, each [1,C,th,tw] (any strides, dtype of `out`);
+ * pixel_coords: n_tiles * 4 int64; out [N,C,H,W] contiguous (N > 1 receives N copies, like the
+ * reference's broadcast); F32 or BF16. Tiles whose rectangle is empty are skipped. Lists longer than
+ * 48 tiles need a workspace (dcb_tile_merge_workspace_bytes), shorter ones none.
+ */
+int64_t dcb_tile_merge_workspace_bytes(int64_t C, int64_t H, int64_t W, int32_t n_tiles);
+int dcb_tile_merge(const DcbTensor* tiles, const int64_t* pixel_coords, int32_t n_tiles, const DcbTensor* out,
+                   int64_t H_px, int64_t W_px, double eps, void* workspace, int64_t workspace_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

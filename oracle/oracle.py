@@ -239,3 +239,65 @@ def backwarp(image, flow, align_corners=None):
     if align_corners is None:
         return torch.nn.functional.grid_sample(image, grid)  # as executed: default False
     return torch.nn.functional.grid_sample(image, grid, align_corners=bool(align_corners))
+
+
+# ---------------------------------------------------------------------------------------------
+# f-3: latent tile merge (patch_utils.py:83-174) and tile cropping (patch_utils.py:189-209)
+# ---------------------------------------------------------------------------------------------
+def _hann_2d(h: int, w: int, dtype):
+    """patch_utils.py:121-133: outer product of two non-periodic Hann windows, max-normalised."""
+    wy = torch.ones(1, dtype=dtype) if h <= 1 else torch.hann_window(h, periodic=False, dtype=dtype)
+    wx = torch.ones(1, dtype=dtype) if w <= 1 else torch.hann_window(w, periodic=False, dtype=dtype)
+    m = wy.unsqueeze(1) * wx.unsqueeze(0)
+    return m / (m.max() + 1e-12)
+
+
+def tile_rects(pixel_coords, full_latent_shape, original_image_size):
+    """patch_utils.py:135-154. The coordinate tuple is unpacked as (x1, x2, y1, y2) although
+    crop_into_tiles() produces (y1, y2, x1, x2): positions 2,3 are scaled by the HEIGHT ratio and
+    positions 0,1 by the WIDTH ratio, as executed. Returns (ly1, ly2, lx1, lx2) per tile, clamped;
+    Python's round() is round-half-to-even."""
+    _, _, h_lat, w_lat = full_latent_shape
+    h_px, w_px = original_image_size
+    rects = []
+    for (p0, p1, p2, p3) in pixel_coords:
+        ly1 = int(round(p2 * (h_lat / float(h_px)))); ly2 = int(round(p3 * (h_lat / float(h_px))))
+        lx1 = int(round(p0 * (w_lat / float(w_px)))); lx2 = int(round(p1 * (w_lat / float(w_px))))
+        ly1 = max(0, min(ly1, h_lat)); ly2 = max(0, min(ly2, h_lat))
+        lx1 = max(0, min(lx1, w_lat)); lx2 = max(0, min(lx2, w_lat))
+        rects.append((ly1, ly2, lx1, lx2))
+    return rects
+
+
+def merge_latent_tiles_from_pixel_coords(latents, pixel_coords, full_latent_shape, original_image_size, eps: float = 1e-8):
+    """Restatement of patch_utils.py:83-174 with torch CPU ops in the reference's order: per tile
+    (list order) optional bilinear resize (align_corners=False) to its latent rectangle, Hann
+    mask, out += tile * mask, weight += mask; merged = out / max(weight, eps)."""
+    assert len(latents) == len(pixel_coords), "latents and coords length mismatch"
+    dtype = latents[0].dtype
+    out = torch.zeros(full_latent_shape, dtype=dtype)
+    weight = torch.zeros_like(out)
+    for tile, (ly1, ly2, lx1, lx2) in zip(latents, tile_rects(pixel_coords, full_latent_shape, original_image_size)):
+        th_, tw_ = ly2 - ly1, lx2 - lx1
+        if th_ <= 0 or tw_ <= 0:
+            continue                                              # patch_utils.py:149-151
+        assert tile.dim() == 4 and tile.size(0) == 1, "expected tile shape (1,C,H,W)"
+        if tile.shape[-2] != th_ or tile.shape[-1] != tw_:
+            tile = torch.nn.functional.interpolate(tile, size=(th_, tw_), mode="bilinear", align_corners=False)
+        mask = _hann_2d(th_, tw_, dtype).unsqueeze(0).unsqueeze(0).expand(1, tile.size(1), th_, tw_)
+        out[:, :, ly1:ly2, lx1:lx2] += tile * mask
+        weight[:, :, ly1:ly2, lx1:lx2] += mask
+    return out / torch.maximum(weight, torch.tensor(eps, dtype=dtype))
+
+
+def crop_into_tiles(img, tile_size, overlap: int = 0, order: str = "hwc"):
+    """patch_utils.py:189-209: row-major overlapping crops; coords are (y, y2, x, x2)."""
+    h, w = (img.shape[0], img.shape[1]) if order == "hwc" else (img.shape[1], img.shape[2])
+    sy, sx = tile_size[0] - overlap, tile_size[1] - overlap
+    tiles, coords = [], []
+    for y in range(0, h, sy):
+        for x in range(0, w, sx):
+            y2, x2 = min(y + tile_size[0], h), min(x + tile_size[1], w)
+            tiles.append(img[y:y2, x:x2, :] if order == "hwc" else img[:, y:y2, x:x2])
+            coords.append((y, y2, x, x2))
+    return tiles, coords, (h, w)

@@ -237,3 +237,69 @@ def test_bidirectional_block(dcb, orc):
     same = (dcb.compute_mask(ff.cuda(), fb.cuda()).cpu() == of) & (dcb.compute_mask(fb.cuda(), ff.cuda()).cpu() == ob)
     assert same.float().mean() > 0.999
     assert_close(got.cpu()[same.expand_as(ref)], ref[same.expand_as(ref)], 1e-5, "bidirectional block")
+
+
+# ---------------------------------------------------------------------------------------------
+# f-3: latent tile merge (patch_utils.py:83-174)
+# ---------------------------------------------------------------------------------------------
+import glob as _glob
+import os as _os
+
+import numpy as _np
+
+_TILE_GOLDEN = sorted(_glob.glob(_os.path.join(_os.path.dirname(__file__), "golden", "ref_tiles_*.npz")))
+
+
+@pytest.mark.parametrize("path", _TILE_GOLDEN, ids=[_os.path.basename(p) for p in _TILE_GOLDEN])
+def test_tile_merge_matches_reference_golden(dcb, path):
+    """The CUDA gather kernel against the output of the reference's own function (oracle/ref_tiles.py)."""
+    z = _np.load(path)
+    tiles = [torch.from_numpy(z[k]).cuda() for k in sorted(k for k in z.files if k.startswith("tile_"))]
+    coords = [tuple(int(v) for v in r) for r in z["coords"]]
+    full, size = tuple(int(v) for v in z["full"]), tuple(int(v) for v in z["size"])
+    got = dcb.merge_latent_tiles_from_pixel_coords(tiles, coords, full, size)
+    want = torch.from_numpy(z["out"])
+    assert got.shape == want.shape and got.dtype == torch.float32
+    assert_close(got, want, 1e-5, "tile merge vs reference")
+    assert torch.equal(got.cpu() == 0, want == 0)          # uncovered / zero-weight pixels are exactly 0, like the reference's 0 / eps
+
+
+def test_tile_merge_full_frame_crop_roundtrip(dcb, orc):
+    """1080p-like canvas at pixel scale: crop_into_tiles views (non-contiguous tiles) merged back.
+    With coordinates in the order the merge reads them, every interior pixel is the input again."""
+    g = torch.Generator().manual_seed(5)
+    img = torch.randn(3, 270, 480, generator=g)
+    tiles, coords, (h, w) = dcb.crop_into_tiles(img.cuda(), (128, 128), overlap=16, order="chw")
+    as_read = [(x, x2, y, y2) for (y, y2, x, x2) in coords]                     # (x1, x2, y1, y2), patch_utils.py:135
+    got = dcb.merge_latent_tiles_from_pixel_coords([t.unsqueeze(0) for t in tiles], as_read, (1, 3, h, w), (h, w))
+    ref = orc.merge_latent_tiles_from_pixel_coords([t.unsqueeze(0).cpu() for t in tiles], as_read, (1, 3, h, w), (h, w))
+    assert_close(got, ref, 1e-5, "crop -> merge")
+    inner = got[0, :, 1:-1, 1:-1].cpu()
+    covered = ref[0, :, 1:-1, 1:-1] != 0
+    assert_close(inner[covered], img[:, 1:-1, 1:-1][covered], 1e-5, "merge of crops reproduces the frame")
+
+
+def test_tile_merge_long_lists_resize_batch_and_bf16(dcb, orc):
+    g = torch.Generator().manual_seed(6)
+    # 130 tiles (> 48 per launch: chained through the workspace canvas), every one resized, canvas batch of 2
+    coords, lat = [], []
+    for i in range(130):
+        x1 = int(torch.randint(0, 180, (1,), generator=g)); y1 = int(torch.randint(0, 100, (1,), generator=g))
+        coords.append((x1, x1 + int(torch.randint(8, 70, (1,), generator=g)), y1, y1 + int(torch.randint(8, 60, (1,), generator=g))))
+        lat.append(torch.randn(1, 6, int(torch.randint(2, 12, (1,), generator=g)), int(torch.randint(2, 12, (1,), generator=g)), generator=g))
+    full, size = (2, 6, 40, 64), (160, 256)
+    ref = orc.merge_latent_tiles_from_pixel_coords(lat, coords, full, size)
+    got = dcb.merge_latent_tiles_from_pixel_coords([t.cuda() for t in lat], coords, full, size)
+    assert_close(got, ref, 2e-5, "130 resized tiles")
+    assert torch.equal(got[0], got[1])
+    # bf16 tiles: fp32 accumulation, within 1e-2 of the fp32 reference on the same (rounded) tiles
+    lat16 = [t.bfloat16() for t in lat[:20]]
+    ref16 = orc.merge_latent_tiles_from_pixel_coords([t.float() for t in lat16], coords[:20], (1, 6, 40, 64), size)
+    got16 = dcb.merge_latent_tiles_from_pixel_coords([t.cuda() for t in lat16], coords[:20], (1, 6, 40, 64), size)
+    assert got16.dtype == torch.bfloat16
+    assert_close(got16.float(), ref16, 1e-2, "bf16 tiles")
+    # every tile outside the canvas: all zeros, like 0 / eps
+    out = dcb.merge_latent_tiles_from_pixel_coords([lat[0].cuda()], [(500, 520, 500, 520)], (1, 6, 40, 64), size)
+    assert float(out.abs().max()) == 0.0
+    with pytest.raises(AssertionError):
+        dcb.merge_latent_tiles_from_pixel_coords([lat[0].cuda()], coords[:2], full, size)

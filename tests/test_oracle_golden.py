@@ -65,3 +65,36 @@ def test_mode_wrapper_matches_reference(path, mode):
     r = _run_oracle(z, mode)
     for k, v in r.items():
         assert np.array_equal(v, z[f"{mode}/{k}"], equal_nan=True), (mode, k)
+
+
+TILE_GOLDEN = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "ref_tiles_*.npz")))
+
+
+def load_tile_case(path):
+    z = np.load(path)
+    tiles = [torch.from_numpy(z[k]) for k in sorted(k for k in z.files if k.startswith("tile_"))]
+    coords = [tuple(int(v) for v in r) for r in z["coords"]]
+    return tiles, coords, tuple(int(v) for v in z["full"]), tuple(int(v) for v in z["size"]), torch.from_numpy(z["out"])
+
+
+@pytest.mark.parametrize("path", TILE_GOLDEN, ids=[os.path.basename(p) for p in TILE_GOLDEN])
+def test_tile_merge_oracle_matches_reference_function(path):
+    """oracle.merge_latent_tiles_from_pixel_coords == the reference's own function text (oracle/ref_tiles.py)."""
+    from oracle import oracle as orc
+    tiles, coords, full, size, want = load_tile_case(path)
+    got = orc.merge_latent_tiles_from_pixel_coords(tiles, coords, full, size)
+    assert torch.equal(got, want)
+
+
+def test_tile_golden_set_is_complete():
+    assert len(TILE_GOLDEN) == 3
+
+
+def test_crop_into_tiles_matches_oracle():
+    from oracle import oracle as orc
+    import diffcodec_b200 as d
+    img = np.arange(3 * 50 * 70, dtype=np.float32).reshape(3, 50, 70)
+    for ts, ov, order, arr in (((32, 32), 8, "chw", img), ((20, 48), 0, "hwc", img.transpose(1, 2, 0))):
+        a, ca, sa = d.crop_into_tiles(arr, ts, overlap=ov, order=order)
+        b, cb, sb = orc.crop_into_tiles(arr, ts, overlap=ov, order=order)
+        assert ca == cb and sa == sb and len(a) == len(b) and all(np.array_equal(x, y) for x, y in zip(a, b))

@@ -132,7 +132,15 @@ def desc(t: torch.Tensor | None):
     return _pack_desc(t.data_ptr(), _DTYPES[t.dtype], 0, *t.shape, *t.stride())
 
 
+_raw_stream = getattr(torch._C, "_cuda_getCurrentRawStream", None)
+
+
 def stream_ptr(device) -> int:
+    """cudaStream_t of torch's current stream on `device` (the raw getter costs 0.3 us, the
+    Stream object of torch.cuda.current_stream() 5 us -- a quarter of a latent-sized call)."""
+    if _raw_stream is not None:
+        idx = device.index
+        return _raw_stream(torch.cuda.current_device() if idx is None else idx)
     return torch.cuda.current_stream(device).cuda_stream
 
 

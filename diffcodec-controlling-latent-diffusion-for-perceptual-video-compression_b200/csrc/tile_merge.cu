@@ -59,6 +59,24 @@ __device__ __forceinline__ void bilinear_axis(int dst, float scale, int in_size,
 template <class T>
 __global__ void __launch_bounds__(256) k_tile_merge(const __grid_constant__ MergeArgs a) {
     const unsigned r = blockIdx.x * 256 + threadIdx.x;
+    // which tiles touch this CTA's 256 pixels at all? two ballots, kept as bit masks so that the
+    // tiles are still visited in list order (typically 1-4 of them instead of all 15-48)
+    __shared__ unsigned live_mask[2];
+    if (threadIdx.x < 64) {
+        const unsigned r0 = blockIdx.x * 256, r1 = min(r0 + 255u, a.HW - 1);
+        const int ya = (int)(r0 / (unsigned)a.W), yb = (int)(r1 / (unsigned)a.W);
+        const int xa = ya == yb ? (int)(r0 - (unsigned)ya * (unsigned)a.W) : 0;
+        const int xb = ya == yb ? (int)(r1 - (unsigned)ya * (unsigned)a.W) : a.W - 1;
+        const int i = threadIdx.x;
+        bool hit = false;
+        if (i < a.n) {
+            const TileDesc& t = a.t[i];
+            hit = t.y0 <= yb && t.y0 + t.h > ya && t.x0 <= xb && t.x0 + t.w > xa;
+        }
+        const unsigned m = __ballot_sync(0xffffffffu, hit);
+        if ((threadIdx.x & 31) == 0) live_mask[threadIdx.x >> 5] = m;
+    }
+    __syncthreads();
     if (r >= a.HW) return;
     const int y = (int)(r / (unsigned)a.W), x = (int)(r - (unsigned)y * (unsigned)a.W);
     float wsum = 0.f;
@@ -72,7 +90,10 @@ __global__ void __launch_bounds__(256) k_tile_merge(const __grid_constant__ Merg
                 if (c0 + j < a.C) acc[j] = a.canvas[(size_t)(c0 + j) * a.HW + r];
             if (c0 == 0) wsum = a.canvas[(size_t)a.C * a.HW + r];
         }
-        for (int i = 0; i < a.n; ++i) {
+        unsigned long long todo = ((unsigned long long)live_mask[1] << 32) | live_mask[0];
+        while (todo) {
+            const int i = __ffsll((long long)todo) - 1;
+            todo &= todo - 1;
             const TileDesc& t = a.t[i];
             const int ty = y - t.y0, tx = x - t.x0;
             if ((unsigned)ty >= (unsigned)t.h || (unsigned)tx >= (unsigned)t.w) continue;

@@ -37,6 +37,7 @@ struct BwdArgs {
     int N, C, H, W;
     int mode, eps;
     int px, cs;          // block shape
+    unsigned pf_dist;    // source pass: L2 prefetch distance in CTAs (one wave)
 };
 
 // K3a -- target-side scalars. 8 channels (16 loads) in flight per thread.
@@ -76,10 +77,13 @@ __global__ void __launch_bounds__(256) k_bwd_target(const BwdArgs a) {
 
 // K3b -- source-side gather. blockDim = (px, cs): px source pixels, cs channel slices per pixel.
 // Loads are unconditional from always-valid addresses (an out-of-range corner reads element 0 of
-// its plane and is then zeroed by a select): no branches in the channel loop, 2 channels = 10
+// its plane and is then zeroed by a select): no branches in the channel loop, 3 channels = 15
 // loads in flight per thread.
 #ifndef DCB_BS_U
-#define DCB_BS_U 2           // channels in flight per thread (5 loads each); 64 registers -> 4 CTAs per SM
+#define DCB_BS_U 3           // channels in flight per thread (5 loads each); 64 registers -> 4 CTAs per SM (measured best of 1..6)
+#endif
+#ifndef DCB_BS_PF
+#define DCB_BS_PF 1
 #endif
 #ifndef DCB_BS_MINCTAS
 #define DCB_BS_MINCTAS 4
@@ -93,6 +97,28 @@ __global__ void __launch_bounds__(256, DCB_BS_MINCTAS) k_bwd_source(const BwdArg
     A* red = (A*)smem_raw;                                        // [cs][px][4] when cs > 1
 
     const int tx = threadIdx.x, ty = threadIdx.y;
+#if DCB_BS_PF
+    if (a.cs == 1) {
+        // L2 prefetch of the rows the CTA one wave ahead will stream (flow, metric, and up to 8 channels of
+        // `in` and gradOut at the zero-flow position): one 128-byte line per thread
+        const unsigned q0 = (blockIdx.x + a.pf_dist) * 256u;
+        if (q0 < a.total) {
+            const unsigned qn = q0 / a.HW, qr = q0 - qn * a.HW;
+            const int qy = (int)(qr / (unsigned)a.W), qx = (int)(qr - (unsigned)qy * (unsigned)a.W);
+            const int line = tx & 7, plane = tx >> 3;                      // 8 lines of 32 pixels, 32 planes
+            const int cmax = a.C < 8 ? a.C : 8;
+            const int px = qx + line * 32;
+            if (px < a.W) {
+                const void* q = nullptr;
+                if (plane < 2) q = (const TF*)a.flow.p + qn * a.flow.sN + plane * a.flow.sC + qy * a.flow.sH + px * a.flow.sW;
+                else if (plane == 2 && a.metric.p) q = (const T*)a.metric.p + qn * a.metric.sN + qy * a.metric.sH + px * a.metric.sW;
+                else if (plane >= 8 && plane < 8 + cmax) q = (const T*)a.in.p + qn * a.in.sN + (plane - 8) * a.in.sC + qy * a.in.sH + px * a.in.sW;
+                else if (plane >= 16 && plane < 16 + cmax) q = (const T*)a.gout.p + qn * a.gout.sN + (plane - 16) * a.gout.sC + qy * a.gout.sH + px * a.gout.sW;
+                if (q) asm volatile("prefetch.global.L2 [%0];" ::"l"(q));
+            }
+        }
+    }
+#endif
     const unsigned p = blockIdx.x * a.px + tx;
     const bool live = p < a.total;
     const unsigned pc = live ? p : 0;
@@ -251,6 +277,7 @@ static int launch_bwd(BwdArgs& a, cudaStream_t st) {
     while (cs < 32 && cs * 2 <= a.C && (long long)a.total * cs < 148LL * 2048) cs *= 2;
     a.cs = cs;
     a.px = 256 / cs;
+    a.pf_dist = (unsigned)(device_sm_count() * DCB_BS_MINCTAS);
     dim3 block(a.px, cs);
     const unsigned blocks = (a.total + a.px - 1) / a.px;
     const size_t smem = cs > 1 ? (size_t)256 * 4 * sizeof(A) : 0;

@@ -40,6 +40,9 @@ struct BwdArgs {
     unsigned pf_dist;    // source pass: L2 prefetch distance in CTAs (one wave)
 };
 
+#ifndef DCB_BS_PF
+#define DCB_BS_PF 1
+#endif
 // K3a -- target-side scalars. 8 channels (16 loads) in flight per thread.
 template <class T>
 __global__ void __launch_bounds__(256) k_bwd_target(const BwdArgs a) {
@@ -61,7 +64,17 @@ __global__ void __launch_bounds__(256) k_bwd_target(const BwdArgs a) {
 #pragma unroll
         for (int j = 0; j < U; ++j) dot += gv[j] * ov[j];
     }
-    for (; c < a.C; ++c) dot += ld<A>(gp + (long long)c * a.gout.sC) * ld<A>(op + (long long)c * a.HW);
+    if (c < a.C) {                                               // last partial block: the loads still go out together
+        A gv[U], ov[U];
+#pragma unroll
+        for (int j = 0; j < U; ++j) {
+            const bool in = c + j < a.C;
+            gv[j] = in ? ld<A>(gp + (long long)(c + j) * a.gout.sC) : (A)0;
+            ov[j] = in ? ld<A>(op + (long long)(c + j) * a.HW) : (A)0;
+        }
+#pragma unroll
+        for (int j = 0; j < U; ++j) dot += gv[j] * ov[j];
+    }
     A keep = (A)1;
     if (a.mask.p) {
         const T* mp = (const T*)a.mask.p + n * a.mask.sN + y * a.mask.sH + x * a.mask.sW;
@@ -81,9 +94,6 @@ __global__ void __launch_bounds__(256) k_bwd_target(const BwdArgs a) {
 // loads in flight per thread.
 #ifndef DCB_BS_U
 #define DCB_BS_U 3           // channels in flight per thread (5 loads each); 64 registers -> 4 CTAs per SM (measured best of 1..6)
-#endif
-#ifndef DCB_BS_PF
-#define DCB_BS_PF 1
 #endif
 #ifndef DCB_BS_MINCTAS
 #define DCB_BS_MINCTAS 4

@@ -244,6 +244,20 @@ def _extras(torch, d, dev, gen, peak):
         ex["C3_backwarp_residual_64x3x1080x1920_f32"] = {"ms": round(ms, 3), "mpixel_s": round(n3 * H * W / ms / 1e3, 1),
                                                          "alg_gbs": round(56 * n3 * H * W / ms / 1e6, 1), "frac_of_peak": round(56 * n3 * H * W / ms / 1e6 / peak, 3)}
         del img, gt, f1, f2
+        # forward + backward (all three gradients) on the headline's frames: (6C+10)*4 = 112 B/px
+        nb = 16
+        ti = torch.rand(nb, 3, H, W, device=dev, generator=gen).requires_grad_(True)
+        me = (-torch.rand(nb, 1, H, W, device=dev, generator=gen)).requires_grad_(True)
+        fl = _smooth_flow(torch, nb, H, W, 8.0, dev, gen).requires_grad_(True)
+        go = torch.randn(nb, 3, H, W, device=dev, generator=gen)
+        def fb():
+            ti.grad = me.grad = fl.grad = None
+            d.softsplat(ti, fl, me, "soft").backward(go)
+        ms = _time_cuda(torch, fb, 5, 2)
+        ex["headline_fwd_bwd_16x3x1080x1920_f32"] = {"us_per_frame": round(ms * 1e3 / nb, 1), "mpixel_s": round(nb * H * W / ms / 1e3, 1),
+                                                      "alg_gbs": round(112 * nb * H * W / ms / 1e6, 1),
+                                                      "frac_of_peak": round(112 * nb * H * W / ms / 1e6 / peak, 3)}
+        del ti, me, fl, go
         # C4: soft forward + backward on 8x64x256x256 fp32 (ControlNet training shape), all grads
         ti = torch.randn(8, 64, 256, 256, device=dev, generator=gen).requires_grad_(True)
         me = (torch.randn(8, 1, 256, 256, device=dev, generator=gen) * 0.5).requires_grad_(True)

@@ -327,6 +327,34 @@ def test_list_path_agrees_with_accumulator_path(dcb):
             assert_close(whole[n:n + 1], part, 1e-5, f"lists vs accumulators {mode} frame {n}")
 
 
+def test_list_path_mask_strides_and_saved_normaliser(dcb, orc):
+    """The list path behind FeatureWarperSoftsplat's call shape: (1 - mask) product, a channel-sliced
+    (non-contiguous) input, and the gradient w.r.t. everything through the saved normaliser."""
+    g = torch.Generator().manual_seed(83)
+    n, c, h, w = 2, 24, 192, 256
+    big = torch.randn(n, c + 8, h, w, generator=g)
+    flow = torch.randn(n, 2, h, w, generator=g) * 3
+    metric = torch.randn(n, 1, h, w, generator=g) * 0.5
+    mask = (torch.rand(n, 1, h, w, generator=g) > 0.7).float()
+    gout = torch.randn(n, c, h, w, generator=g)
+    # oracle: soft splat of the channel slice, times (1 - mask)   (control_utils.py:62-70)
+    ti = big[:, 4:4 + c].clone().requires_grad_(True); fl = flow.clone().requires_grad_(True); me = metric.clone().requires_grad_(True)
+    ref = orc.softsplat(ti, fl, me, "soft") * (1 - mask)
+    ref.backward(gout)
+    bigc = big.cuda()
+    tic = bigc[:, 4:4 + c].requires_grad_(True)              # a view: strides of the 32-channel tensor
+    assert not tic.is_contiguous()
+    flc = flow.cuda().requires_grad_(True); mec = metric.cuda().requires_grad_(True)
+    from diffcodec_b200.softsplat import _splat_normalised
+    from diffcodec_b200 import _lib
+    got = _splat_normalised(tic, flc, mec, _lib.MODE_SOFT, _lib.EPS_ADD, mask=mask.cuda())
+    got.backward(gout.cuda())
+    assert_close(got, ref, 1e-5, "lists + mask + strides")
+    assert_close(tic.grad, ti.grad, 2e-5, "gin")
+    assert_close(flc.grad, fl.grad, 1e-4, "gflow")
+    assert_close(mec.grad, me.grad, 1e-4, "gmetric")
+
+
 def test_mass_conservation_c4_shape(dcb):
     """BASELINE config C4 (8 x 64 x 256 x 256) through the list path: a 'sum' splat whose footprints all stay
     inside the frame moves mass without creating or losing any; 'avg' of a constant is that constant."""

@@ -31,7 +31,7 @@ int device_sm_count() {
 
 // implemented in the kernel translation units
 long long splat_fwd_workspace(long long N, long long C, long long H, long long W, int dtype, int mode);
-long long splat_bwd_workspace(long long N, long long H, long long W, int dtype, int mode);
+long long splat_bwd_workspace(long long N, long long C, long long H, long long W, int dtype, int mode);
 long long det_workspace(long long N, long long C, long long H, long long W, int dtype, int mode);
 int splat_fwd_impl(const DcbTensor*, const DcbTensor*, const DcbTensor*, const DcbTensor*, const DcbTensor*,
                    const DcbTensor*, void*, long long, int, int, int, cudaStream_t);
@@ -141,9 +141,9 @@ int64_t dcb_splat_fwd_workspace_bytes(int64_t N, int64_t C, int64_t H, int64_t W
 }
 
 int64_t dcb_splat_bwd_workspace_bytes(int64_t N, int64_t C, int64_t H, int64_t W, int32_t dtype, int32_t mode, int32_t flags) {
-    (void)C; (void)flags;
-    if (N < 0 || H < 0 || W < 0) return 0;
-    return (int64_t)splat_bwd_workspace(N, H, W, dtype, mode);
+    (void)flags;
+    if (N < 0 || C < 0 || H < 0 || W < 0) return 0;
+    return (int64_t)splat_bwd_workspace(N, C, H, W, dtype, mode);
 }
 
 int64_t dcb_splat_workspace_bytes(int64_t N, int64_t C, int64_t H, int64_t W, int32_t dtype, int32_t mode, int32_t flags) {

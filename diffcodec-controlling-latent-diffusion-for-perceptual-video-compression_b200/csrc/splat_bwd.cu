@@ -23,6 +23,8 @@
 // hundreds of channels); the A_k partials are then reduced through shared memory.
 #include "dcb_common.cuh"
 
+#include <type_traits>
+
 namespace dcb {
 
 struct BwdArgs {
@@ -270,14 +272,138 @@ __global__ void __launch_bounds__(256, DCB_BS_MINCTAS) k_bwd_source(const BwdArg
 }
 
 // ---------------------------------------------------------------------------------------------
-long long splat_bwd_workspace(long long N, long long H, long long W, int dtype, int mode) {
+// Few channels (C <= 3: frames, flows, masks) in fp32 / bf16, normalised modes: the target pass packs
+// everything the source pass needs from a target pixel into ONE float4
+//       P_c = a * G_c  (c < 3, zero-padded),   T
+// because  gradIn_c = g * sum_k w_k P_c(k)   and   B_k = a_k A_k + T_k = sum_c P_c(k) in_c + T_k.
+// The source pass then gathers one 16-byte cell per corner (4 loads) instead of C gradOut scalars
+// plus two scalars (20 loads at C = 3), and neighbouring lanes read neighbouring cells.
+// ---------------------------------------------------------------------------------------------
+template <class T>
+__global__ void __launch_bounds__(256) k_bwd_target4(const BwdArgs a) {
+    const unsigned p = blockIdx.x * 256 + threadIdx.x;
+    if (p >= a.total) return;
+    const unsigned n = p / a.HW, r = p - n * a.HW;
+    const int y = (int)(r / (unsigned)a.W), x = (int)(r - (unsigned)y * (unsigned)a.W);
+    const float d = ld_stream((const float*)a.norm + p);
+    const T* gp = (const T*)a.gout.p + n * a.gout.sN + y * a.gout.sH + x * a.gout.sW;
+    const T* op = (const T*)a.out + (long long)n * a.C * a.HW + r;
+    float gv[3] = {0.f, 0.f, 0.f}, ov[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+    for (int c = 0; c < 3; ++c)
+        if (c < a.C) { gv[c] = ld_stream(gp + (long long)c * a.gout.sC); ov[c] = ld_stream(op + (long long)c * a.HW); }
+    float dot = 0.f;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) dot += gv[c] * ov[c];
+    float keep = 1.f;
+    if (a.mask.p) {
+        const T* mp = (const T*)a.mask.p + n * a.mask.sN + y * a.mask.sH + x * a.mask.sW;
+        keep = 1.f - ld<float>(mp);
+    }
+    const float av = keep / d;
+    const bool clipped = a.eps == DCB_EPS_CLIP && d == 0.0000001f;     // see k_bwd_target
+    __stcg((float4*)a.tscal + p, make_float4(av * gv[0], av * gv[1], av * gv[2], clipped ? 0.f : -dot / d));
+}
+
+template <class T, class TF>
+__global__ void __launch_bounds__(256) k_bwd_source4(const BwdArgs a) {
+    const unsigned p = blockIdx.x * 256 + threadIdx.x;
+    if (p >= a.total) return;
+    const unsigned n = p / a.HW, r = p - n * a.HW;
+    const int y = (int)(r / (unsigned)a.W), x = (int)(r - (unsigned)y * (unsigned)a.W);
+    const int W = a.W, H = a.H;
+    const TF* fp = (const TF*)a.flow.p + n * a.flow.sN + y * a.flow.sH + x * a.flow.sW;
+    const Foot<float> f = make_foot<float>(x, y, (float)ld_stream(fp), (float)ld_stream(fp + a.flow.sC));
+    const int x1 = (int)((unsigned)f.x0 + 1u), y1 = (int)((unsigned)f.y0 + 1u);
+    const bool vx0 = (unsigned)f.x0 < (unsigned)W, vx1 = (unsigned)x1 < (unsigned)W;
+    const bool vy0 = (unsigned)f.y0 < (unsigned)H, vy1 = (unsigned)y1 < (unsigned)H;
+    const bool ok = f.finite;                                     // softsplat.py:389-390, 460-461
+    const bool b[4] = {ok && vx0 && vy0, ok && vx1 && vy0, ok && vx0 && vy1, ok && vx1 && vy1};
+    const bool any = b[0] || b[1] || b[2] || b[3];
+    const float w[4] = {f.wnw, f.wne, f.wsw, f.wse};
+
+    float g = 1.f, gprime = 1.f;
+    if (a.mode == DCB_MODE_LINEAR || a.mode == DCB_MODE_SOFT) {
+        const T* mp = (const T*)a.metric.p + n * a.metric.sN + y * a.metric.sH + x * a.metric.sW;
+        const float m = ld_stream(mp);
+        g = a.mode == DCB_MODE_SOFT ? expf(m) : m;
+        gprime = a.mode == DCB_MODE_SOFT ? g : 1.f;
+    }
+    // the four target cells: one 16-byte gather each (element 0 of the frame stands in for a corner out of range)
+    const float4* cell = (const float4*)a.tscal + (size_t)n * a.HW;
+    const int o0 = f.y0 * W + f.x0;
+    const int co[4] = {b[0] ? o0 : 0, b[1] ? o0 + 1 : 0, b[2] ? o0 + W : 0, b[3] ? o0 + W + 1 : 0};
+    float4 P[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) P[k] = __ldcg(cell + co[k]);
+    const T* ip = (const T*)a.in.p + n * a.in.sN + y * a.in.sH + x * a.in.sW;
+    float v[3] = {0.f, 0.f, 0.f};
+    const bool need_A = (a.gflow != nullptr) || (a.gmetric != nullptr);
+    if (need_A) {
+#pragma unroll
+        for (int c = 0; c < 3; ++c)
+            if (c < a.C) v[c] = ld_stream(ip + (long long)c * a.in.sC);
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+        if (!b[k]) P[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+
+    if (a.gin) {
+        T* gi = (T*)a.gin + (long long)n * a.C * a.HW + r;
+        // a dropped corner carries P = 0, but its weight may be inf (huge finite flow): keep 0 * inf out
+        const float wz[4] = {b[0] ? w[0] : 0.f, b[1] ? w[1] : 0.f, b[2] ? w[2] : 0.f, b[3] ? w[3] : 0.f};
+        const float s0 = fma_rn(P[3].x, wz[3], fma_rn(P[2].x, wz[2], fma_rn(P[1].x, wz[1], mul_rn(P[0].x, wz[0]))));
+        const float s1 = fma_rn(P[3].y, wz[3], fma_rn(P[2].y, wz[2], fma_rn(P[1].y, wz[1], mul_rn(P[0].y, wz[0]))));
+        const float s2 = fma_rn(P[3].z, wz[3], fma_rn(P[2].z, wz[2], fma_rn(P[1].z, wz[1], mul_rn(P[0].z, wz[0]))));
+        st_stream(gi, (any ? s0 : 0.f) * g);
+        if (a.C > 1) st_stream(gi + a.HW, (any ? s1 : 0.f) * g);
+        if (a.C > 2) st_stream(gi + 2ll * a.HW, (any ? s2 : 0.f) * g);
+    }
+    if (!need_A) return;
+    float B[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+        B[k] = b[k] ? fma_rn(P[k].x, v[0], fma_rn(P[k].y, v[1], fma_rn(P[k].z, v[2], P[k].w))) : 0.f;
+    if (a.gmetric) {
+        float s = 0.f;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) if (b[k]) s = fma_rn(w[k], B[k], s);
+        st<T, float>((T*)a.gmetric + p, any ? s * gprime : 0.f);
+    }
+    if (a.gflow) {
+        const float ey = sub_rn((float)y1, f.fy), dy = sub_rn(f.fy, (float)f.y0);      // d w / d flow, softsplat.py:477-487
+        const float ex = sub_rn((float)x1, f.fx), dx = sub_rn(f.fx, (float)f.x0);
+        float gx = (B[1] - B[0]) * ey + (B[3] - B[2]) * dy;
+        float gy = (B[2] - B[0]) * ex + (B[3] - B[1]) * dx;
+        if (!any) { gx = 0.f; gy = 0.f; }
+        TF* gf = (TF*)a.gflow + (long long)n * 2 * a.HW + r;
+        st<TF, float>(gf, gx * g);
+        st<TF, float>(gf + a.HW, gy * g);
+    }
+}
+
+static bool packed_bwd(int C, int dtype, int mode) { return C <= 3 && mode != DCB_MODE_SUM && dtype != DCB_F64; }
+
+// ---------------------------------------------------------------------------------------------
+long long splat_bwd_workspace(long long N, long long C, long long H, long long W, int dtype, int mode) {
     if (mode == DCB_MODE_SUM) return 0;
+    if (packed_bwd((int)(C > 3 ? 4 : C), dtype, mode)) return align_up(N * H * W * 16, 256);      // one float4 per target pixel
     return align_up(N * H * W * 2 * (dtype == DCB_F64 ? 8 : 4), 256);
 }
 
 template <class T, class TF>
-static int launch_bwd(BwdArgs& a, cudaStream_t st) {
+static int launch_bwd(BwdArgs& a, int dtype, cudaStream_t st) {
     using A = typename Acc<T>::type;
+    if constexpr (!std::is_same<T, double>::value) {
+        if (packed_bwd(a.C, dtype, a.mode)) {
+            const unsigned blocks = (a.total + 255) / 256;
+            k_bwd_target4<T><<<blocks, 256, 0, st>>>(a);
+            DCB_CHECK_LAUNCH("k_bwd_target4");
+            k_bwd_source4<T, TF><<<blocks, 256, 0, st>>>(a);
+            DCB_CHECK_LAUNCH("k_bwd_source4");
+            return DCB_OK;
+        }
+    }
     if (a.mode != DCB_MODE_SUM) {
         k_bwd_target<T><<<(a.total + 255) / 256, 256, 0, st>>>(a);
         DCB_CHECK_LAUNCH("k_bwd_target");
@@ -326,7 +452,7 @@ int splat_bwd_impl(const DcbTensor* gout, const DcbTensor* in, const DcbTensor* 
     if (a.total == 0) return DCB_OK;
     if (!a.gin && !a.gflow && !a.gmetric) return DCB_OK;
     if (mode != DCB_MODE_SUM) {
-        const long long need = splat_bwd_workspace(a.N, a.H, a.W, in->dtype, mode);
+        const long long need = splat_bwd_workspace(a.N, a.C, a.H, a.W, in->dtype, mode);
         if (!ws || ws_bytes < need || ((uintptr_t)ws & 255))
             return set_error(DCB_E_WORKSPACE, "splat_bwd: workspace of %lld bytes (256 B aligned) required, got %lld",
                              need, ws_bytes);
@@ -334,10 +460,10 @@ int splat_bwd_impl(const DcbTensor* gout, const DcbTensor* in, const DcbTensor* 
     }
     const bool flow_f32 = flow->dtype == DCB_F32;
     switch (in->dtype) {
-        case DCB_F32: return launch_bwd<float, float>(a, st);
-        case DCB_F64: return launch_bwd<double, double>(a, st);
+        case DCB_F32: return launch_bwd<float, float>(a, DCB_F32, st);
+        case DCB_F64: return launch_bwd<double, double>(a, DCB_F64, st);
         case DCB_BF16:
-            return flow_f32 ? launch_bwd<__nv_bfloat16, float>(a, st) : launch_bwd<__nv_bfloat16, __nv_bfloat16>(a, st);
+            return flow_f32 ? launch_bwd<__nv_bfloat16, float>(a, DCB_BF16, st) : launch_bwd<__nv_bfloat16, __nv_bfloat16>(a, DCB_BF16, st);
     }
     return set_error(DCB_E_DTYPE, "splat_bwd: unsupported dtype %d", in->dtype);
 }

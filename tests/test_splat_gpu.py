@@ -345,9 +345,9 @@ def test_list_path_mask_strides_and_saved_normaliser(dcb, orc):
     tic = bigc[:, 4:4 + c].requires_grad_(True)              # a view: strides of the 32-channel tensor
     assert not tic.is_contiguous()
     flc = flow.cuda().requires_grad_(True); mec = metric.cuda().requires_grad_(True)
-    from diffcodec_b200.softsplat import _splat_normalised
-    from diffcodec_b200 import _lib
-    got = _splat_normalised(tic, flc, mec, _lib.MODE_SOFT, _lib.EPS_ADD, mask=mask.cuda())
+    import importlib
+    impl = importlib.import_module(dcb.__name__ + ".softsplat")      # the submodule (the package re-exports the function under its name)
+    got = impl._splat_normalised(tic, flc, mec, dcb._lib.MODE_SOFT, dcb._lib.EPS_ADD, mask=mask.cuda())
     got.backward(gout.cuda())
     assert_close(got, ref, 1e-5, "lists + mask + strides")
     assert_close(tic.grad, ti.grad, 2e-5, "gin")

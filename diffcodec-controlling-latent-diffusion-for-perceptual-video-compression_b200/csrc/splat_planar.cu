@@ -196,7 +196,7 @@ __device__ __forceinline__ void planar_scatter_strip(const PlanarArgs& a, int fr
 
 template <class T>
 __device__ __forceinline__ void planar_normalize_chunk(const PlanarArgs& a, int frame, int chunk, int q_begin, int q_end,
-                                                       float* acc, const float* dplane, int lane) {
+                                                       float* acc, float* dplane, int lane) {
     const int C = a.C;
     T* out = (T*)a.out + (long long)frame * C * a.HW;
     constexpr int kPer = kPChunk / 32;
@@ -209,7 +209,8 @@ __device__ __forceinline__ void planar_normalize_chunk(const PlanarArgs& a, int 
         scale[i] = 1.f;
         if (r < a.HW) {
             if (normalised) {
-                float d = __ldcg(dplane + r);     // shared by the warps of every channel group: re-zeroed a step later
+                float d = __ldcg(dplane + r);     // shared by the warps of every channel group: re-zeroed a step later ...
+                if (a.ncg_n == 1) __stcg(dplane + r, 0.f);   // ... unless this warp is its only reader
                 // softsplat.py:256-266
                 if (a.eps == DCB_EPS_ADD) d = add_rn(d, 0.0000001f);
                 else if (a.eps == DCB_EPS_ZERO) d = (d == 0.f) ? 1.f : d;
@@ -265,7 +266,7 @@ __global__ void __launch_bounds__(kPThreads, DCB_PMINCTAS) k_planar_step(const _
         const int chunk = q % a.tn, cgi = q / a.tn;
         const int f = a.n_frame0 + fi, g = a.step - 1;
         float* acc = a.acc + (size_t)(g & 1) * slot_floats + (size_t)fi * frame_floats;
-        const float* dplane = a.dacc + (size_t)(g % 3) * dslot + (size_t)fi * a.HW;
+        float* dplane = a.dacc + (size_t)(g % 3) * dslot + (size_t)fi * a.HW;
         planar_normalize_chunk<T>(a, f, chunk, cgi * a.cg_n, min(a.Cq, (cgi + 1) * a.cg_n), acc, dplane, lane);
         return;
     }
@@ -342,7 +343,8 @@ template <class T, class TF> static int launch_planar(PlanarArgs& a, cudaStream_
         count_launch();
     }
     // the normaliser slot read by the last step is the only part of the workspace left non-zero
-    if (normalised)
+    // (with one reader per cell the normalise items have zeroed it themselves)
+    if (normalised && a.ncg_n > 1)
         DCB_CHECK_CUDA(cudaMemsetAsync(a.dacc + (size_t)((groups - 1) % 3) * a.G * a.HW, 0, (size_t)a.G * a.HW * 4, st));
     return DCB_OK;
 }

@@ -1,0 +1,232 @@
+// tile_bench.cu -- round-2 probe (not product code): does aggregating a warp's contributions in a PRIVATE
+// shared-memory window before they go to L2 beat register merging when the flow is rough?
+//
+// The forward splat is bound by the sectors its reductions touch in L2 (profiles/r01/NOTES.md, sections 2
+// and 6): ~0.7 sector-ops per pixel on smooth flow, 2.2-2.7 on the bench flow, because lone 16-byte reds cost
+// a whole sector-op each. A warp that owns a 32 x 4 strip could add all four corners of its 128 pixels into
+// a window in shared memory (fp32 shared atomics are CAS loops on sm_100a, but the window is private to the
+// warp, so they only ever retry on collisions inside one instruction) and then flush every touched cell ONCE,
+// neighbouring cells from neighbouring lanes (full sectors). This binary times, one 1080p frame per launch
+// into ONE L2-resident accumulator (the regime of the step pipeline):
+//     naive 4 x red.v4 | east-merge by shuffle | shared-memory window (several window sizes)
+// on a smooth, a rough (|dflow/dx| ~ 0.25, like bench.py) and a random flow.
+//   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -o tile_bench tile_bench.cu
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <math.h>
+
+#define CK(x) do { cudaError_t e = (x); if (e != cudaSuccess) { printf("CUDA error %s at %s:%d\n", cudaGetErrorString(e), __FILE__, __LINE__); exit(1); } } while (0)
+
+constexpr int H = 1080, W = 1920, HW = H * W;
+
+__device__ __forceinline__ void red4(float* p, float a, float b, float c, float d) {
+    asm volatile("red.global.add.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
+// pattern 0 smooth (|d/dx| ~ 0.03), 1 rough (~0.25, amplitude 8 px), 2 hash-random +-32 px
+__global__ void k_make_flow(float* flow, int frames, int pattern) {
+    int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= frames * HW) return;
+    int n = p / HW, r = p - n * HW, y = r / W, x = r - y * W;
+    float fx, fy;
+    if (pattern == 0) {
+        fx = 5.f * sinf(x * 0.0042f + y * 0.0026f + n) + 3.f * cosf(y * 0.0094f - x * 0.0018f);
+        fy = 4.f * cosf(x * 0.0034f - y * 0.0038f + 2 * n) + 3.f * sinf(x * 0.0062f + 0.5f);
+    } else if (pattern == 1) {
+        fx = 5.f * sinf(x * 0.045f + y * 0.027f + n) + 3.f * cosf(y * 0.09f - x * 0.02f);
+        fy = 4.f * cosf(x * 0.037f - y * 0.041f + 2 * n) + 3.f * sinf(x * 0.066f + 0.5f);
+    } else {
+        unsigned h = (unsigned)p * 2654435761u; h ^= h >> 15; h *= 2246822519u; h ^= h >> 13;
+        fx = ((h & 0xffff) / 65535.f - 0.5f) * 64.f;
+        fy = (((h >> 16) & 0xffff) / 65535.f - 0.5f) * 64.f;
+    }
+    flow[(size_t)n * 2 * HW + r] = fx;
+    flow[(size_t)n * 2 * HW + HW + r] = fy;
+}
+
+struct Foot { int x0, y0; float w[4]; bool b[4]; };
+__device__ __forceinline__ Foot foot(int x, int y, float fx, float fy) {
+    Foot f;
+    float px = x + fx, py = y + fy;
+    float x0f = floorf(px), y0f = floorf(py);
+    f.x0 = (int)x0f; f.y0 = (int)y0f;
+    float dx = px - x0f, dy = py - y0f, ex = (x0f + 1.f) - px, ey = (y0f + 1.f) - py;
+    f.w[0] = ex * ey; f.w[1] = dx * ey; f.w[2] = ex * dy; f.w[3] = dx * dy;
+    bool vx0 = (unsigned)f.x0 < (unsigned)W, vx1 = (unsigned)(f.x0 + 1) < (unsigned)W;
+    bool vy0 = (unsigned)f.y0 < (unsigned)H, vy1 = (unsigned)(f.y0 + 1) < (unsigned)H;
+    f.b[0] = vx0 && vy0; f.b[1] = vx1 && vy0; f.b[2] = vx0 && vy1; f.b[3] = vx1 && vy1;
+    return f;
+}
+
+// one frame; in [3,H,W], metric [H,W], flow [2,H,W]; acc [H*W][4]
+__global__ void __launch_bounds__(256) k_naive(const float* __restrict__ in, const float* __restrict__ metric,
+                                               const float* __restrict__ flow, float* acc) {
+    int r = blockIdx.x * 256 + threadIdx.x;
+    if (r >= HW) return;
+    int y = r / W, x = r - y * W;
+    Foot f = foot(x, y, __ldcs(flow + r), __ldcs(flow + HW + r));
+    float g = expf(__ldcs(metric + r));
+    float v0 = __ldcs(in + r) * g, v1 = __ldcs(in + HW + r) * g, v2 = __ldcs(in + 2 * HW + r) * g;
+    float* a = acc + ((size_t)f.y0 * W + f.x0) * 4;
+    const int off[4] = {0, 4, 4 * W, 4 * W + 4};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) if (f.b[k]) red4(a + off[k], v0 * f.w[k], v1 * f.w[k], v2 * f.w[k], g * f.w[k]);
+}
+
+__global__ void __launch_bounds__(256) k_merge_east(const float* __restrict__ in, const float* __restrict__ metric,
+                                                    const float* __restrict__ flow, float* acc) {
+    int r = blockIdx.x * 256 + threadIdx.x;
+    bool live = r < HW;
+    int rc = live ? r : HW - 1;
+    int y = rc / W, x = rc - y * W;
+    Foot f = foot(x, y, __ldcs(flow + rc), __ldcs(flow + HW + rc));
+    float g = expf(__ldcs(metric + rc));
+    float v[4] = {__ldcs(in + rc) * g, __ldcs(in + HW + rc) * g, __ldcs(in + 2 * HW + rc) * g, g};
+    if (!live) f.b[0] = f.b[1] = f.b[2] = f.b[3] = false;
+    const unsigned lane = threadIdx.x & 31;
+    float westN[4], westS[4], eastN[4], eastS[4];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+        westN[c] = f.b[0] ? v[c] * f.w[0] : 0.f; eastN[c] = f.b[1] ? v[c] * f.w[1] : 0.f;
+        westS[c] = f.b[2] ? v[c] * f.w[2] : 0.f; eastS[c] = f.b[3] ? v[c] * f.w[3] : 0.f;
+    }
+    int lx0 = __shfl_up_sync(0xffffffffu, f.x0, 1), ly0 = __shfl_up_sync(0xffffffffu, f.y0, 1);
+    bool take = lane > 0 && lx0 + 1 == f.x0 && ly0 == f.y0;
+    bool given = __shfl_down_sync(0xffffffffu, (int)take, 1) && lane < 31;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+        float en = __shfl_up_sync(0xffffffffu, eastN[c], 1), es = __shfl_up_sync(0xffffffffu, eastS[c], 1);
+        if (take) { westN[c] += en; westS[c] += es; }
+    }
+    bool vx0 = (unsigned)f.x0 < (unsigned)W, vy0 = (unsigned)f.y0 < (unsigned)H, vy1 = (unsigned)(f.y0 + 1) < (unsigned)H;
+    bool vx1 = (unsigned)(f.x0 + 1) < (unsigned)W;
+    float* a = acc + ((size_t)f.y0 * W + f.x0) * 4;
+    if (live || take) {
+        if (vx0 && vy0) red4(a, westN[0], westN[1], westN[2], westN[3]);
+        if (vx0 && vy1) red4(a + 4 * W, westS[0], westS[1], westS[2], westS[3]);
+    }
+    if (live && !given) {
+        if (vx1 && vy0) red4(a + 4, eastN[0], eastN[1], eastN[2], eastN[3]);
+        if (vx1 && vy1) red4(a + 4 * W + 4, eastS[0], eastS[1], eastS[2], eastS[3]);
+    }
+}
+
+// one warp per SX x SY strip (SX * SY / 32 pixels per lane), private WX x WY window of float4 cells kept as
+// four planes (bank-conflict free for neighbouring cells)
+template <int SX, int SY, int WX, int WY>
+__global__ void __launch_bounds__(32) k_window(const float* __restrict__ in, const float* __restrict__ metric,
+                                               const float* __restrict__ flow, float* acc, unsigned long long* spilled) {
+    constexpr int CELLS = WX * WY, PER = SX * SY / 32, LY = 32 / SX;      // lanes cover SX columns x LY rows per pass
+    __shared__ float win[4 * CELLS];
+    const int lane = threadIdx.x;
+    const int tiles_x = (W + SX - 1) / SX;
+    const int tx = blockIdx.x % tiles_x, ty = blockIdx.x / tiles_x;
+    const int lx = lane % SX, ly = lane / SX;
+    for (int i = lane; i < 4 * CELLS; i += 32) win[i] = 0.f;
+    Foot f[PER];
+    float v[PER][4];
+    int minx = 1 << 30, miny = 1 << 30;
+#pragma unroll
+    for (int p = 0; p < PER; ++p) {
+        const int x = tx * SX + lx, y = ty * SY + p * LY + ly;
+        const bool in_img = x < W && y < H;
+        const int r = in_img ? y * W + x : 0;
+        f[p] = foot(x, y, __ldcs(flow + r), __ldcs(flow + HW + r));
+        const float g = expf(__ldcs(metric + r));
+        v[p][0] = __ldcs(in + r) * g; v[p][1] = __ldcs(in + HW + r) * g; v[p][2] = __ldcs(in + 2 * HW + r) * g; v[p][3] = g;
+        if (!in_img) f[p].b[0] = f[p].b[1] = f[p].b[2] = f[p].b[3] = false;
+        if (f[p].b[0] || f[p].b[1] || f[p].b[2] || f[p].b[3]) { minx = min(minx, f[p].x0); miny = min(miny, f[p].y0); }
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+        minx = min(minx, __shfl_xor_sync(0xffffffffu, minx, d));
+        miny = min(miny, __shfl_xor_sync(0xffffffffu, miny, d));
+    }
+    if (minx < 0) minx = 0;                                        // a corner at x0 = -1 is out of the frame anyway
+    if (miny < 0) miny = 0;
+    __syncwarp();
+    unsigned nspill = 0;
+#pragma unroll
+    for (int p = 0; p < PER; ++p) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            if (!f[p].b[k]) continue;
+            const int gx = f[p].x0 + (k & 1), gy = f[p].y0 + (k >> 1);
+            const int cx = gx - minx, cy = gy - miny;
+            const float wk = f[p].w[k];
+            if ((unsigned)cx < (unsigned)WX && (unsigned)cy < (unsigned)WY) {
+                float* c = win + cy * WX + cx;
+                atomicAdd(c, v[p][0] * wk); atomicAdd(c + CELLS, v[p][1] * wk);
+                atomicAdd(c + 2 * CELLS, v[p][2] * wk); atomicAdd(c + 3 * CELLS, v[p][3] * wk);
+            } else {
+                red4(acc + ((size_t)gy * W + gx) * 4, v[p][0] * wk, v[p][1] * wk, v[p][2] * wk, v[p][3] * wk);
+                ++nspill;
+            }
+        }
+    }
+    __syncwarp();
+    for (int i = lane; i < CELLS; i += 32) {
+        const float a0 = win[i], a1 = win[CELLS + i], a2 = win[2 * CELLS + i], a3 = win[3 * CELLS + i];
+        if (a3 != 0.f) {                                           // the weight channel is positive wherever anything landed
+            const int gx = minx + i % WX, gy = miny + i / WX;
+            red4(acc + ((size_t)gy * W + gx) * 4, a0, a1, a2, a3);
+        }
+    }
+    if (spilled && nspill) atomicAdd(spilled, (unsigned long long)nspill);
+}
+
+struct Timer {
+    cudaEvent_t a, b;
+    Timer() { CK(cudaEventCreate(&a)); CK(cudaEventCreate(&b)); }
+    template <class F> float run(F f, int warm, int iters) {
+        for (int i = 0; i < warm; ++i) f(i);
+        CK(cudaEventRecord(a));
+        for (int i = 0; i < iters; ++i) f(i);
+        CK(cudaEventRecord(b)); CK(cudaEventSynchronize(b));
+        float ms; CK(cudaEventElapsedTime(&ms, a, b));
+        return ms / iters;
+    }
+};
+
+template <int SX, int SY, int WX, int WY>
+static void bench_window(Timer& T, const char* name, const float* in, const float* metric, const float* flow, float* acc,
+                         unsigned long long* spilled, int POOL) {
+    const int strips = ((W + SX - 1) / SX) * ((H + SY - 1) / SY);
+    CK(cudaMemset(spilled, 0, 8));
+    float ms = T.run([&](int i) { size_t s = i % POOL;
+        k_window<SX, SY, WX, WY><<<strips, 32>>>(in + s * 3 * HW, metric + s * HW, flow + s * 2 * HW, acc, spilled); }, 4, 32);
+    unsigned long long sp; CK(cudaMemcpy(&sp, spilled, 8, cudaMemcpyDeviceToHost));
+    printf("  window %-22s: %7.1f us/frame   %.2f %% of corners spilled past the window\n", name, ms * 1e3, 100.0 * sp / 36.0 / (4.0 * HW));
+}
+
+int main() {
+    cudaDeviceProp prop; CK(cudaGetDeviceProperties(&prop, 0));
+    printf("# device %s, %d SMs; one 1080p frame per launch into one 33 MB accumulator (L2-resident)\n", prop.name, prop.multiProcessorCount);
+    const int POOL = 16;
+    float *in, *metric, *flow[3], *acc; unsigned long long* spilled;
+    CK(cudaMalloc(&in, (size_t)POOL * 3 * HW * 4)); CK(cudaMalloc(&metric, (size_t)POOL * HW * 4));
+    for (int i = 0; i < 3; ++i) CK(cudaMalloc(&flow[i], (size_t)POOL * 2 * HW * 4));
+    CK(cudaMalloc(&acc, (size_t)HW * 16)); CK(cudaMalloc(&spilled, 8));
+    CK(cudaMemset(in, 0, (size_t)POOL * 3 * HW * 4)); CK(cudaMemset(metric, 0, (size_t)POOL * HW * 4)); CK(cudaMemset(acc, 0, (size_t)HW * 16));
+    for (int pat = 0; pat < 3; ++pat) k_make_flow<<<(POOL * HW + 255) / 256, 256>>>(flow[pat], POOL, pat);
+    CK(cudaDeviceSynchronize());
+    Timer T;
+    const char* pname[3] = {"smooth (|d/dx| ~ 0.03)", "rough (|d/dx| ~ 0.25)", "random +-32 px"};
+    const int blocks = (HW + 255) / 256;
+    for (int pat = 0; pat < 3; ++pat) {
+        printf("--- %s ---\n", pname[pat]);
+        float ms = T.run([&](int i) { size_t s = i % POOL; k_naive<<<blocks, 256>>>(in + s * 3 * HW, metric + s * HW, flow[pat] + s * 2 * HW, acc); }, 4, 32);
+        printf("  naive 4 x red.v4              : %7.1f us/frame\n", ms * 1e3);
+        ms = T.run([&](int i) { size_t s = i % POOL; k_merge_east<<<blocks, 256>>>(in + s * 3 * HW, metric + s * HW, flow[pat] + s * 2 * HW, acc); }, 4, 32);
+        printf("  east merge by shuffle         : %7.1f us/frame\n", ms * 1e3);
+        bench_window<32, 4, 40, 8>(T, "32x4 strip, 40x8", in, metric, flow[pat], acc, spilled, POOL);
+        bench_window<32, 4, 48, 12>(T, "32x4 strip, 48x12", in, metric, flow[pat], acc, spilled, POOL);
+        bench_window<32, 4, 48, 20>(T, "32x4 strip, 48x20", in, metric, flow[pat], acc, spilled, POOL);
+        bench_window<16, 8, 24, 16>(T, "16x8 strip, 24x16", in, metric, flow[pat], acc, spilled, POOL);
+        bench_window<16, 8, 32, 20>(T, "16x8 strip, 32x20", in, metric, flow[pat], acc, spilled, POOL);
+        bench_window<8, 16, 16, 24>(T, "8x16 strip, 16x24", in, metric, flow[pat], acc, spilled, POOL);
+    }
+    printf("done\n");
+    return 0;
+}

@@ -95,7 +95,8 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-WORKLOAD = "soft (softmax) forward splat, fp32, {F}x3x1080x1920 frames per GPU per step, smooth synthetic flow ~8 px"
+WORKLOAD = ("soft (softmax) forward splat, fp32, {F}x3x1080x1920 frames per GPU per step, synthetic flow ~8 px "
+            "(bicubic-upsampled noise, mean |dflow/dx| 0.28 px/px: rougher than real optical flow; extra.headline_on_smooth_flow has 0.03)")
 
 
 def _cpu_port_mpixel_s(frames, threads, repeats=1):

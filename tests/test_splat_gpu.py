@@ -327,6 +327,20 @@ def test_list_path_agrees_with_accumulator_path(dcb):
             assert_close(whole[n:n + 1], part, 1e-5, f"lists vs accumulators {mode} frame {n}")
 
 
+def test_list_path_ragged_sizes(dcb, orc):
+    """Frame sizes that are multiples of neither the 32 x 8 gather tile nor the 256-pixel CTAs of the
+    list builders (203 x 331), odd channel count (21: a short last channel block), three frames."""
+    tin, flow, metric, gout = make_inputs(84, 3, 21, 203, 331, flow_scale=3.5)
+    assert tin.numel() * 4 >= 16 << 20
+    for mode in ("avg", "soft"):
+        ref = oracle_run(orc, tin, flow, metric, gout, mode)
+        truth = oracle_run(orc, tin.double(), flow.double(), metric.double(), gout.double(), mode)
+        got = cuda_run(dcb.softsplat, tin, flow, metric, gout, mode)
+        for k in ("out", "gin", "gflow", "gmetric"):
+            if ref[k] is not None:
+                assert_close(got[k], ref[k], 2e-5, f"ragged lists {mode} {k}", truth=truth[k])
+
+
 def test_list_path_mask_strides_and_saved_normaliser(dcb, orc):
     """The list path behind FeatureWarperSoftsplat's call shape: (1 - mask) product, a channel-sliced
     (non-contiguous) input, and the gradient w.r.t. everything through the saved normaliser."""

@@ -125,93 +125,70 @@ __global__ void __launch_bounds__(256) k_backwarp_fwd(const WarpArgs a, const Ta
     }
 }
 
-// K4, fp32 fast path: PX consecutive output pixels per thread, vector loads of flow / gt and
-// vector stores of warped / residual, 32-bit element offsets, CU channels in flight. The per-pixel
-// arithmetic is the same sequence as above, so the results are bit-identical to the generic kernel.
-#ifndef DCB_BW_PX
-#define DCB_BW_PX 2          // 2 or 4 pixels per thread
-#endif
-#ifndef DCB_BW_CU
-#define DCB_BW_CU 1          // channels in flight per thread: 4 * PX * CU tap loads + CU gt loads
-#endif
+// K4, fast path for unit-stride rows (fp32 or bf16): two consecutive output pixels per thread, paired
+// loads of flow / gt and paired stores of warped / residual, 32-bit element offsets, 8-row x 64-column
+// CTA tiles, one channel in flight (48 registers -> 40 warps per SM), L2 prefetch one wave ahead. The
+// per-pixel arithmetic is the same sequence as above, so the results are bit-identical to the generic kernel.
 #ifndef DCB_BW_MINCTAS
 #define DCB_BW_MINCTAS 5
-#endif
-#ifndef DCB_BW_TILE
-#define DCB_BW_TILE 1
 #endif
 #ifndef DCB_BW_PF
 #define DCB_BW_PF 1          // L2 prefetch one wave of CTAs ahead (0 = off)
 #endif
 
 struct WarpRowsArgs {
-    const float *image, *flow, *gt;
-    float *warped, *residual;
+    const void *image, *flow, *gt;
+    void *warped, *residual;
     int isN, isC, isH, isW;      // image strides (elements)
     int fsN, fsC, fsH;           // flow strides; sW == 1
     int gsN, gsC, gsH;           // gt strides; sW == 1
-    unsigned totalv, Wv;         // threads in all, threads per row
     unsigned tiles_x, pf_dist;   // CTAs per tile row; prefetch distance = resident CTAs
     int C, H, W, HW, align;
 };
 
-template <int PX> struct VecOf;
-template <> struct VecOf<2> { using type = float2; };
-template <> struct VecOf<4> { using type = float4; };
-__device__ __forceinline__ void unpack(const float2& v, float* o) { o[0] = v.x; o[1] = v.y; }
-__device__ __forceinline__ void unpack(const float4& v, float* o) { o[0] = v.x; o[1] = v.y; o[2] = v.z; o[3] = v.w; }
-__device__ __forceinline__ void pack(float2& v, const float* o) { v = make_float2(o[0], o[1]); }
-__device__ __forceinline__ void pack(float4& v, const float* o) { v = make_float4(o[0], o[1], o[2], o[3]); }
+__device__ __forceinline__ void ld2_stream(const float* p, float (&o)[2]) { const float2 v = __ldcs((const float2*)p); o[0] = v.x; o[1] = v.y; }
+__device__ __forceinline__ void ld2_stream(const __nv_bfloat16* p, float (&o)[2]) {
+    const __nv_bfloat162 v = __ldcs((const __nv_bfloat162*)p);
+    o[0] = __low2float(v); o[1] = __high2float(v);
+}
+__device__ __forceinline__ void st2_stream(float* p, float a, float b) { __stcs((float2*)p, make_float2(a, b)); }
+__device__ __forceinline__ void st2_stream(__nv_bfloat16* p, float a, float b) { __stcs((__nv_bfloat162*)p, __floats2bfloat162_rn(a, b)); }
 
+template <class T, class TF>
 __global__ void __launch_bounds__(256, DCB_BW_MINCTAS) k_backwarp_rows(const WarpRowsArgs a, const TapConst<float> kc) {
-    constexpr int CU = DCB_BW_CU, PX = DCB_BW_PX;
-    using V = typename VecOf<PX>::type;
-#if DCB_BW_TILE
-    // a CTA covers 8 rows x (32 * PX) columns: the two image rows a warp gathers from are the rows
-    // its neighbours in the CTA gather from too, so they are served by this SM's L1
+    constexpr int PX = 2;
+    // a CTA covers 8 rows x 64 columns: the two image rows a warp gathers from are the rows its
+    // neighbours in the CTA gather from too, so they are served by this SM's L1
     const unsigned tx = blockIdx.x % a.tiles_x, ty = blockIdx.x / a.tiles_x;
     const unsigned n = blockIdx.y;
     const int y = (int)(ty * 8 + (threadIdx.x >> 5));
     const int x = (int)((tx * 32 + (threadIdx.x & 31)) * PX);
 #if DCB_BW_PF
-    {   // L2 prefetch of the rows a CTA one wave ahead will stream: one 128-byte line per lane
+    {   // L2 prefetch of the rows a CTA one wave ahead will stream: one line per lane
         unsigned pb = blockIdx.x + a.pf_dist, pn = n;
         if (pb >= gridDim.x) { pb -= gridDim.x; ++pn; }
         if (pn < gridDim.y && pb < gridDim.x) {
             const int px0 = (int)((pb % a.tiles_x) * 32 * PX), py = (int)((pb / a.tiles_x) * 8 + (threadIdx.x >> 5));
             const int lane = threadIdx.x & 31;
-            constexpr int LPR = PX * 32 * 4 / 128;                  // lines per row segment
-            const int plane = lane / LPR, line = lane % LPR;
-            const int pxl = px0 + line * 32;
+            const int plane = lane >> 1, pxl = px0 + (lane & 1) * 32;      // two lines of 32 elements per row segment
             if (py < a.H && pxl < a.W) {
-                const float* q = nullptr;
-                if (plane < 2) q = a.flow + (int)pn * a.fsN + plane * a.fsC + py * a.fsH + pxl;
-                else if (plane < 2 + a.C && a.gt) q = a.gt + (int)pn * a.gsN + (plane - 2) * a.gsC + py * a.gsH + pxl;
-                else if (plane >= 8 && plane < 8 + a.C) q = a.image + (int)pn * a.isN + (plane - 8) * a.isC + py * a.isH + pxl * a.isW;
+                const void* q = nullptr;
+                if (plane < 2) q = (const TF*)a.flow + (int)pn * a.fsN + plane * a.fsC + py * a.fsH + pxl;
+                else if (plane < 2 + a.C && a.gt) q = (const T*)a.gt + (int)pn * a.gsN + (plane - 2) * a.gsC + py * a.gsH + pxl;
+                else if (plane >= 8 && plane < 8 + a.C) q = (const T*)a.image + (int)pn * a.isN + (plane - 8) * a.isC + py * a.isH + pxl * a.isW;
                 if (q) asm volatile("prefetch.global.L2 [%0];" ::"l"(q));
             }
         }
     }
 #endif
     if (y >= a.H || x >= a.W) return;
-#else
-    const unsigned q = blockIdx.x * 256 + threadIdx.x;
-    if (q >= a.totalv) return;
-    const unsigned row = q / a.Wv;                         // n * H + y
-    const int x = (int)(q - row * a.Wv) * PX;
-    const unsigned n = row / (unsigned)a.H;
-    const int y = (int)(row - n * (unsigned)a.H);
-#endif
-    const float* fp = a.flow + (int)n * a.fsN + y * a.fsH + x;
-    const V fxv = __ldcs((const V*)fp), fyv = __ldcs((const V*)(fp + a.fsC));
-    // the gt rows do not depend on the flow: put the first block's loads in flight before the taps
-    const float* gt = a.gt ? a.gt + (int)n * a.gsN + y * a.gsH + x : nullptr;
-    V g[CU];
-#pragma unroll
-    for (int u = 0; u < CU; ++u)
-        if (gt) g[u] = __ldcs((const V*)(gt + (u < a.C ? u : a.C - 1) * a.gsC));
+    const TF* fp = (const TF*)a.flow + (int)n * a.fsN + y * a.fsH + x;
     float fx[PX], fy[PX];
-    unpack(fxv, fx); unpack(fyv, fy);
+    ld2_stream(fp, fx); ld2_stream(fp + a.fsC, fy);
+    // the gt row does not depend on the flow: put the first channel's load in flight before the taps
+    const T* gt = a.gt ? (const T*)a.gt + (int)n * a.gsN + y * a.gsH + x : nullptr;
+    float g[PX] = {0.f, 0.f};
+    if (gt) ld2_stream(gt, g);
 
     int to[PX][4];
     float tw[PX][4];
@@ -228,46 +205,30 @@ __global__ void __launch_bounds__(256, DCB_BW_MINCTAS) k_backwarp_rows(const War
 #pragma unroll
         for (int k = 0; k < 4; ++k) valid |= (t.b[k] ? 1u : 0u) << (j * 4 + k);
     }
-    const float* im = a.image + (int)n * a.isN;
+    const T* im = (const T*)a.image + (int)n * a.isN;
     const int oo = ((int)n * a.C) * a.HW + y * a.W + x;
-    float* wp = a.warped + oo;
-    float* rp = a.residual ? a.residual + oo : nullptr;
-    for (int c0 = 0; c0 < a.C; c0 += CU) {
-        float v[CU][PX][4];
+    T* wp = (T*)a.warped + oo;
+    T* rp = a.residual ? (T*)a.residual + oo : nullptr;
+    for (int c = 0; c < a.C; ++c, im += a.isC, wp += a.HW) {
+        float v[PX][4];
 #pragma unroll
-        for (int u = 0; u < CU; ++u) {
-            const float* pl = im + (c0 + u < a.C ? c0 + u : a.C - 1) * a.isC;
+        for (int j = 0; j < PX; ++j)
 #pragma unroll
-            for (int j = 0; j < PX; ++j)
+            for (int k = 0; k < 4; ++k) v[j][k] = ld<float>(im + to[j][k]);      // the image is re-read by neighbours: keep it cached
+        if (c > 0 && gt) ld2_stream(gt + c * a.gsC, g);
+        float acc[PX];
 #pragma unroll
-                for (int k = 0; k < 4; ++k) v[u][j][k] = pl[to[j][k]];
+        for (int j = 0; j < PX; ++j) {
+            acc[j] = 0.f;
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+                acc[j] = (valid >> (j * 4 + k)) & 1u ? fma_rn(v[j][k], tw[j][k], acc[j]) : acc[j];   // grid_sample's tap order and fma chain
         }
-        if (c0 > 0 && gt) {
-#pragma unroll
-            for (int u = 0; u < CU; ++u) g[u] = __ldcs((const V*)(gt + (c0 + u < a.C ? c0 + u : a.C - 1) * a.gsC));
-        }
-#pragma unroll
-        for (int u = 0; u < CU; ++u) {
-            if (c0 + u < a.C) {
-                float acc[PX], gv[PX];
-#pragma unroll
-                for (int j = 0; j < PX; ++j) {
-                    acc[j] = 0.f;
-#pragma unroll
-                    for (int k = 0; k < 4; ++k)
-                        acc[j] = (valid >> (j * 4 + k)) & 1u ? fma_rn(v[u][j][k], tw[j][k], acc[j]) : acc[j];
-                }
-                V o;
-                pack(o, acc);
-                __stcs((V*)(wp + (c0 + u) * a.HW), o);
-                if (rp) {
-                    unpack(g[u], gv);
-#pragma unroll
-                    for (int j = 0; j < PX; ++j) gv[j] = sub_rn(gv[j], acc[j]);
-                    pack(o, gv);
-                    __stcs((V*)(rp + (c0 + u) * a.HW), o);
-                }
-            }
+        st2_stream(wp, acc[0], acc[1]);
+        if (rp) {
+            // residual of the value as stored (rounded to T), like `gt - warped` on the stored tensor
+            st2_stream(rp, sub_rn(g[0], round_as<T>(acc[0])), sub_rn(g[1], round_as<T>(acc[1])));
+            rp += a.HW;
         }
     }
 }
@@ -345,41 +306,40 @@ static long long max_offset31(const DcbTensor* t) {
     return m < (1ll << 31) ? m : -1;
 }
 
-static bool rows_vec(const DcbTensor* t) {      // vector loads along x are legal
-    constexpr int V = DCB_BW_PX;
-    return t->dtype == DCB_F32 && t->stride[3] == 1 && t->stride[0] % V == 0 && t->stride[1] % V == 0 &&
-           t->stride[2] % V == 0 && ((uintptr_t)t->ptr & (V * 4 - 1)) == 0 && max_offset31(t) >= 0;
+static bool rows_vec(const DcbTensor* t) {      // paired loads along x are legal
+    const int es = elem_size(t->dtype);
+    return t->dtype != DCB_F64 && t->stride[3] == 1 && t->stride[0] % 2 == 0 && t->stride[1] % 2 == 0 &&
+           t->stride[2] % 2 == 0 && ((uintptr_t)t->ptr & (uintptr_t)(2 * es - 1)) == 0 && max_offset31(t) >= 0;
 }
 
 static bool rows_supported(const DcbTensor* image, const DcbTensor* flow, const DcbTensor* gt, const DcbTensor* warped,
                            const DcbTensor* residual) {
-    if (image->size[0] > 65535 || image->dtype != DCB_F32 || image->size[3] % DCB_BW_PX != 0 || max_offset31(image) < 0) return false;
+    if (image->size[0] > 65535 || image->dtype == DCB_F64 || image->size[3] % 2 != 0 || max_offset31(image) < 0) return false;
     if (image->size[0] * image->size[1] * image->size[2] * image->size[3] >= (1ll << 31)) return false;
-    if (!rows_vec(flow) || (gt && !rows_vec(gt))) return false;
-    if (((uintptr_t)warped->ptr & (DCB_BW_PX * 4 - 1)) || (residual && ((uintptr_t)residual->ptr & (DCB_BW_PX * 4 - 1)))) return false;
+    if (!rows_vec(flow) || (gt && (!rows_vec(gt) || gt->dtype != image->dtype))) return false;
+    if (flow->dtype != image->dtype && !(image->dtype == DCB_BF16 && flow->dtype == DCB_F32)) return false;
+    const uintptr_t m = (uintptr_t)(2 * elem_size(image->dtype) - 1);
+    if (((uintptr_t)warped->ptr & m) || (residual && ((uintptr_t)residual->ptr & m))) return false;
     return true;
 }
 
 static int launch_warp_rows(const DcbTensor* image, const DcbTensor* flow, const DcbTensor* gt, const DcbTensor* warped,
                             const DcbTensor* residual, int align, cudaStream_t st) {
     WarpRowsArgs a{};
-    a.image = (const float*)image->ptr; a.flow = (const float*)flow->ptr; a.gt = gt ? (const float*)gt->ptr : nullptr;
-    a.warped = (float*)warped->ptr; a.residual = residual ? (float*)residual->ptr : nullptr;
+    a.image = image->ptr; a.flow = flow->ptr; a.gt = gt ? gt->ptr : nullptr;
+    a.warped = warped->ptr; a.residual = residual ? residual->ptr : nullptr;
     a.isN = (int)image->stride[0]; a.isC = (int)image->stride[1]; a.isH = (int)image->stride[2]; a.isW = (int)image->stride[3];
     a.fsN = (int)flow->stride[0]; a.fsC = (int)flow->stride[1]; a.fsH = (int)flow->stride[2];
     if (gt) { a.gsN = (int)gt->stride[0]; a.gsC = (int)gt->stride[1]; a.gsH = (int)gt->stride[2]; }
     a.C = (int)image->size[1]; a.H = (int)image->size[2]; a.W = (int)image->size[3];
     a.HW = a.H * a.W; a.align = align;
-    a.Wv = (unsigned)(a.W / DCB_BW_PX);
-    a.totalv = (unsigned)(image->size[0] * a.H) * a.Wv;
-#if DCB_BW_TILE
-    a.tiles_x = (a.Wv + 31) / 32;
+    a.tiles_x = (unsigned)(a.W / 2 + 31) / 32;
     a.pf_dist = (unsigned)(device_sm_count() * DCB_BW_MINCTAS);
     const dim3 grid(a.tiles_x * (unsigned)((a.H + 7) / 8), (unsigned)image->size[0]);
-    k_backwarp_rows<<<grid, 256, 0, st>>>(a, make_tap_const<float>(a.W, a.H));
-#else
-    k_backwarp_rows<<<(a.totalv + 255) / 256, 256, 0, st>>>(a, make_tap_const<float>(a.W, a.H));
-#endif
+    const TapConst<float> kc = make_tap_const<float>(a.W, a.H);
+    if (image->dtype == DCB_F32) k_backwarp_rows<float, float><<<grid, 256, 0, st>>>(a, kc);
+    else if (flow->dtype == DCB_F32) k_backwarp_rows<__nv_bfloat16, float><<<grid, 256, 0, st>>>(a, kc);
+    else k_backwarp_rows<__nv_bfloat16, __nv_bfloat16><<<grid, 256, 0, st>>>(a, kc);
     DCB_CHECK_LAUNCH("k_backwarp_rows");
     return DCB_OK;
 }

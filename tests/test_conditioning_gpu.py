@@ -188,6 +188,15 @@ def test_backwarp_vector_path_is_bit_identical(dcb, align):
     w_a = dcb.backwarp(big[:, 1:4], flow, align_corners=align)
     w_b = dcb.backwarp(big[:, 1:4].contiguous(), flow, align_corners=align)
     assert torch.equal(torch.nan_to_num(w_a, nan=7.0), torch.nan_to_num(w_b, nan=7.0))
+    # bf16 images (fp32 and bf16 flow): paired kernel vs generic kernel, bit for bit
+    for fdt in (torch.float32, torch.bfloat16):
+        ib, gb, fb = img.bfloat16(), gt.bfloat16(), flow.to(fdt)
+        wb = torch.zeros(2, 2, 36, 128, device="cuda", dtype=fdt); wb[..., ::2] = fb
+        w1, r1 = dcb.backwarp_residual(ib, fb, gb, align_corners=align)
+        w2, r2 = dcb.backwarp_residual(ib, wb[..., ::2], gb, align_corners=align)
+        assert w1.dtype == torch.bfloat16 and r1.dtype == torch.bfloat16
+        assert torch.equal(torch.nan_to_num(w1.float(), nan=7.0), torch.nan_to_num(w2.float(), nan=7.0))
+        assert torch.equal(torch.nan_to_num(r1.float(), nan=7.0), torch.nan_to_num(r2.float(), nan=7.0))
 
 
 def test_backwarp_identity_and_layer(dcb):

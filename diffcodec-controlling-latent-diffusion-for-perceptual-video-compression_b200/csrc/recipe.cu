@@ -42,7 +42,7 @@ __global__ void __launch_bounds__(256) k_recipe_fuse(const FuseArgs a) {
     if (p >= a.total) return;
     const unsigned n = p / a.HW, r = p - n * a.HW;
     const int y = (int)(r / (unsigned)a.W), x = (int)(r - (unsigned)y * (unsigned)a.W);
-    const float of = ld<float>((const T*)a.occ_fwd + p), ob = ld<float>((const T*)a.occ_bwd + p);
+    const float of = ld_stream((const T*)a.occ_fwd + p), ob = ld_stream((const T*)a.occ_bwd + p);
     float w0, w1;
     if (a.variant == DCB_RECIPE_DATASET) {        // dataset.py:255-259: masks are the confidences
         const float ws = add_rn(add_rn(of, ob), 0.000001f);
@@ -55,13 +55,24 @@ __global__ void __launch_bounds__(256) k_recipe_fuse(const FuseArgs a) {
     const T* gp = (const T*)a.gt.p + n * a.gt.sN + (long long)y * a.gt.sH + (long long)x * a.gt.sW;
     T* fo = (T*)a.fused + (long long)n * a.C * a.HW + r;
     T* ro = (T*)a.residual + (long long)n * a.C * a.HW + r;
-    for (int c = 0; c < a.C; ++c) {
-        const float warped = ld<float>(fo + (long long)c * a.HW);                 // warped1 == warped2
-        float fused = add_rn(mul_rn(w0, warped), mul_rn(w1, warped));
-        if (hole) fused = mul_rn(0.5f, add_rn(warped, warped));
-        st<T, float>(fo + (long long)c * a.HW, fused);
-        fused = ld<float>(fo + (long long)c * a.HW);                              // the stored (rounded) value
-        st_stream(ro + (long long)c * a.HW, sub_rn(ld<float>(gp + c * a.gt.sC), fused));
+    constexpr int U = 4;                                         // channels in flight: 2 * U loads per thread
+    for (int c0 = 0; c0 < a.C; c0 += U) {
+        float wv[U], gv[U];
+#pragma unroll
+        for (int j = 0; j < U; ++j) {
+            const bool in = c0 + j < a.C;
+            wv[j] = in ? ld_stream(fo + (long long)(c0 + j) * a.HW) : 0.f;                 // warped1 == warped2
+            gv[j] = in ? ld_stream(gp + (long long)(c0 + j) * a.gt.sC) : 0.f;
+        }
+#pragma unroll
+        for (int j = 0; j < U; ++j) {
+            if (c0 + j < a.C) {
+                float fused = add_rn(mul_rn(w0, wv[j]), mul_rn(w1, wv[j]));
+                if (hole) fused = mul_rn(0.5f, add_rn(wv[j], wv[j]));
+                st_stream(fo + (long long)(c0 + j) * a.HW, fused);
+                st_stream(ro + (long long)(c0 + j) * a.HW, sub_rn(gv[j], round_as<T>(fused)));   // residual of the stored (rounded) value
+            }
+        }
     }
 }
 

@@ -45,38 +45,44 @@ struct BwdArgs {
 #ifndef DCB_BS_PF
 #define DCB_BS_PF 1
 #endif
-// K3a -- target-side scalars. 8 channels (16 loads) in flight per thread.
+// K3a -- target-side scalars. blockDim = (px, cs) like K3b: cs channel slices per pixel when pixels are scarce
+// (one thread per pixel walked the 1280 channels of an 8x8 pyramid level in 160 dependent steps: 175 us).
+// 8 channels (16 loads) in flight per thread.
 template <class T>
 __global__ void __launch_bounds__(256) k_bwd_target(const BwdArgs a) {
     using A = typename Acc<T>::type;
-    const unsigned p = blockIdx.x * 256 + threadIdx.x;
-    if (p >= a.total) return;
-    const unsigned n = p / a.HW, r = p - n * a.HW;
+    extern __shared__ unsigned char smem_raw[];
+    A* red = (A*)smem_raw;                                        // [cs][px] when cs > 1
+    const int tx = threadIdx.x, ty = threadIdx.y, cs = blockDim.y, npx = blockDim.x;
+    const unsigned p = blockIdx.x * npx + tx;
+    const bool live = p < a.total;
+    const unsigned pc = live ? p : 0;
+    const unsigned n = pc / a.HW, r = pc - n * a.HW;
     const int y = (int)(r / (unsigned)a.W), x = (int)(r - (unsigned)y * (unsigned)a.W);
-    const A d = ((const A*)a.norm)[p];
     const T* gp = (const T*)a.gout.p + n * a.gout.sN + y * a.gout.sH + x * a.gout.sW;
     const T* op = (const T*)a.out + (long long)n * a.C * a.HW + r;
     A dot = (A)0;
     constexpr int U = 8;
-    int c = 0;
-    for (; c + U <= a.C; c += U) {
-        A gv[U], ov[U];
-#pragma unroll
-        for (int j = 0; j < U; ++j) { gv[j] = ld<A>(gp + (long long)(c + j) * a.gout.sC); ov[j] = ld<A>(op + (long long)(c + j) * a.HW); }
-#pragma unroll
-        for (int j = 0; j < U; ++j) dot += gv[j] * ov[j];
-    }
-    if (c < a.C) {                                               // last partial block: the loads still go out together
+    for (int c0 = ty; c0 < a.C; c0 += U * cs) {
         A gv[U], ov[U];
 #pragma unroll
         for (int j = 0; j < U; ++j) {
-            const bool in = c + j < a.C;
-            gv[j] = in ? ld<A>(gp + (long long)(c + j) * a.gout.sC) : (A)0;
-            ov[j] = in ? ld<A>(op + (long long)(c + j) * a.HW) : (A)0;
+            const int c = c0 + j * cs;
+            const bool in = c < a.C;
+            gv[j] = in ? ld<A>(gp + (long long)c * a.gout.sC) : (A)0;
+            ov[j] = in ? ld<A>(op + (long long)c * a.HW) : (A)0;
         }
 #pragma unroll
         for (int j = 0; j < U; ++j) dot += gv[j] * ov[j];
     }
+    if (cs > 1) {
+        red[(size_t)ty * npx + tx] = dot;
+        __syncthreads();
+        if (ty != 0) return;
+        for (int s = 1; s < cs; ++s) dot += red[(size_t)s * npx + tx];
+    }
+    if (!live) return;
+    const A d = ((const A*)a.norm)[p];
     A keep = (A)1;
     if (a.mask.p) {
         const T* mp = (const T*)a.mask.p + n * a.mask.sN + y * a.mask.sH + x * a.mask.sW;
@@ -404,13 +410,16 @@ static int launch_bwd(BwdArgs& a, int dtype, cudaStream_t st) {
             return DCB_OK;
         }
     }
-    if (a.mode != DCB_MODE_SUM) {
-        k_bwd_target<T><<<(a.total + 255) / 256, 256, 0, st>>>(a);
-        DCB_CHECK_LAUNCH("k_bwd_target");
-    }
     // channel slices: fill ~148 SMs x 8 CTAs when pixels are scarce
     int cs = 1;
     while (cs < 32 && cs * 2 <= a.C && (long long)a.total * cs < 148LL * 2048) cs *= 2;
+    if (a.mode != DCB_MODE_SUM) {
+        int ct = 1;                                               // the target pass keeps 8 channels per slice in flight
+        while (ct < 32 && ct * 2 * 8 <= a.C && (long long)a.total * ct < 148LL * 2048) ct *= 2;
+        const int tpx = 256 / ct;
+        k_bwd_target<T><<<(a.total + tpx - 1) / tpx, dim3(tpx, ct), ct > 1 ? (size_t)256 * sizeof(A) : 0, st>>>(a);
+        DCB_CHECK_LAUNCH("k_bwd_target");
+    }
     a.cs = cs;
     a.px = 256 / cs;
     a.pf_dist = (unsigned)(device_sm_count() * DCB_BS_MINCTAS);

@@ -21,21 +21,28 @@ from .control_utils import compute_mask
 __all__ = ["bidir_fuse", "bidirectional_warp_fuse"]
 
 
+def _fuse_forward(A, B, conf_a, conf_b, occ_a, occ_b):
+    assert A.is_cuda and A.dim() == 4 and A.shape == B.shape, "bidir_fuse expects two [N,C,H,W] CUDA tensors"
+    dt = A.dtype
+    if B.dtype != dt: B = B.to(dt)
+    if conf_a.dtype != dt: conf_a = conf_a.to(dt)
+    if conf_b.dtype != dt: conf_b = conf_b.to(dt)
+    if occ_a is not None and (occ_a.dtype != dt or occ_b.dtype != dt):
+        occ_a, occ_b = occ_a.to(dt), occ_b.to(dt)
+    lib = _lib.lib()
+    dev = A.device
+    fused = torch.empty(A.shape, dtype=dt, device=dev)
+    with _lib.on_device(dev):
+        rc = lib.dcb_bidir_fuse_fwd(_lib.desc(A), _lib.desc(B), _lib.desc(conf_a), _lib.desc(conf_b),
+                                    _lib.desc(occ_a), _lib.desc(occ_b), _lib.desc(fused), _lib.stream_ptr(dev))
+    _lib.check(rc, "dcb_bidir_fuse_fwd")
+    return fused, (A, B, conf_a, conf_b, occ_a, occ_b)
+
+
 class _bidir_fuse_func(torch.autograd.Function):
     @staticmethod
     def forward(ctx, A, B, conf_a, conf_b, occ_a, occ_b):
-        assert A.is_cuda and A.dim() == 4 and A.shape == B.shape, "bidir_fuse expects two [N,C,H,W] CUDA tensors"
-        dt = A.dtype
-        B, conf_a, conf_b = B.to(dt), conf_a.to(dt), conf_b.to(dt)
-        if occ_a is not None:
-            occ_a, occ_b = occ_a.to(dt), occ_b.to(dt)
-        lib = _lib.lib()
-        dev = A.device
-        fused = torch.empty(A.shape, dtype=dt, device=dev)
-        with _lib.on_device(dev):
-            rc = lib.dcb_bidir_fuse_fwd(_lib.desc(A), _lib.desc(B), _lib.desc(conf_a), _lib.desc(conf_b),
-                                        _lib.desc(occ_a), _lib.desc(occ_b), _lib.desc(fused), _lib.stream_ptr(dev))
-        _lib.check(rc, "dcb_bidir_fuse_fwd")
+        fused, (A, B, conf_a, conf_b, occ_a, occ_b) = _fuse_forward(A, B, conf_a, conf_b, occ_a, occ_b)
         ctx.has_occ = occ_a is not None
         ctx.save_for_backward(*([A, B, conf_a, conf_b] + ([occ_a, occ_b] if occ_a is not None else [])))
         return fused
@@ -65,7 +72,9 @@ def bidir_fuse(warped_a, warped_b, conf_a, conf_b, occ_a=None, occ_b=None):
     (``occ_a + occ_b > 1.5``) ``0.5*(A + B)`` -- reference ``extractors.py:298-310`` -- in one kernel,
     differentiable w.r.t. both maps and both confidences, without the ``holes.any()`` host sync."""
     assert (occ_a is None) == (occ_b is None)
-    return _bidir_fuse_func.apply(warped_a, warped_b, conf_a, conf_b, occ_a, occ_b)
+    if torch.is_grad_enabled() and any(t.requires_grad for t in (warped_a, warped_b, conf_a, conf_b)):
+        return _bidir_fuse_func.apply(warped_a, warped_b, conf_a, conf_b, occ_a, occ_b)
+    return _fuse_forward(warped_a, warped_b, conf_a, conf_b, occ_a, occ_b)[0]     # inference: no autograd.Function bookkeeping
 
 
 def bidirectional_warp_fuse(first_features, last_features, flow_f, flow_b, warper):

@@ -248,6 +248,28 @@ def test_bidirectional_block(dcb, orc):
     assert_close(got.cpu()[same.expand_as(ref)], ref[same.expand_as(ref)], 1e-5, "bidirectional block")
 
 
+def test_bidirectional_block_single_node_matches_composition(dcb):
+    """bidirectional_warp_fuse as one autograd node (metric = ones, flows without gradient) == the five-call
+    composition it replaces (forced here by a flow that asks for a gradient): values and feature gradients."""
+    g = torch.Generator().manual_seed(44)
+    n, c, r = 2, 48, 24
+    f1 = torch.randn(n, c, r, r, generator=g).cuda(); f2 = torch.randn(n, c, r, r, generator=g).cuda()
+    ff, fb = _flows(8, n, r, r, 0.8)
+    ff, fb = ff.cuda(), fb.cuda()
+    go = torch.randn(n, c, r, r, generator=g).cuda()
+    warper = dcb.FeatureWarperSoftsplat(with_learnable_metric=False)
+    res = []
+    for composed in (False, True):
+        a = f1.clone().requires_grad_(True); b = f2.clone().requires_grad_(True)
+        out = dcb.bidirectional_warp_fuse(a, b, ff.clone().requires_grad_(composed), fb, warper)
+        out.backward(go)
+        res.append((out.detach(), a.grad, b.grad))
+    for x, y, what in zip(res[0], res[1], ("fused", "grad first", "grad last")):
+        assert_close(x, y, 1e-6, f"single node vs composition: {what}")
+    with torch.no_grad():
+        assert_close(dcb.bidirectional_warp_fuse(f1, f2, ff, fb, warper), res[0][0], 1e-6, "no-grad call")
+
+
 # ---------------------------------------------------------------------------------------------
 # f-3: latent tile merge (patch_utils.py:83-174)
 # ---------------------------------------------------------------------------------------------

@@ -40,6 +40,7 @@ struct BwdArgs {
     int mode, eps;
     int px, cs;          // block shape
     unsigned pf_dist;    // source pass: L2 prefetch distance in CTAs (one wave)
+    unsigned tiles_x, tiles;   // packed source pass: 32 x 8 pixel tiles per row / per frame
 };
 
 #ifndef DCB_BS_PF
@@ -312,12 +313,44 @@ __global__ void __launch_bounds__(256) k_bwd_target4(const BwdArgs a) {
 }
 
 template <class T, class TF>
+#ifndef DCB_B4_TILE
+#define DCB_B4_TILE 1
+#endif
+#ifndef DCB_B4_PF
+#define DCB_B4_PF 1
+#endif
 __global__ void __launch_bounds__(256) k_bwd_source4(const BwdArgs a) {
+    const int W = a.W, H = a.H;
+#if DCB_B4_TILE
+    // 32 x 8 pixel tiles: the packed cells gathered by vertically adjacent pixels are the same rows (L1)
+    const unsigned tile = blockIdx.x % a.tiles, n = blockIdx.x / a.tiles;
+    const int x = (int)((tile % a.tiles_x) * 32 + (threadIdx.x & 31)), y = (int)((tile / a.tiles_x) * 8 + (threadIdx.x >> 5));
+#if DCB_B4_PF
+    {   // L2 prefetch for the tile one wave ahead: flow (2), metric, in (3) and the packed cells at the zero-flow position
+        const unsigned pb = blockIdx.x + a.pf_dist;
+        if (pb < gridDim.x) {
+            const unsigned ptile = pb % a.tiles, pn = pb / a.tiles;
+            const int px0 = (int)((ptile % a.tiles_x) * 32), py = (int)((ptile / a.tiles_x) * 8 + (threadIdx.x & 7));
+            const int plane = threadIdx.x >> 3;
+            if (py < H) {
+                const void* q = nullptr;
+                if (plane < 2) q = (const TF*)a.flow.p + pn * a.flow.sN + plane * a.flow.sC + py * a.flow.sH + px0 * a.flow.sW;
+                else if (plane == 2 && a.metric.p) q = (const T*)a.metric.p + pn * a.metric.sN + py * a.metric.sH + px0 * a.metric.sW;
+                else if (plane >= 4 && plane < 4 + a.C) q = (const T*)a.in.p + pn * a.in.sN + (plane - 4) * a.in.sC + py * a.in.sH + px0 * a.in.sW;
+                else if (plane >= 8 && plane < 12) q = (const float4*)a.tscal + (size_t)pn * a.HW + (size_t)py * W + px0 + (plane - 8) * 8;
+                if (q) asm volatile("prefetch.global.L2 [%0];" ::"l"(q));
+            }
+        }
+    }
+#endif
+    if (x >= W || y >= H) return;
+    const unsigned r = (unsigned)y * (unsigned)W + (unsigned)x, p = n * a.HW + r;
+#else
     const unsigned p = blockIdx.x * 256 + threadIdx.x;
     if (p >= a.total) return;
     const unsigned n = p / a.HW, r = p - n * a.HW;
     const int y = (int)(r / (unsigned)a.W), x = (int)(r - (unsigned)y * (unsigned)a.W);
-    const int W = a.W, H = a.H;
+#endif
     const TF* fp = (const TF*)a.flow.p + n * a.flow.sN + y * a.flow.sH + x * a.flow.sW;
     const Foot<float> f = make_foot<float>(x, y, (float)ld_stream(fp), (float)ld_stream(fp + a.flow.sC));
     const int x1 = (int)((unsigned)f.x0 + 1u), y1 = (int)((unsigned)f.y0 + 1u);
@@ -405,7 +438,14 @@ static int launch_bwd(BwdArgs& a, int dtype, cudaStream_t st) {
             const unsigned blocks = (a.total + 255) / 256;
             k_bwd_target4<T><<<blocks, 256, 0, st>>>(a);
             DCB_CHECK_LAUNCH("k_bwd_target4");
+#if DCB_B4_TILE
+            a.tiles_x = (unsigned)(a.W + 31) / 32;
+            a.tiles = a.tiles_x * ((unsigned)(a.H + 7) / 8);
+            a.pf_dist = (unsigned)(device_sm_count() * 5);      // 48 registers: 5 CTAs per SM
+            k_bwd_source4<T, TF><<<a.tiles * (unsigned)a.N, 256, 0, st>>>(a);
+#else
             k_bwd_source4<T, TF><<<blocks, 256, 0, st>>>(a);
+#endif
             DCB_CHECK_LAUNCH("k_bwd_source4");
             return DCB_OK;
         }

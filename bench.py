@@ -423,9 +423,11 @@ def run_ours(args):
         if world == 1 and not args.no_cpu:
             from oracle import oracle as orc
             threads = orc.max_threads()
-            v, secs = _cpu_port_mpixel_s(max(threads, 4), threads)
+            nsample = max(4, (F // max(threads, 1)) * threads) if F >= threads else F      # whole rounds of the thread pool
+            v, secs = _cpu_port_mpixel_s(nsample, threads, repeats=2)
             line["cpu_baseline"] = {"value": round(v, 2), "unit": "Mpixel/s", "cores": threads, "kind": "port",
-                                    "sample": f"{max(threads, 4)} of the workload's 1080p frames, soft fwd fp32, {secs:.1f} s (oracle C kernel over pthreads + torch CPU pre/post ops)"}
+                                    "sample": f"{nsample} of the step's {F} 1080p frames, soft fwd fp32, best of 2 runs of {secs:.1f} s = "
+                                              f"{secs * threads:.0f} core-seconds (oracle C kernel over {threads} pthreads + torch CPU pre/post ops)"}
         else:
             line["cpu_baseline"] = None
         if world == 1 and not args.no_extra:

@@ -58,6 +58,8 @@ SYMBOLS = {
     "dcb_splat_workspace_bytes": (ctypes.c_int64, [ctypes.c_int64] * 4 + [ctypes.c_int32] * 3),
     "dcb_splat_fwd_workspace_bytes": (ctypes.c_int64, [ctypes.c_int64] * 4 + [ctypes.c_int32] * 3),
     "dcb_splat_bwd_workspace_bytes": (ctypes.c_int64, [ctypes.c_int64] * 4 + [ctypes.c_int32] * 3),
+    "dcb_splat_fwd_workspace_is_scratch": (ctypes.c_int32, [ctypes.c_int64] * 4 + [ctypes.c_int32] * 3),
+    "dcb_set_option": (ctypes.c_int, [ctypes.c_char_p, ctypes.c_int64]),
     "dcb_splat_fwd": (ctypes.c_int, [_P] * 6 + [ctypes.c_void_p, ctypes.c_int64] + [ctypes.c_int32] * 3 + [ctypes.c_void_p]),
     "dcb_splat_bwd": (ctypes.c_int, [_P] * 10 + [ctypes.c_void_p, ctypes.c_int64] + [ctypes.c_int32] * 3 + [ctypes.c_void_p]),
     "dcb_backwarp_fwd": (ctypes.c_int, [_P] * 5 + [ctypes.c_int32, ctypes.c_void_p]),
@@ -100,7 +102,34 @@ def lib() -> ctypes.CDLL:
                     fn = getattr(handle, name)
                     fn.restype, fn.argtypes = res, args
                 _lib = handle
+                for opt in ("fwd_path", "owner_group_bytes", "pipe_group_bytes"):      # A/B knobs: DCB_FWD_PATH=1 python ...
+                    v = os.environ.get("DCB_" + opt.upper())
+                    if v:
+                        handle.dcb_set_option(opt.encode(), int(v))
     return _lib
+
+
+def set_option(name: str, value: int) -> None:
+    """Process-wide tuning / test knob of the native library (``dcb_set_option`` in the header)."""
+    check(lib().dcb_set_option(name.encode(), int(value)), "dcb_set_option")
+    _scratch_cache.clear()
+    for hook in _option_hooks:
+        hook()
+
+
+_option_hooks: list = []          # callables that drop size caches derived from the library's dispatch
+
+
+_scratch_cache: dict = {}
+
+
+def fwd_is_scratch(n, c, h, w, dt, mode, flags=0) -> bool:
+    """True when the forward of these sizes keeps no accumulators in its workspace (plain scratch, no clean protocol)."""
+    key = (n, c, h, w, dt, mode, flags)
+    v = _scratch_cache.get(key)
+    if v is None:
+        v = _scratch_cache[key] = bool(lib().dcb_splat_fwd_workspace_is_scratch(n, c, h, w, dt, mode, flags))
+    return v
 
 
 class DcbError(RuntimeError):

@@ -45,10 +45,11 @@ def compute_mask(flow_bwd_tensor, flow_fwd_tensor):
         dev = a.device
         mask = torch.empty((n, 1, h, w), dtype=a.dtype, device=dev)
         need = lib.dcb_occlusion_mask_workspace_bytes(n, h, w)
-        ws = _lib.workspace(dev, need, "acc")
+        scratch = _lib.fwd_is_scratch(n, 2, h, w, _lib._DTYPES[a.dtype], _lib.MODE_SOFT)
+        ws = _lib.workspace(dev, need, "scratch" if scratch else "acc")
         with _lib.on_device(dev):
             rc = lib.dcb_occlusion_mask(_lib.desc(a), _lib.desc(b), _lib.desc(mask), ws.data_ptr(), ws.numel(),
-                                        _lib.FLAG_WS_CLEAN, _lib.stream_ptr(dev))
+                                        0 if scratch else _lib.FLAG_WS_CLEAN, _lib.stream_ptr(dev))
         if rc != 0:
             _lib.invalidate_acc(dev)
         _lib.check(rc, "dcb_occlusion_mask")

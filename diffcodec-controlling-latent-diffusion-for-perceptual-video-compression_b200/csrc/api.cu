@@ -46,7 +46,7 @@ long long backwarp_bwd_workspace(long long N, long long C, long long H, long lon
 int backwarp_bwd_impl(const DcbTensor*, const DcbTensor*, const DcbTensor*, const DcbTensor*, const DcbTensor*, int,
                       void*, long long, cudaStream_t);
 long long mask_workspace(long long N, long long H, long long W);
-long long recipe_workspace(long long N, long long H, long long W);
+long long recipe_workspace(long long N, long long C, long long H, long long W);
 int occlusion_mask_impl(const DcbTensor*, const DcbTensor*, const DcbTensor*, void*, long long, int, cudaStream_t);
 int residual_fused_impl(const DcbTensor*, const DcbTensor*, const DcbTensor*, const DcbTensor*, const DcbTensor*,
                         const DcbTensor*, const DcbTensor*, const DcbTensor*, void*, long long, int, int, cudaStream_t);
@@ -55,6 +55,11 @@ int bidir_fuse_fwd_impl(const DcbTensor*, const DcbTensor*, const DcbTensor*, co
 int bidir_fuse_bwd_impl(const DcbTensor*, const DcbTensor*, const DcbTensor*, const DcbTensor*, const DcbTensor*,
                         const DcbTensor*, const DcbTensor*, const DcbTensor*, const DcbTensor*, const DcbTensor*,
                         const DcbTensor*, cudaStream_t);
+
+extern int g_fwd_path;
+bool use_owner(int dtype, int mode, long long C, long long H, long long W);
+void owner_set_group_bytes(long long b);
+void pipe_set_group_bytes(long long b);
 
 long long tile_merge_workspace(long long C, long long H, long long W, int n_tiles);
 int tile_merge_impl(const DcbTensor*, const long long*, int, const DcbTensor*, long long, long long, double, void*, long long,
@@ -138,6 +143,24 @@ int64_t dcb_splat_fwd_workspace_bytes(int64_t N, int64_t C, int64_t H, int64_t W
     if (N < 0 || C < 0 || H < 0 || W < 0) return 0;
     if (flags & DCB_FLAG_DETERMINISTIC) return (int64_t)det_workspace(N, C, H, W, dtype, mode);
     return (int64_t)splat_fwd_workspace(N, C, H, W, dtype, mode);
+}
+
+int32_t dcb_splat_fwd_workspace_is_scratch(int64_t N, int64_t C, int64_t H, int64_t W, int32_t dtype, int32_t mode, int32_t flags) {
+    (void)N;
+    if (flags & DCB_FLAG_DETERMINISTIC) return 1;
+    return use_owner(dtype, mode, C, H, W) ? 1 : 0;
+}
+
+int dcb_set_option(const char* name, int64_t value) {
+    if (!name) return set_error(DCB_E_NULL, "dcb_set_option: name is required");
+    if (!strcmp(name, "fwd_path")) {
+        if (value < 0 || value > 2) return set_error(DCB_E_MODE, "dcb_set_option: fwd_path is 0, 1 or 2");
+        g_fwd_path = (int)value;
+        return DCB_OK;
+    }
+    if (!strcmp(name, "pipe_group_bytes")) { pipe_set_group_bytes(value); return DCB_OK; }
+    if (!strcmp(name, "owner_group_bytes")) { owner_set_group_bytes(value); return DCB_OK; }
+    return set_error(DCB_E_MODE, "dcb_set_option: unknown option '%s'", name);
 }
 
 int64_t dcb_splat_bwd_workspace_bytes(int64_t N, int64_t C, int64_t H, int64_t W, int32_t dtype, int32_t mode, int32_t flags) {
@@ -298,8 +321,7 @@ int dcb_occlusion_mask(const DcbTensor* flow_a, const DcbTensor* flow_b, const D
 }
 
 int64_t dcb_residual_workspace_bytes(int64_t N, int64_t C, int64_t H, int64_t W) {
-    (void)C;
-    return (int64_t)recipe_workspace(N, H, W);
+    return (int64_t)recipe_workspace(N, C, H, W);
 }
 
 int dcb_residual_fused(const DcbTensor* image1, const DcbTensor* flow1, const DcbTensor* flow2, const DcbTensor* gt,

@@ -25,6 +25,23 @@ int splat_pipe_impl(const DcbTensor* in, const DcbTensor* flow, const DcbTensor*
                     const DcbTensor* norm, const DcbTensor* mask, void* ws, int mode, int eps, bool ws_clean,
                     cudaStream_t st, bool ones_metric, const DcbTensor* mask_out);
 
+// implemented in splat_owner.cu / splat_fwd.cu
+long long owner_workspace(long long N, long long H, long long W);
+bool use_owner(int dtype, int mode, long long C, long long H, long long W);
+bool pipe_supported(const DcbTensor* in, const DcbTensor* flow, const DcbTensor* metric);
+int splat_owner_impl(const DcbTensor* in, const DcbTensor* flow, const DcbTensor* metric, const DcbTensor* out,
+                     const DcbTensor* norm, const DcbTensor* mask, void* ws, int mode, int eps, cudaStream_t st,
+                     bool ones_metric, const DcbTensor* mask_out);
+
+// one soft splat with an all-ones metric through whichever forward applies (owner kernels, or the accumulator pipeline)
+static int ones_splat(const DcbTensor* in, const DcbTensor* flow, const DcbTensor* out, const DcbTensor* mask_out, void* ws,
+                      bool owner, bool ws_clean, cudaStream_t st) {
+    if (!pipe_supported(in, flow, nullptr))
+        return set_error(DCB_E_LIMIT, "conditioning: tensor spans beyond 2^31 elements are not supported (32-bit in-frame offsets)");
+    if (owner) return splat_owner_impl(in, flow, nullptr, out, nullptr, nullptr, ws, DCB_MODE_SOFT, DCB_EPS_ADD, st, true, mask_out);
+    return splat_pipe_impl(in, flow, nullptr, out, nullptr, nullptr, ws, DCB_MODE_SOFT, DCB_EPS_ADD, ws_clean, st, true, mask_out);
+}
+
 struct FuseArgs {
     View gt;
     void* fused;           // in: warped, out: fused   [N,C,H,W]
@@ -77,11 +94,16 @@ __global__ void __launch_bounds__(256) k_recipe_fuse(const FuseArgs a) {
 }
 
 // ---------------------------------------------------------------------------------------------
-long long mask_workspace(long long N, long long H, long long W) { return pipe_workspace(N, H, W); }
+static long long splat_part(long long N, long long C, long long H, long long W) {
+    return use_owner(DCB_F32, DCB_MODE_SOFT, C, H, W) ? owner_workspace(N, H, W) : pipe_workspace(N, H, W);
+}
 
-long long recipe_workspace(long long N, long long H, long long W) {
-    // pipeline accumulators + two mask planes (sized for fp32) when the caller does not want them
-    return pipe_workspace(N, H, W) + 2 * align_up(N * H * W * 4, 256);
+long long mask_workspace(long long N, long long H, long long W) { return splat_part(N, 2, H, W); }
+
+long long recipe_workspace(long long N, long long C, long long H, long long W) {
+    // splat workspace (landing boxes, or pipeline accumulators) + two mask planes (sized for fp32) when the caller does not want them
+    const long long a = splat_part(N, C, H, W), b = splat_part(N, 2, H, W);
+    return (a > b ? a : b) + 2 * align_up(N * H * W * 4, 256);
 }
 
 int occlusion_mask_impl(const DcbTensor* flow_a, const DcbTensor* flow_b, const DcbTensor* mask, void* ws,
@@ -89,12 +111,14 @@ int occlusion_mask_impl(const DcbTensor* flow_a, const DcbTensor* flow_b, const 
     const long long N = flow_a->size[0], H = flow_a->size[2], W = flow_a->size[3];
     if (N * H * W == 0) return DCB_OK;
     const long long need = mask_workspace(N, H, W);
-    if (!ws || ws_bytes < need || ((uintptr_t)ws & 255))
+    if (need > 0 && (!ws || ws_bytes < need || ((uintptr_t)ws & 255)))
         return set_error(DCB_E_WORKSPACE, "occlusion_mask: workspace of %lld bytes required, got %lld", need, ws_bytes);
     if (flow_a->dtype != DCB_F32 && flow_a->dtype != DCB_BF16)
         return set_error(DCB_E_DTYPE, "occlusion_mask: F32 or BF16 only, got %d", flow_a->dtype);
-    return splat_pipe_impl(flow_a, flow_b, nullptr, nullptr, nullptr, nullptr, ws, DCB_MODE_SOFT, DCB_EPS_ADD,
-                           (flags & DCB_FLAG_WS_CLEAN) != 0, st, true, mask);
+    const bool owner = use_owner(flow_a->dtype, DCB_MODE_SOFT, 2, H, W), clean = (flags & DCB_FLAG_WS_CLEAN) != 0;
+    const int rc = ones_splat(flow_a, flow_b, nullptr, mask, ws, owner, clean, st);
+    if (rc == DCB_OK && owner && clean && need > 0) DCB_CHECK_CUDA(cudaMemsetAsync(ws, 0, (size_t)need, st));
+    return rc;
 }
 
 template <class T> static int launch_fuse(const FuseArgs& a, cudaStream_t st) {
@@ -109,13 +133,14 @@ int residual_fused_impl(const DcbTensor* image1, const DcbTensor* flow1, const D
                         cudaStream_t st) {
     const long long N = image1->size[0], C = image1->size[1], H = image1->size[2], W = image1->size[3];
     if (N * H * W == 0) return DCB_OK;
-    const long long need = recipe_workspace(N, H, W);
+    const long long need = recipe_workspace(N, C, H, W);
     if (!ws || ws_bytes < need || ((uintptr_t)ws & 255))
         return set_error(DCB_E_WORKSPACE, "residual_fused: workspace of %lld bytes required, got %lld", need, ws_bytes);
     if (image1->dtype != DCB_F32 && image1->dtype != DCB_BF16)
         return set_error(DCB_E_DTYPE, "residual_fused: F32 or BF16 only, got %d", image1->dtype);
     const bool clean = (flags & DCB_FLAG_WS_CLEAN) != 0;
-    const long long pipe_bytes = pipe_workspace(N, H, W), plane = align_up(N * H * W * 4, 256);
+    const long long plane = align_up(N * H * W * 4, 256), pipe_bytes = need - 2 * plane;
+    const bool own_img = use_owner(image1->dtype, DCB_MODE_SOFT, C, H, W), own_flow = use_owner(image1->dtype, DCB_MODE_SOFT, 2, H, W);
     // the mask planes live behind the accumulators; they are scratch (not part of the clean region)
     DcbTensor m1 = *flow1, m2 = *flow1;
     m1.size[1] = m2.size[1] = 1;
@@ -125,13 +150,17 @@ int residual_fused_impl(const DcbTensor* image1, const DcbTensor* flow1, const D
     const DcbTensor* pf = occ_fwd ? occ_fwd : &m1;
     const DcbTensor* pb = occ_bwd ? occ_bwd : &m2;
 
-    int rc = splat_pipe_impl(image1, flow1, nullptr, fused, nullptr, nullptr, ws, DCB_MODE_SOFT, DCB_EPS_ADD, clean, st, true, nullptr);
+    // a pipeline pass after an owner pass would find landing boxes where it expects all-zero accumulators
+    const bool mixed = own_img != own_flow;
+    int rc = ones_splat(image1, flow1, fused, nullptr, ws, own_img, clean, st);
     if (rc != DCB_OK) return rc;
+    if (mixed && own_img) DCB_CHECK_CUDA(cudaMemsetAsync(ws, 0, (size_t)pipe_bytes, st));
     // compute_mask(flow1, flow2): flow1 splatted by flow2; compute_mask(flow2, flow1): the other way round
-    rc = splat_pipe_impl(flow1, flow2, nullptr, nullptr, nullptr, nullptr, ws, DCB_MODE_SOFT, DCB_EPS_ADD, true, st, true, pf);
+    rc = ones_splat(flow1, flow2, nullptr, pf, ws, own_flow, !own_img || mixed, st);
     if (rc != DCB_OK) return rc;
-    rc = splat_pipe_impl(flow2, flow1, nullptr, nullptr, nullptr, nullptr, ws, DCB_MODE_SOFT, DCB_EPS_ADD, true, st, true, pb);
+    rc = ones_splat(flow2, flow1, nullptr, pb, ws, own_flow, true, st);
     if (rc != DCB_OK) return rc;
+    if (clean && own_flow && pipe_bytes > 0) DCB_CHECK_CUDA(cudaMemsetAsync(ws, 0, (size_t)pipe_bytes, st));
 
     FuseArgs a;
     a.gt = make_view(gt);

@@ -140,6 +140,13 @@ int splat_planar_impl(const DcbTensor* in, const DcbTensor* flow, const DcbTenso
                       const DcbTensor* norm, const DcbTensor* mask, void* ws, int mode, int eps, bool ws_clean,
                       cudaStream_t st);
 
+// implemented in splat_owner.cu
+long long owner_workspace(long long N, long long H, long long W);
+bool owner_supported(long long C, int mode, long long H, long long W);
+int splat_owner_impl(const DcbTensor* in, const DcbTensor* flow, const DcbTensor* metric, const DcbTensor* out,
+                     const DcbTensor* norm, const DcbTensor* mask, void* ws, int mode, int eps, cudaStream_t st,
+                     bool ones_metric = false, const DcbTensor* mask_out = nullptr);
+
 // implemented in splat_lists.cu
 long long lists_workspace(long long N, long long H, long long W);
 bool lists_supported(const DcbTensor* in, const DcbTensor* flow, const DcbTensor* metric, int mode);
@@ -161,7 +168,19 @@ static bool use_pipe(int dtype, int mode, long long C) {
     return dtype != DCB_F64 && C + (mode == DCB_MODE_SUM ? 0 : 1) <= 4;
 }
 
+// dcb_set_option("fwd_path"): 0 = automatic, 1 = round-1 accumulator pipeline, 2 = target-tile owner wherever it applies
+int g_fwd_path = 0;
+
+// C+1 <= 8 channels in fp32 / bf16: target-tile ownership, accumulators in shared memory (splat_owner.cu)
+// Opt-in only: measured on B200 (profiles/r02/NOTES.md) it needs 2-3x the instructions of the accumulator pipeline and loses
+// at every size, so the automatic dispatch never picks it.
+bool use_owner(int dtype, int mode, long long C, long long H, long long W) {
+    if (dtype == DCB_F64 || g_fwd_path != 2) return false;
+    return owner_supported(C, mode, H, W);
+}
+
 long long splat_fwd_workspace(long long N, long long C, long long H, long long W, int dtype, int mode) {
+    if (use_owner(dtype, mode, C, H, W)) return owner_workspace(N, H, W);
     if (use_pipe(dtype, mode, C)) return pipe_workspace(N, H, W);
     if (dtype != DCB_F64) {
         const long long planar = planar_workspace(N, C, H, W, dtype, mode);
@@ -245,6 +264,17 @@ int splat_fwd_impl(const DcbTensor* in, const DcbTensor* flow, const DcbTensor* 
         return splat_fwd_f64(a, out, ws, ws_bytes, mode, ws_clean, mask != nullptr, st);
     }
     if (in->dtype != DCB_F32 && in->dtype != DCB_BF16) return set_error(DCB_E_DTYPE, "splat_fwd: unsupported dtype %d", in->dtype);
+    if (use_owner(in->dtype, mode, C, H, W)) {
+        if (!pipe_supported(in, flow, metric))
+            return set_error(DCB_E_LIMIT, "splat_fwd: tensor spans beyond 2^31 elements are not supported (32-bit in-frame offsets)");
+        const long long need = owner_workspace(N, H, W);
+        if (need > 0 && (!ws || ws_bytes < need || ((uintptr_t)ws & 255)))
+            return set_error(DCB_E_WORKSPACE, "splat_fwd: workspace of %lld bytes (256 B aligned) required, got %lld", need, ws_bytes);
+        const int rc = splat_owner_impl(in, flow, metric, out, norm, mask, ws, mode, eps, st);
+        // the flag promises an all-zero workspace on exit; callers that ask dcb_splat_fwd_workspace_is_scratch() never pass it here
+        if (rc == DCB_OK && ws_clean && need > 0) DCB_CHECK_CUDA(cudaMemsetAsync(ws, 0, (size_t)need, st));
+        return rc;
+    }
     const bool pipe = use_pipe(in->dtype, mode, C);
     if (pipe && !pipe_supported(in, flow, metric))
         return set_error(DCB_E_LIMIT, "splat_fwd: tensor spans beyond 2^31 elements are not supported by the float4 path");

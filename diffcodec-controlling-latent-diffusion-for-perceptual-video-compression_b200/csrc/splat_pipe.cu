@@ -320,8 +320,13 @@ __global__ void __launch_bounds__(kPipeThreads, kMinCtas) k_splat_step(const __g
 // ---------------------------------------------------------------------------------------------
 // host
 // ---------------------------------------------------------------------------------------------
+// dcb_set_option("pipe_group_bytes"): tests shrink the ring slots so that small tensors run through many groups
+long long g_pipe_group_bytes = 0;
+void pipe_set_group_bytes(long long b) { g_pipe_group_bytes = b > 0 ? b : 0; }
+
 static long long group_frames(long long N, long long H, long long W) {
-    long long g = kGroupBytes / (H * W * 16 > 0 ? H * W * 16 : 1);
+    const long long gb = g_pipe_group_bytes > 0 ? g_pipe_group_bytes : kGroupBytes;
+    long long g = gb / (H * W * 16 > 0 ? H * W * 16 : 1);
     if (g < 1) g = 1;
     return g > N ? (N < 1 ? 1 : N) : g;
 }

@@ -292,9 +292,11 @@ __global__ void __launch_bounds__(kPThreads, DCB_PMINCTAS) k_planar_step(const _
 // ---------------------------------------------------------------------------------------------
 // host
 // ---------------------------------------------------------------------------------------------
+extern long long g_pipe_group_bytes;      // splat_pipe.cu: dcb_set_option("pipe_group_bytes")
+
 static long long planar_group_frames(long long N, long long C, long long H, long long W) {
     const long long per = (C + 3) / 4 * 16 * H * W;
-    long long g = kPGroupBytes / (per > 0 ? per : 1);
+    long long g = (g_pipe_group_bytes > 0 ? g_pipe_group_bytes : (long long)kPGroupBytes) / (per > 0 ? per : 1);
     if (g < 1) g = 1;
     return g > N ? (N < 1 ? 1 : N) : g;
 }

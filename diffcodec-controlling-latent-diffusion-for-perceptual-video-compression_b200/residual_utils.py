@@ -66,11 +66,13 @@ def residual_conditioning(image1, flow1, flow2, gt, variant: str = "dataset", re
         occ_fwd = torch.empty((n, 1, h, w), dtype=image1.dtype, device=dev)
         occ_bwd = torch.empty_like(occ_fwd)
         need = lib.dcb_residual_workspace_bytes(n, c, h, w)
-        ws = _lib.workspace(dev, need, "acc")
+        dt = _lib._DTYPES[image1.dtype]
+        scratch = _lib.fwd_is_scratch(n, c, h, w, dt, _lib.MODE_SOFT) and _lib.fwd_is_scratch(n, 2, h, w, dt, _lib.MODE_SOFT)
+        ws = _lib.workspace(dev, need, "scratch" if scratch else "acc")
         with _lib.on_device(dev):
             rc = lib.dcb_residual_fused(_lib.desc(image1), _lib.desc(flow1), _lib.desc(flow2), _lib.desc(gt),
                                         _lib.desc(fused), _lib.desc(residual), _lib.desc(occ_fwd), _lib.desc(occ_bwd),
-                                        ws.data_ptr(), ws.numel(), _VARIANTS[variant], _lib.FLAG_WS_CLEAN,
+                                        ws.data_ptr(), ws.numel(), _VARIANTS[variant], 0 if scratch else _lib.FLAG_WS_CLEAN,
                                         _lib.stream_ptr(dev))
         if rc != 0:
             _lib.invalidate_acc(dev)

@@ -34,6 +34,7 @@ _EPS = {"addeps": _lib.EPS_ADD, "zeroeps": _lib.EPS_ZERO, "clipeps": _lib.EPS_CL
 
 _state = threading.local()
 _ws_sizes: dict = {}
+_lib._option_hooks.append(_ws_sizes.clear)
 
 
 def is_deterministic() -> bool:
@@ -88,7 +89,7 @@ def _forward(tenIn, tenFlow, tenMetric, mask, mode: int, eps: int, det: bool, wa
     stream = _lib.stream_ptr(dev)
     ws, ws_ptr = None, None
     if need > 0:
-        if det:
+        if det or _lib.fwd_is_scratch(n, c, h, w, dt, mode, flags):
             ws = _lib.workspace(dev, need, "scratch", stream)
         else:
             ws = _lib.workspace(dev, need, "acc", stream)

@@ -96,6 +96,27 @@ int64_t dcb_splat_bwd_workspace_bytes(int64_t N, int64_t C, int64_t H, int64_t W
                                       int32_t mode, int32_t flags);
 
 /*
+ * 1 when the forward splat of these sizes keeps NO accumulators in its workspace (target-tile-owner kernels:
+ * the workspace only holds small per-strip landing boxes): the workspace is then plain scratch, DCB_FLAG_WS_CLEAN
+ * buys nothing (if it is passed anyway the library zeroes what it wrote, to honour the flag's exit guarantee).
+ * 0 when the workspace holds accumulators and the all-zero protocol of DCB_FLAG_WS_CLEAN saves a memset.
+ */
+int32_t dcb_splat_fwd_workspace_is_scratch(int64_t N, int64_t C, int64_t H, int64_t W, int32_t elem_dtype,
+                                           int32_t mode, int32_t flags);
+
+/*
+ * Tuning / test knobs (process-wide, not thread-safe against concurrent calls; defaults are what ships):
+ *   "fwd_path"          0 automatic | 1 round-1 accumulator pipeline (red.global into L2-resident cells)
+ *                       | 2 target-tile owner kernels wherever they apply
+ *   "pipe_group_bytes"  accumulator bytes per ring slot of the accumulator pipelines (tests shrink it so that
+ *                       small tensors run through many ring groups); 0 restores the default
+ *   "owner_group_bytes" flow bytes per (pre-pass, owner) launch pair; 0 restores the default
+ * Returns DCB_OK, or DCB_E_MODE for an unknown name. There is no equivalent in the reference (its kernels are
+ * re-specialised per shape by string templating, controlnet/softsplat.py:27-216).
+ */
+int dcb_set_option(const char* name, int64_t value);
+
+/*
  * Forward splat. Replaces, in one call, the eager pre-ops, `new_zeros`, the `softsplat_out`
  * kernel and the eager post-ops of softsplat() -- controlnet/softsplat.py:232-274 and
  * softsplat_func.forward :277-355. With mode = DCB_MODE_SUM it is exactly

@@ -4,6 +4,12 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspa
 import torch
 import diffcodec_b200 as d
 F = 32
+# argv[1]: forward kernel family (0 automatic, 1 round-1 accumulator pipeline, 2 target-tile owner); argv[2]: owner_group_bytes
+if len(sys.argv) > 1:
+    d._lib.set_option("fwd_path", int(sys.argv[1]))
+if len(sys.argv) > 2:
+    d._lib.set_option("owner_group_bytes", int(sys.argv[2]))
+print("fwd_path", sys.argv[1] if len(sys.argv) > 1 else 0, "owner_group_bytes", sys.argv[2] if len(sys.argv) > 2 else "default")
 g = torch.Generator(device="cuda").manual_seed(0)
 tin = torch.rand(F, 3, 1080, 1920, device="cuda", generator=g)
 metric = -torch.rand(F, 1, 1080, 1920, device="cuda", generator=g)

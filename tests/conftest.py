@@ -15,3 +15,14 @@ def pytest_configure(config):
 @pytest.fixture(scope="session")
 def golden_dir():
     return os.path.join(ROOT, "tests", "golden")
+
+
+@pytest.fixture(scope="session", autouse=True)
+def _forward_path_override():
+    """DCB_TEST_FWD_PATH=1|2 runs the whole suite with the forward pinned to one kernel family
+    (1 = round-1 accumulator pipeline, 2 = target-tile owner); default: the library's own dispatch."""
+    v = os.environ.get("DCB_TEST_FWD_PATH")
+    if v:
+        import diffcodec_b200
+        diffcodec_b200._lib.set_option("fwd_path", int(v))
+    yield

@@ -40,6 +40,26 @@ def test_workspace_queries_need_no_gpu():
     assert lib.dcb_splat_fwd_workspace_bytes(1, 3, 1080, 1920, L.DCB_F32, L.MODE_SOFT, 0) == 1080 * 1920 * 16
     assert lib.dcb_splat_fwd_workspace_bytes(64, 3, 1080, 1920, L.DCB_F32, L.MODE_SOFT, 0) == 2 * 1080 * 1920 * 16
     assert lib.dcb_splat_workspace_bytes(1, 8, 64, 64, L.DCB_F32, L.MODE_SUM, 0) == 2 * 64 * 64 * 16   # two channel quads
+    assert lib.dcb_splat_fwd_workspace_is_scratch(1, 3, 1080, 1920, L.DCB_F32, L.MODE_SOFT, 0) == 0
+    assert lib.dcb_splat_fwd_workspace_is_scratch(1, 3, 1080, 1920, L.DCB_F32, L.MODE_SOFT, L.FLAG_DETERMINISTIC) == 1
+    L.set_option("pipe_group_bytes", 1 << 20)          # tests shrink the ring slots: many groups on small tensors
+    try:
+        assert lib.dcb_splat_fwd_workspace_bytes(64, 3, 256, 256, L.DCB_F32, L.MODE_SOFT, 0) == 2 * 256 * 256 * 16
+    finally:
+        L.set_option("pipe_group_bytes", 0)
+    L.set_option("fwd_path", 2)      # opt-in target-tile owner kernels (C + 1 <= 4): the workspace only holds the landing boxes
+    try:                             # of the 32 x 4 source strips (8 B per strip + 8 B per strip row); small frames need none
+        boxes = 270 * (60 + 1) * 8
+        assert lib.dcb_splat_fwd_workspace_bytes(1, 3, 1080, 1920, L.DCB_F32, L.MODE_SOFT, 0) == (boxes + 255) // 256 * 256
+        assert lib.dcb_splat_fwd_workspace_bytes(64, 3, 1080, 1920, L.DCB_F32, L.MODE_SOFT, 0) == 64 * boxes
+        assert lib.dcb_splat_fwd_workspace_bytes(4, 3, 135, 240, L.DCB_BF16, L.MODE_SOFT, 0) == 0
+        assert lib.dcb_splat_fwd_workspace_is_scratch(1, 3, 1080, 1920, L.DCB_F32, L.MODE_SOFT, 0) == 1
+        assert lib.dcb_splat_fwd_workspace_is_scratch(8, 64, 256, 256, L.DCB_F32, L.MODE_SOFT, 0) == 0
+        assert lib.dcb_occlusion_mask_workspace_bytes(2, 64, 64) == 0
+    finally:
+        L.set_option("fwd_path", 0)
+    with pytest.raises(AssertionError):
+        L.set_option("no_such_option", 1)
     assert lib.dcb_splat_workspace_bytes(1, 8, 64, 64, L.DCB_F64, L.MODE_SUM, 0) == 0        # fp64 reds go straight into out
     # many channels: planar accumulators, 2 slots x 2 frames x 64 planes + 3 slots x 2 normaliser planes
     assert lib.dcb_splat_workspace_bytes(8, 64, 256, 256, L.DCB_F32, L.MODE_SOFT, 0) == (2 * 2 * 64 + 3 * 2) * 256 * 256 * 4

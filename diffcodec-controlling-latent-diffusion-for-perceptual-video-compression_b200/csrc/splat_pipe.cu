@@ -36,8 +36,11 @@ constexpr int kWarpsPerCta = kPipeThreads / 32;
 #ifndef DCB_KROWS
 #define DCB_KROWS 4
 #endif
+#ifndef DCB_NORM_V
+#define DCB_NORM_V 2         // normalise stage: 0 = one pixel per lane (any layout), 2 = two pixels per lane with 256-bit accesses, 4 = four
+#endif
 #ifndef DCB_KPASSES
-#define DCB_KPASSES 1
+#define DCB_KPASSES 2
 #endif
 #ifndef DCB_MINCTAS
 #define DCB_MINCTAS 32
@@ -50,10 +53,11 @@ constexpr int kStripH = kRows * kPasses;    // a scatter item: 32 columns x 16 r
 #define DCB_NPER 8
 #endif
 #ifndef DCB_NBATCH
-#define DCB_NBATCH 2
+#define DCB_NBATCH (DCB_KROWS * DCB_KPASSES / DCB_NPER)
 #endif
 constexpr int kNPer = DCB_NPER;             // normalise: pixels per lane per batch
 constexpr int kNBatches = DCB_NBATCH;
+static_assert(kNBatches >= 1 && kNPer % 4 == 0, "a normalise item covers the pixels of one scatter strip");
 constexpr int kChunk = 32 * kNPer * kNBatches;   // a normalise item: 512 target pixels
 constexpr float kExp1 = 2.7182817459106445f;     // expf(1.0f): what tenMetric.exp() yields for an all-ones metric
 constexpr long long kGroupBytes = 34ll << 20;    // accumulator bytes per ring slot (one 1080p frame = 31.6 MiB)
@@ -67,13 +71,16 @@ struct PipeArgs {
     unsigned HW;
     int eps;
     int G;                   // frames per group (per accumulator slot)
-    int tiles_x, ts, tn;     // scatter strips per row / per frame, normalise chunks per frame
+    int tiles_x, tiles_y, ts, tn;   // scatter strips per row / per column / per frame, normalise chunks per frame
     int s_frame0, s_frames;  // this step scatters frames [s_frame0, s_frame0 + s_frames)
     int n_frame0, n_frames;  // ... and normalises frames [n_frame0, n_frame0 + n_frames)
     View epi_flow;           // epilogue 1 (occlusion mask): the motion field compared with the splatted one
     void* mask_out;          // epilogue 1: [N,1,H,W] in T
     int epi;                 // 0 = normalise (softsplat), 1 = occlusion mask (control_utils.py:15-16)
     int ones;                // metric is all-ones and not materialised (compute_mask, dataset wrappers)
+    float* acc_s;            // accumulator slot of the frame group this launch scatters (frame s_frame0 at offset 0)
+    float* acc_n;            // ... and of the group it normalises
+    int vec4;                // H*W % 4 == 0 and out / norm 16-byte aligned: the normalise stage works on 4 pixels per lane
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -91,9 +98,8 @@ __device__ __forceinline__ void red4_if(bool p, float* acc, int off, const float
 }
 
 template <class T, class TF, int MODE, int CA>
-__device__ __forceinline__ void scatter_strip(const PipeArgs& a, int frame, int tile, float* acc, int lane) {
+__device__ __forceinline__ void scatter_strip(const PipeArgs& a, int frame, int tx, int ty, float* acc, int lane) {
     constexpr int C = CA - (MODE != DCB_MODE_SUM ? 1 : 0);
-    const int tx = tile % a.tiles_x, ty = tile / a.tiles_x;
     const int x = tx * 32 + lane;
     const int W = a.W, H = a.H;
     const bool xin = x < W;
@@ -249,6 +255,129 @@ __device__ __forceinline__ void normalize_chunk(const PipeArgs& a, int frame, in
     }
 }
 
+// four consecutive pixels per lane: 128-bit accumulator loads, re-zero stores and output stores (one per channel
+// for FOUR pixels instead of one per channel per pixel): 60 -> ~18 instructions per pixel
+__device__ __forceinline__ void st_stream4(float* p, float a, float b, float c, float d) { __stcs((float4*)p, make_float4(a, b, c, d)); }
+__device__ __forceinline__ void st_stream4(__nv_bfloat16* p, float a, float b, float c, float d) {
+    const __nv_bfloat162 lo = __floats2bfloat162_rn(a, b), hi = __floats2bfloat162_rn(c, d);
+    uint2 u; u.x = *reinterpret_cast<const unsigned*>(&lo); u.y = *reinterpret_cast<const unsigned*>(&hi);
+    __stcs((uint2*)p, u);
+}
+
+template <class T, int MODE, int CA>
+__device__ __forceinline__ void normalize_chunk_v4(const PipeArgs& a, int frame, int chunk, float* acc, int lane) {
+    constexpr int C = CA - (MODE != DCB_MODE_SUM ? 1 : 0);
+    constexpr int kGroups = kNPer / 4;                                   // groups of 4 pixels per lane per batch
+    T* out = (T*)a.out + (long long)frame * C * a.HW;
+    float* normp = a.norm ? (float*)a.norm + (long long)frame * a.HW : nullptr;
+#pragma unroll 1
+    for (int b = 0; b < kNBatches; ++b) {
+        const unsigned base = (unsigned)chunk * kChunk + b * (32 * kNPer);
+        if (base >= a.HW) break;
+        float4 s[kGroups][4];
+#pragma unroll
+        for (int g = 0; g < kGroups; ++g) {                              // all L2 reads in flight first
+            const unsigned r = base + g * 128 + lane * 4;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                s[g][i] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (r < a.HW) s[g][i] = __ldcg((const float4*)acc + r + i);
+            }
+        }
+#pragma unroll
+        for (int g = 0; g < kGroups; ++g) {
+            const unsigned r = base + g * 128 + lane * 4;
+            if (r < a.HW) {
+                float scale[4], dn[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    __stcg((float4*)acc + r + i, make_float4(0.f, 0.f, 0.f, 0.f));   // accumulators leave the kernel all-zero
+                    scale[i] = 1.f; dn[i] = 1.f;
+                    if (MODE != DCB_MODE_SUM) {
+                        float d = C == 0 ? s[g][i].x : (C == 1 ? s[g][i].y : (C == 2 ? s[g][i].z : s[g][i].w));
+                        // softsplat.py:256-266
+                        if (a.eps == DCB_EPS_ADD) d = add_rn(d, 0.0000001f);
+                        else if (a.eps == DCB_EPS_ZERO) d = (d == 0.f) ? 1.f : d;
+                        else d = (d < 0.0000001f) ? 0.0000001f : d;
+                        scale[i] = __frcp_rn(d);
+                        dn[i] = d;
+                    }
+                }
+                if (MODE != DCB_MODE_SUM && normp) __stcs((float4*)(normp + r), make_float4(dn[0], dn[1], dn[2], dn[3]));
+                if (C > 0) st_stream4(out + r, MODE != DCB_MODE_SUM ? mul_rn(s[g][0].x, scale[0]) : s[g][0].x, MODE != DCB_MODE_SUM ? mul_rn(s[g][1].x, scale[1]) : s[g][1].x,
+                                      MODE != DCB_MODE_SUM ? mul_rn(s[g][2].x, scale[2]) : s[g][2].x, MODE != DCB_MODE_SUM ? mul_rn(s[g][3].x, scale[3]) : s[g][3].x);
+                if (C > 1) st_stream4(out + (size_t)a.HW + r, MODE != DCB_MODE_SUM ? mul_rn(s[g][0].y, scale[0]) : s[g][0].y, MODE != DCB_MODE_SUM ? mul_rn(s[g][1].y, scale[1]) : s[g][1].y,
+                                      MODE != DCB_MODE_SUM ? mul_rn(s[g][2].y, scale[2]) : s[g][2].y, MODE != DCB_MODE_SUM ? mul_rn(s[g][3].y, scale[3]) : s[g][3].y);
+                if (C > 2) st_stream4(out + 2 * (size_t)a.HW + r, MODE != DCB_MODE_SUM ? mul_rn(s[g][0].z, scale[0]) : s[g][0].z, MODE != DCB_MODE_SUM ? mul_rn(s[g][1].z, scale[1]) : s[g][1].z,
+                                      MODE != DCB_MODE_SUM ? mul_rn(s[g][2].z, scale[2]) : s[g][2].z, MODE != DCB_MODE_SUM ? mul_rn(s[g][3].z, scale[3]) : s[g][3].z);
+                if (C > 3) st_stream4(out + 3 * (size_t)a.HW + r, s[g][0].w, s[g][1].w, s[g][2].w, s[g][3].w);      // SUM mode only
+            }
+        }
+    }
+}
+
+// two consecutive pixels per lane: ONE 256-bit load fetches both accumulator cells (a full 32-byte sector per lane, the
+// same L2 sectors per warp as the scalar layout), one 256-bit store re-zeroes them, one 64-bit store per channel
+__device__ __forceinline__ void ld_cells2(const float* p, float4& a, float4& b) {
+    asm volatile("ld.global.cg.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w), "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w) : "l"(p));
+}
+__device__ __forceinline__ void zero_cells2(float* p) {
+    asm volatile("st.global.cg.v8.f32 [%0], {%1,%1,%1,%1,%1,%1,%1,%1};" :: "l"(p), "f"(0.f) : "memory");
+}
+__device__ __forceinline__ void st_stream2(float* p, float a, float b) { __stcs((float2*)p, make_float2(a, b)); }
+__device__ __forceinline__ void st_stream2(__nv_bfloat16* p, float a, float b) {
+    const __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
+    __stcs((unsigned*)p, *reinterpret_cast<const unsigned*>(&v));
+}
+__device__ __forceinline__ float comp(const float4& v, int i) { return i == 0 ? v.x : (i == 1 ? v.y : (i == 2 ? v.z : v.w)); }
+
+template <class T, int MODE, int CA>
+__device__ __forceinline__ void normalize_chunk_v2(const PipeArgs& a, int frame, int chunk, float* acc, int lane) {
+    constexpr int C = CA - (MODE != DCB_MODE_SUM ? 1 : 0);
+    constexpr int kGroups = kNPer / 2;                                   // groups of 2 pixels per lane per batch
+    T* out = (T*)a.out + (long long)frame * C * a.HW;
+    float* normp = a.norm ? (float*)a.norm + (long long)frame * a.HW : nullptr;
+#pragma unroll 1
+    for (int b = 0; b < kNBatches; ++b) {
+        const unsigned base = (unsigned)chunk * kChunk + b * (32 * kNPer);
+        if (base >= a.HW) break;
+        float4 s[kGroups][2];
+#pragma unroll
+        for (int g = 0; g < kGroups; ++g) {                              // all L2 reads in flight first
+            const unsigned r = base + g * 64 + lane * 2;
+            s[g][0] = s[g][1] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (r < a.HW) ld_cells2(acc + (size_t)r * 4, s[g][0], s[g][1]);
+        }
+#pragma unroll
+        for (int g = 0; g < kGroups; ++g) {
+            const unsigned r = base + g * 64 + lane * 2;
+            if (r < a.HW) {
+                zero_cells2(acc + (size_t)r * 4);                        // accumulators leave the kernel all-zero
+                float scale[2] = {1.f, 1.f}, dn[2] = {1.f, 1.f};
+                if (MODE != DCB_MODE_SUM) {
+#pragma unroll
+                    for (int i = 0; i < 2; ++i) {
+                        float d = comp(s[g][i], C);
+                        // softsplat.py:256-266
+                        if (a.eps == DCB_EPS_ADD) d = add_rn(d, 0.0000001f);
+                        else if (a.eps == DCB_EPS_ZERO) d = (d == 0.f) ? 1.f : d;
+                        else d = (d < 0.0000001f) ? 0.0000001f : d;
+                        scale[i] = __frcp_rn(d);
+                        dn[i] = d;
+                    }
+                    if (normp) __stcs((float2*)(normp + r), make_float2(dn[0], dn[1]));
+                }
+#pragma unroll
+                for (int c = 0; c < C; ++c) {
+                    const float v0 = comp(s[g][0], c), v1 = comp(s[g][1], c);
+                    st_stream2(out + (size_t)c * a.HW + r, MODE != DCB_MODE_SUM ? mul_rn(v0, scale[0]) : v0, MODE != DCB_MODE_SUM ? mul_rn(v1, scale[1]) : v1);
+                }
+            }
+        }
+    }
+}
+
 // ---------------------------------------------------------------------------------------------
 // occlusion epilogue (compute_mask, controlnet/control_utils.py:11-17): the accumulators hold the
 // soft splat of a 2-channel flow (x*e, y*e, e); mask = (||motion + splat/(norm + 1e-7)||_2 > 0.3)
@@ -296,24 +425,27 @@ __global__ void __launch_bounds__(kPipeThreads, kMinCtas) k_splat_step(const __g
     // the same accumulator ring). The launch latency of 65 dependent launches is thereby hidden.
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     asm volatile("griddepcontrol.wait;" ::: "memory");
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const unsigned n_items = (unsigned)a.n_frames * a.tn, s_items = (unsigned)a.s_frames * a.ts;
-    const unsigned n_ctas = (n_items + kWarpsPerCta - 1) / kWarpsPerCta;      // grid = n_ctas + s_ctas
-    const unsigned b = blockIdx.x;
-    const size_t slot_floats = (size_t)a.G * a.HW * 4;
-    if (b < n_ctas) {
-        const unsigned item = b * kWarpsPerCta + warp;
-        if (item >= n_items) return;
-        const int f = a.n_frame0 + item / a.tn, chunk = item % a.tn;
-        float* acc = a.acc + (size_t)((f / a.G) & 1) * slot_floats + (size_t)(f % a.G) * a.HW * 4;
-        if (a.epi == 1) mask_chunk<T>(a, f, chunk, acc, lane);
-        else normalize_chunk<T, MODE, CA>(a, f, chunk, acc, lane);
+    // 3-d grid, no integer division anywhere: z < n_frames -> normalise item (frame z of the group, chunk y * gridDim.x + x),
+    // else scatter item (frame z - n_frames of its group, strip column x, strip row y); the host passes both slot pointers
+    const int lane = threadIdx.x & 31;
+    const unsigned z = blockIdx.z;
+    const size_t frame_floats = (size_t)a.HW * 4;
+    if (z < (unsigned)a.n_frames) {
+        const unsigned chunk = blockIdx.y * gridDim.x + blockIdx.x;
+        if (chunk >= (unsigned)a.tn) return;
+        const int f = a.n_frame0 + (int)z;
+        float* acc = a.acc_n + z * frame_floats;
+        if (a.epi == 1) mask_chunk<T>(a, f, (int)chunk, acc, lane);
+#if DCB_NORM_V == 4
+        else if (a.vec4 && a.mask.p == nullptr) normalize_chunk_v4<T, MODE, CA>(a, f, (int)chunk, acc, lane);
+#elif DCB_NORM_V == 2
+        else if (a.vec4 && a.mask.p == nullptr) normalize_chunk_v2<T, MODE, CA>(a, f, (int)chunk, acc, lane);
+#endif
+        else normalize_chunk<T, MODE, CA>(a, f, (int)chunk, acc, lane);
     } else {
-        const unsigned s = (b - n_ctas) * kWarpsPerCta + warp;
-        if (s >= s_items) return;
-        const int f = a.s_frame0 + s / a.ts, strip = s % a.ts;
-        float* acc = a.acc + (size_t)((f / a.G) & 1) * slot_floats + (size_t)(f % a.G) * a.HW * 4;
-        scatter_strip<T, TF, MODE, CA>(a, f, strip, acc, lane);
+        const unsigned zs = z - (unsigned)a.n_frames;
+        if (blockIdx.x >= (unsigned)a.tiles_x || blockIdx.y >= (unsigned)a.tiles_y) return;
+        scatter_strip<T, TF, MODE, CA>(a, a.s_frame0 + (int)zs, (int)blockIdx.x, (int)blockIdx.y, a.acc_s + zs * frame_floats, lane);
     }
 }
 
@@ -323,17 +455,25 @@ __global__ void __launch_bounds__(kPipeThreads, kMinCtas) k_splat_step(const __g
 // dcb_set_option("pipe_group_bytes"): tests shrink the ring slots so that small tensors run through many groups
 long long g_pipe_group_bytes = 0;
 void pipe_set_group_bytes(long long b) { g_pipe_group_bytes = b > 0 ? b : 0; }
+// dcb_set_option("pipe_ring_slots"): 1 (default) = one accumulator slot, scatter and normalise of a frame group in
+// alternating launches; 2 = round 1's ring (step k normalises group k-1 while it scatters group k). Measured on 1080p
+// frames with `ncu --cache-control none` (profiles/r02/): two 33 MB slots do not stay in the 126 MB L2 next to the streaming
+// inputs / outputs (131-178 MB of DRAM traffic per 75 MB frame); ONE slot does (50.4 MB read by the scatter launch, 0.2 MB
+// read + the output written by the normalise launch: exactly the compulsory bytes), and it is as fast or faster.
+int g_pipe_ring_slots = 1;
+void pipe_set_ring_slots(long long n) { g_pipe_ring_slots = n == 1 ? 1 : 2; }
 
 static long long group_frames(long long N, long long H, long long W) {
     const long long gb = g_pipe_group_bytes > 0 ? g_pipe_group_bytes : kGroupBytes;
     long long g = gb / (H * W * 16 > 0 ? H * W * 16 : 1);
     if (g < 1) g = 1;
+    if (g > 32767) g = 32767;                    // gridDim.z = frames normalised + frames scattered <= 65535
     return g > N ? (N < 1 ? 1 : N) : g;
 }
 
 long long pipe_acc_bytes(long long N, long long H, long long W) {
     const long long G = group_frames(N, H, W);
-    const long long slots = N > G ? 2 : 1;
+    const long long slots = (N > G && g_pipe_ring_slots == 2) ? 2 : 1;
     return align_up(slots * G * H * W * 16, 256);
 }
 
@@ -341,16 +481,24 @@ long long pipe_workspace(long long N, long long H, long long W) { return pipe_ac
 
 template <class T, class TF, int MODE, int CA> static int launch_steps(PipeArgs& a, cudaStream_t st) {
     const int groups = (a.N + a.G - 1) / a.G;
-    for (int k = 0; k <= groups; ++k) {
-        a.s_frame0 = k * a.G;
-        a.s_frames = k < groups ? (a.N - a.s_frame0 < a.G ? a.N - a.s_frame0 : a.G) : 0;
-        a.n_frame0 = (k - 1) * a.G;
-        a.n_frames = k > 0 ? (a.N - a.n_frame0 < a.G ? a.N - a.n_frame0 : a.G) : 0;
-        const long long n_ctas = ((long long)a.n_frames * a.tn + kWarpsPerCta - 1) / kWarpsPerCta;
-        const long long s_ctas = ((long long)a.s_frames * a.ts + kWarpsPerCta - 1) / kWarpsPerCta;
-        const unsigned grid = (unsigned)(n_ctas + s_ctas);
+    const size_t slot_floats = (size_t)a.G * a.HW * 4;
+    // both item kinds cover 32 * kStripH pixels, so one (x, y) extent serves the normalise chunks and the scatter strips
+    const unsigned gx = (unsigned)a.tiles_x;
+    const unsigned rows_n = (unsigned)((a.tn + a.tiles_x - 1) / a.tiles_x);
+    const unsigned gy = rows_n > (unsigned)a.tiles_y ? rows_n : (unsigned)a.tiles_y;
+    const bool one_slot = g_pipe_ring_slots == 1;
+    for (int k = 0; k <= (one_slot ? 2 * groups - 1 : groups); ++k) {
+        // two slots: launch k = normalise(group k-1) + scatter(group k); one slot: launch 2g = scatter(g), launch 2g+1 = normalise(g)
+        const int gs = one_slot ? ((k & 1) ? -1 : k / 2) : (k < groups ? k : -1);
+        const int gn = one_slot ? ((k & 1) ? k / 2 : -1) : k - 1;
+        a.s_frame0 = gs >= 0 ? gs * a.G : 0;
+        a.s_frames = gs >= 0 ? (a.N - a.s_frame0 < a.G ? a.N - a.s_frame0 : a.G) : 0;
+        a.n_frame0 = gn >= 0 ? gn * a.G : 0;
+        a.n_frames = gn >= 0 ? (a.N - a.n_frame0 < a.G ? a.N - a.n_frame0 : a.G) : 0;
+        a.acc_s = a.acc + (one_slot ? 0 : (size_t)(gs & 1) * slot_floats);
+        a.acc_n = a.acc + (one_slot ? 0 : (size_t)(gn & 1) * slot_floats);
         cudaLaunchConfig_t cfg = {};
-        cfg.gridDim = dim3(grid); cfg.blockDim = dim3(kPipeThreads); cfg.dynamicSmemBytes = 0; cfg.stream = st;
+        cfg.gridDim = dim3(gx, gy, (unsigned)(a.n_frames + a.s_frames)); cfg.blockDim = dim3(kPipeThreads); cfg.dynamicSmemBytes = 0; cfg.stream = st;
         cudaLaunchAttribute attr[1];
         attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
         attr[0].val.programmaticStreamSerializationAllowed = 1;
@@ -407,11 +555,13 @@ int splat_pipe_impl(const DcbTensor* in, const DcbTensor* flow, const DcbTensor*
     a.eps = eps;
     a.G = (int)group_frames(a.N, a.H, a.W);
     a.tiles_x = (a.W + 31) / 32;
-    a.ts = a.tiles_x * ((a.H + kStripH - 1) / kStripH);
+    a.tiles_y = (a.H + kStripH - 1) / kStripH;
+    a.ts = a.tiles_x * a.tiles_y;
     a.tn = (int)((a.HW + kChunk - 1) / kChunk);
     a.out = out ? out->ptr : nullptr;
     a.norm = norm ? norm->ptr : nullptr;
     a.acc = (float*)ws;
+    a.vec4 = (a.HW % 4 == 0 && out && ((uintptr_t)out->ptr & 15) == 0 && (!norm || ((uintptr_t)norm->ptr & 15) == 0)) ? 1 : 0;
     if (!ws_clean) DCB_CHECK_CUDA(cudaMemsetAsync(ws, 0, (size_t)pipe_workspace(a.N, a.H, a.W), st));
     const bool ff = flow->dtype == DCB_F32;
     if (in->dtype == DCB_F32) return launch_pipe<float, float>(a, mode, st);

@@ -110,6 +110,8 @@ int32_t dcb_splat_fwd_workspace_is_scratch(int64_t N, int64_t C, int64_t H, int6
  *                       | 2 target-tile owner kernels wherever they apply
  *   "pipe_group_bytes"  accumulator bytes per ring slot of the accumulator pipelines (tests shrink it so that
  *                       small tensors run through many ring groups); 0 restores the default
+ *   "pipe_ring_slots"   1 (default) one accumulator slot, scatter and normalise of a frame group in alternating
+ *                       launches | 2 round 1's two-slot ring (normalise of group k-1 inside the launch that scatters group k)
  *   "owner_group_bytes" flow bytes per (pre-pass, owner) launch pair; 0 restores the default
  * Returns DCB_OK, or DCB_E_MODE for an unknown name. There is no equivalent in the reference (its kernels are
  * re-specialised per shape by string templating, controlnet/softsplat.py:27-216).

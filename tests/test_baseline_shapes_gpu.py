@@ -41,14 +41,16 @@ def orc():
     return oracle
 
 
-@pytest.fixture(params=["owner", "pipe"])
+@pytest.fixture(params=["owner", "pipe", "pipe-ring2"])
 def path(request, dcb):
     """Pin the forward kernel family; restore the library's own dispatch afterwards."""
     L = dcb._lib
     L.set_option("fwd_path", 2 if request.param == "owner" else 1)
+    L.set_option("pipe_ring_slots", 2 if request.param == "pipe-ring2" else 1)
     L.release_workspaces()
     yield request.param
     L.set_option("fwd_path", 0)
+    L.set_option("pipe_ring_slots", 1)
     L.set_option("pipe_group_bytes", 0)
     L.set_option("owner_group_bytes", 0)
     L.release_workspaces()

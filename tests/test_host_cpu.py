@@ -36,15 +36,18 @@ def test_workspace_queries_need_no_gpu():
     import diffcodec_b200
     L = diffcodec_b200._lib
     lib = L.lib()
-    # C+1 <= 4: one or two L2-sized slots of float4 accumulators (a slot = one 1080p frame)
+    # C+1 <= 4: ONE L2-sized slot of float4 accumulators (a slot = one 1080p frame); round 1's two-slot ring is an option
     assert lib.dcb_splat_fwd_workspace_bytes(1, 3, 1080, 1920, L.DCB_F32, L.MODE_SOFT, 0) == 1080 * 1920 * 16
+    assert lib.dcb_splat_fwd_workspace_bytes(64, 3, 1080, 1920, L.DCB_F32, L.MODE_SOFT, 0) == 1080 * 1920 * 16
+    L.set_option("pipe_ring_slots", 2)
     assert lib.dcb_splat_fwd_workspace_bytes(64, 3, 1080, 1920, L.DCB_F32, L.MODE_SOFT, 0) == 2 * 1080 * 1920 * 16
+    L.set_option("pipe_ring_slots", 1)
     assert lib.dcb_splat_workspace_bytes(1, 8, 64, 64, L.DCB_F32, L.MODE_SUM, 0) == 2 * 64 * 64 * 16   # two channel quads
     assert lib.dcb_splat_fwd_workspace_is_scratch(1, 3, 1080, 1920, L.DCB_F32, L.MODE_SOFT, 0) == 0
     assert lib.dcb_splat_fwd_workspace_is_scratch(1, 3, 1080, 1920, L.DCB_F32, L.MODE_SOFT, L.FLAG_DETERMINISTIC) == 1
     L.set_option("pipe_group_bytes", 1 << 20)          # tests shrink the ring slots: many groups on small tensors
     try:
-        assert lib.dcb_splat_fwd_workspace_bytes(64, 3, 256, 256, L.DCB_F32, L.MODE_SOFT, 0) == 2 * 256 * 256 * 16
+        assert lib.dcb_splat_fwd_workspace_bytes(64, 3, 256, 256, L.DCB_F32, L.MODE_SOFT, 0) == 256 * 256 * 16
     finally:
         L.set_option("pipe_group_bytes", 0)
     L.set_option("fwd_path", 2)      # opt-in target-tile owner kernels (C + 1 <= 4): the workspace only holds the landing boxes

@@ -398,7 +398,8 @@ def test_bf16_forward_wild_flows(dcb, orc):
 
 
 def test_multi_frame_pipeline_many_frames(dcb, orc):
-    """More frames than ring slots: every stage of the persistent pipeline (S0|S1|N0,S2|...) is exercised."""
+    """Seven small frames, forward + all gradients, three times on the self-cleaning workspace. (At this size all
+    seven frames form ONE frame group; the many-group schedules are driven by tests/test_baseline_shapes_gpu.py.)"""
     tin, flow, metric, gout = make_inputs(31, 7, 3, 70, 150, flow_scale=3.0)
     ref = oracle_run(orc, tin, flow, metric, gout, "soft")
     truth = oracle_run(orc, tin.double(), flow.double(), metric.double(), gout.double(), "soft")

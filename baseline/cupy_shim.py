@@ -80,8 +80,8 @@ class _Function:
                 values.append(int(a)); types_.append(ctypes.c_int)
             elif isinstance(a, np.float32):
                 values.append(float(a)); types_.append(ctypes.c_float)
-            else:                            # tensor.data_ptr()
-                values.append(int(a)); types_.append(ctypes.c_void_p)
+            else:                            # tensor.data_ptr(); None is a null pointer (softsplat.py:433, :523)
+                values.append(0 if a is None else int(a)); types_.append(ctypes.c_void_p)
         ptr = getattr(stream, "ptr", 0) if stream is not None else 0
         grid = tuple(grid) + (1,) * (3 - len(grid)); block = tuple(block) + (1,) * (3 - len(block))
         _check(drv.cuLaunchKernel(self._fn, grid[0], grid[1], grid[2], block[0], block[1], block[2], shared_mem,

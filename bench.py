@@ -99,6 +99,13 @@ WORKLOAD = ("soft (softmax) forward splat, fp32, {F}x3x1080x1920 frames per GPU 
             "(bicubic-upsampled noise, mean |dflow/dx| 0.28 px/px: rougher than real optical flow; extra.headline_on_smooth_flow has 0.03)")
 
 
+def _config(frames):
+    """The SAME dict in both arms (the driver compares them)."""
+    return {"workload": WORKLOAD.format(F=frames), "frames_per_gpu": frames,
+            "l2_policy": f"inputs+outputs per step = {(36 * frames * H * W) >> 20} MiB per GPU, larger than the 126 MB L2; no flush needed",
+            "partition": "frames sharded by rank, no data-path collective"}
+
+
 _cpu_inputs = {}
 
 
@@ -148,9 +155,9 @@ def run_reference(args):
         "unit": "Mpixel/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": round(dt / max(args.steps, 1) * 1e3, 2), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD.format(F=args.frames), "frames_per_gpu": args.frames,
-                   "sample": f"each step = {frames} of the workload's frames on rank 0's host cores"},
-        "cpu_baseline": {"value": round(v, 2), "unit": "Mpixel/s", "cores": threads, "kind": "port", "sample": sample},
+        "config": _config(args.frames),
+        "cpu_baseline": {"value": round(v, 2), "unit": "Mpixel/s", "cores": threads, "kind": "port",
+                         "sample": sample + f"; each step = {frames} of the workload's frames on rank 0's host cores"},
         "e2e": {"value": round(v, 2), "unit": "Mpixel/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "note": "the reference has no CPU path and CuPy is absent: this is the committed CPU port of its kernel (oracle/)",
     }))
@@ -306,31 +313,125 @@ def _extras(torch, d, dev, gen, peak):
     return ex
 
 
+def _reference_gpu(torch, d, dev, gen):
+    """B-ref-gpu: the reference's OWN, unmodified controlnet/softsplat.py on this GPU -- its eager
+    pre/post ops and its three kernel strings, NVRTC-compiled for the device through baseline/cupy_shim.py -- timed next
+    to this library on the same tensors: C1 (avg, one 1080p frame), the headline op (soft forward, 16 frames per call)
+    and C4 (soft forward + backward, all three gradients, 8 x 64 x 256 x 256)."""
+    base = os.path.join(ROOT, "baseline")
+    if base not in sys.path:
+        sys.path.insert(0, base)
+    import ref_gpu
+    why = ref_gpu.available()
+    if why:
+        return {"unavailable": why}
+    ref = ref_gpu.load()
+    res = {"what": "unmodified reference controlnet/softsplat.py, kernels NVRTC-compiled for this GPU (baseline/cupy_shim.py over cuda-python)"}
+
+    def both(tag, px, mk, iters, warm):
+        row = {}
+        for name, fn in (("reference", ref.softsplat), ("ours", d.softsplat)):
+            ms = _time_cuda(torch, mk(fn), iters, warm)
+            row[name + "_us"] = round(ms * 1e3, 1); row[name + "_mpixel_s"] = round(px / ms / 1e3, 1)
+        row["speedup"] = round(row["reference_us"] / row["ours_us"], 2)
+        res[tag] = row
+
+    t1 = torch.rand(1, 3, H, W, device=dev, generator=gen); f1 = _smooth_flow(torch, 1, H, W, 8.0, dev, gen)
+    both("C1_avg_fwd_1x3x1080x1920_f32", H * W, lambda fn: (lambda: fn(tenIn=t1, tenFlow=f1, tenMetric=None, strMode="avg")), 30, 5)
+    n = 16
+    tn = torch.rand(n, 3, H, W, device=dev, generator=gen); mn = -torch.rand(n, 1, H, W, device=dev, generator=gen)
+    fn_ = _smooth_flow(torch, n, H, W, 8.0, dev, gen)
+    both("headline_soft_fwd_16x3x1080x1920_f32", n * H * W, lambda fn: (lambda: fn(tenIn=tn, tenFlow=fn_, tenMetric=mn, strMode="soft")), 10, 3)
+    # agreement on the headline tensors (atomic order differs: 1e-5 relative is the north star's bound)
+    a, b = ref.softsplat(tenIn=tn[:2], tenFlow=fn_[:2], tenMetric=mn[:2], strMode="soft"), d.softsplat(tn[:2], fn_[:2], mn[:2], "soft")
+    res["headline_max_abs_diff_over_max_ref"] = float((a - b).abs().max() / a.abs().max())
+    del tn, mn, fn_, a, b
+    ti = torch.randn(8, 64, 256, 256, device=dev, generator=gen).requires_grad_(True)
+    me = (torch.randn(8, 1, 256, 256, device=dev, generator=gen) * 0.5).requires_grad_(True)
+    fl = _smooth_flow(torch, 8, 256, 256, 4.0, dev, gen).requires_grad_(True)
+    go = torch.randn(8, 64, 256, 256, device=dev, generator=gen)
+
+    def mk4(fn):
+        def run():
+            ti.grad = me.grad = fl.grad = None
+            fn(tenIn=ti, tenFlow=fl, tenMetric=me, strMode="soft").backward(go)
+        return run
+    both("C4_soft_fwd_bwd_8x64x256x256_f32", 8 * 256 * 256, mk4, 10, 3)
+    return res
+
+
 def _uvg_sweep(torch, d, dev, rank, world, peak, gops_per_chunk=16):
-    """C5: the UVG-shaped synthetic 1080p sweep (7 sequences, 3900 frames, 975 GOP-4 units, 2925 inter
-    frames), GOPs sharded round-robin over the ranks, the conditioning recipe (a-7) per inter frame.
-    Inputs are generated on the device per chunk from the GOP seed (untimed); only the recipe is timed."""
+    """C5: the UVG-shaped synthetic 1080p sweep (7 sequences, 3900 frames, 975 GOP-4 units, 2925 inter frames), GOPs
+    sharded round-robin over the ranks (STRONG scaling: the sweep is fixed, ranks split it), the conditioning recipe (a-7)
+    per inter frame. Every GOP's inputs come from that GOP's own seed, so the per-GOP checksums do not depend on the
+    number of ranks. Inputs are generated on the device per chunk (untimed); the recipe is timed with CUDA events; the
+    per-GOP checksum table is all-gathered over NCCL afterwards (timed separately)."""
+    import torch.distributed as dist
     units = d.shard_units(d.enumerate_gops(), rank, world)
     ev_a, ev_b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    total_ms, frames, digest = 0.0, 0, 0.0
+    total_ms, frames, table = 0.0, 0, []
+    nmax = gops_per_chunk * 3
+    img = torch.empty(nmax, 3, H, W, device=dev); gt = torch.empty(nmax, 3, H, W, device=dev)
+    low1 = torch.empty(nmax, 2, H // 32, W // 32, device=dev); low2 = torch.empty_like(low1)
     for i in range(0, len(units), gops_per_chunk):
         chunk = units[i:i + gops_per_chunk]
         n = sum(u.inter_frames for u in chunk)
-        gen = torch.Generator(device=dev).manual_seed(chunk[0].seed())
-        img = torch.rand(n, 3, H, W, device=dev, generator=gen); gt = torch.rand(n, 3, H, W, device=dev, generator=gen)
-        f1 = _smooth_flow(torch, n, H, W, 8.0, dev, gen); f2 = -f1 + 0.5 * _smooth_flow(torch, n, H, W, 1.0, dev, gen)
+        at = 0
+        for u in chunk:                                               # per-GOP seeds: independent of chunking and sharding
+            gen = torch.Generator(device=dev).manual_seed(u.seed())
+            k = u.inter_frames
+            img[at:at + k].uniform_(generator=gen); gt[at:at + k].uniform_(generator=gen)
+            low1[at:at + k].normal_(generator=gen); low2[at:at + k].normal_(generator=gen)
+            at += k
+        f1 = torch.nn.functional.interpolate(low1[:n], size=(H, W), mode="bicubic", align_corners=False) * 8.0
+        f2 = -f1 + 0.5 * torch.nn.functional.interpolate(low2[:n], size=(H, W), mode="bicubic", align_corners=False)
         if i == 0:
-            d.residual_conditioning(img, f1, f2, gt, "dataset")          # warm-up, untimed
+            d.residual_conditioning(img[:n], f1, f2, gt[:n], "dataset")          # warm-up, untimed
         torch.cuda.synchronize()
         ev_a.record()
-        fused, res = d.residual_conditioning(img, f1, f2, gt, "dataset")
+        fused, res = d.residual_conditioning(img[:n], f1, f2, gt[:n], "dataset")
         ev_b.record(); torch.cuda.synchronize()
         total_ms += ev_a.elapsed_time(ev_b); frames += n
-        digest += float(res[:, :, ::64, ::64].double().sum())
-        del img, gt, f1, f2, fused, res
-    return {"gops": len(units), "inter_frames": frames, "ms": round(total_ms, 2), "frames_per_s": round(frames / total_ms * 1e3, 1),
-            "mpixel_s": round(frames * H * W / total_ms / 1e3, 1), "alg_gbs": round(64 * frames * H * W / total_ms / 1e6, 1),
-            "frac_of_peak": round(64 * frames * H * W / total_ms / 1e6 / peak, 3), "digest": round(digest, 3)}
+        per = res.view(len(chunk), -1)
+        table.append(torch.stack([per.sum(dim=1, dtype=torch.float64), (per * per).sum(dim=1, dtype=torch.float64),
+                                  torch.full((len(chunk),), float(per.shape[1]), dtype=torch.float64, device=dev)], dim=1))
+        del f1, f2, fused, res, per
+    local = torch.cat(table) if table else torch.zeros((0, 3), dtype=torch.float64, device=dev)
+    t = torch.tensor([total_ms], device=dev, dtype=torch.float64)
+    torch.cuda.synchronize()
+    g0 = time.perf_counter()
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    allsums = d.gather_checksums(local)                                # [world, kmax, 3] over NCCL (after the sweep, off the timed path)
+    torch.cuda.synchronize()
+    gather_ms = (time.perf_counter() - g0) * 1e3
+    ms = float(t.item())
+    all_frames = 2925
+    digest = float(allsums[:, :, 0].sum().item())
+    # deterministic mode on the first 8 GOPs of the sweep: an exact integer hash of the residual bits, independent of how many
+    # ranks shared the work (SURVEY.md App. C-15)
+    hashes = torch.zeros(8, dtype=torch.int64, device=dev)
+    with d.deterministic(True):
+        for gi, u in enumerate(d.enumerate_gops()[:8]):
+            if gi % world != rank:
+                continue
+            gen = torch.Generator(device=dev).manual_seed(u.seed())
+            k = u.inter_frames
+            img[:k].uniform_(generator=gen); gt[:k].uniform_(generator=gen); low1[:k].normal_(generator=gen); low2[:k].normal_(generator=gen)
+            f1 = torch.nn.functional.interpolate(low1[:k], size=(H, W), mode="bicubic", align_corners=False) * 8.0
+            f2 = -f1 + 0.5 * torch.nn.functional.interpolate(low2[:k], size=(H, W), mode="bicubic", align_corners=False)
+            _, res = d.residual_conditioning(img[:k], f1, f2, gt[:k], "dataset")
+            hashes[gi] = res.contiguous().view(torch.int32).to(torch.int64).sum()
+    if world > 1:
+        dist.all_reduce(hashes, op=dist.ReduceOp.SUM)                  # exact (integers); every GOP is owned by one rank
+    det_hash = int(hashes.sum().item()) & ((1 << 62) - 1)
+    return {"gops": 975, "gops_this_rank": len(units), "inter_frames": all_frames, "ms": round(ms, 2), "scaling": "strong",
+            "frames_per_s": round(all_frames / ms * 1e3, 1), "mpixel_s": round(all_frames * H * W / ms / 1e3, 1),
+            "alg_gbs_per_gpu": round(64 * all_frames * H * W / ms / 1e6 / world, 1),
+            "frac_of_peak": round(64 * all_frames * H * W / ms / 1e6 / world / peak, 3),
+            "digest": float(f"{digest:.9g}"), "checksum_gather": {"backend": "nccl" if world > 1 else "none", "ms": round(gather_ms, 2),
+                                                                   "table": list(allsums.shape)},
+            "deterministic_hash_first_8_gops": det_hash}
 
 
 def run_ours(args):
@@ -347,6 +448,11 @@ def run_ours(args):
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
     import diffcodec_b200 as d
+    numa = d.bind_to_gpu_numa(dev)              # before any pinned allocation: host buffers land next to this GPU's PCIe root
+
+    sampler = ClockSampler(local)               # clocks / throttle reasons from before the warm-up to the end of the timed regions
+    if rank == 0:
+        sampler.start()
 
     F = args.frames
     gen = torch.Generator(device=dev).manual_seed(1234 + rank)
@@ -363,12 +469,15 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    def max_over_ranks(ms):
+        t = torch.tensor([ms], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
     for _ in range(max(args.warmup, 3)):
         out = step()
     barrier()
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
     launches0 = d.launch_count()
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
@@ -378,52 +487,92 @@ def run_ours(args):
     b.record()
     barrier()
     launches = d.launch_count() - launches0
-    ms_total = a.elapsed_time(b)
-    clocks = sampler.stop() if rank == 0 else None
-    t = torch.tensor([ms_total], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_step = float(t.item()) / args.steps
+    ms_step = max_over_ranks(a.elapsed_time(b)) / args.steps
     value = world * px_per_step / ms_step / 1e3                            # Mpixel/s, whole job
+    out0 = out[:1].clone()                                                 # for the output check below
+
+    # ---- forward + backward (the other half of BASELINE's metric): all three gradients, 16 frames per GPU per step ----
+    nb = min(F, 16)
+    ti = tin[:nb].clone().requires_grad_(True); me = metric[:nb].clone().requires_grad_(True); fl = flow[:nb].clone().requires_grad_(True)
+    go = torch.randn(nb, C, H, W, device=dev, generator=gen)
+
+    def fb():
+        ti.grad = me.grad = fl.grad = None
+        d.softsplat(ti, fl, me, "soft").backward(go)
+    for _ in range(3):
+        fb()
+    barrier()
+    a.record()
+    for _ in range(5):
+        fb()
+    b.record()
+    barrier()
+    ms_fb = max_over_ranks(a.elapsed_time(b)) / 5
+    del ti, me, fl, go
 
     # ---- e2e: public API from pinned host buffers, H2D + op + D2H inside the timed region ----
     Fe = min(F, args.e2e_frames)
     h_in = torch.rand(Fe, C, H, W).pin_memory(); h_me = (-torch.rand(Fe, 1, H, W)).pin_memory()
     h_fl = flow[:Fe].cpu().pin_memory(); h_out = torch.empty(Fe, C, H, W).pin_memory()
-    def e2e_step():
-        # public host-buffer API: chunked H2D / kernels / D2H over three streams, result back in h_out
-        d.softsplat_host(h_in, h_fl, h_me, "soft", out=h_out, device=dev, chunk_frames=8)
-    for _ in range(2):
-        e2e_step()
-    barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(args.e2e_steps):
-        e2e_step()
-    e1.record()
-    barrier()
-    te = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(te, op=dist.ReduceOp.MAX)
-    e2e_value = world * Fe * H * W / (float(te.item()) / args.e2e_steps) / 1e3
+    # the same frames as a video pipeline holds them: 8-bit pixels, half-precision flow / metric, bf16 result (the latent dtype)
+    c_in = (h_in * 255).round().to(torch.uint8).pin_memory(); c_me = h_me.half().pin_memory(); c_fl = h_fl.half().pin_memory()
+    c_out = torch.empty(Fe, C, H, W, dtype=torch.bfloat16).pin_memory()
 
+    def time_e2e(fn):
+        for _ in range(2):
+            fn()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(args.e2e_steps):
+            fn()
+        e1.record()
+        barrier()
+        return world * Fe * H * W / (max_over_ranks(e0.elapsed_time(e1)) / args.e2e_steps) / 1e3
+    e2e_fp32 = time_e2e(lambda: d.softsplat_host(h_in, h_fl, h_me, "soft", out=h_out, device=dev, chunk_frames=8))
+    e2e_compact = time_e2e(lambda: d.softsplat_host(c_in, c_fl, c_me, "soft", out=c_out, device=dev, chunk_frames=8))
+    # 8-bit / fp16 / bf16 rounding only; a mean, because at hole borders a 0.01 px shift of an fp16 flow flips single pixels between "empty" and "covered"
+    e2e_check = float((c_out[:2].float() - h_out[:2]).abs().mean() / h_out[:2].abs().mean())
+    del h_in, h_me, h_fl, h_out, c_in, c_me, c_fl, c_out
+
+    # ---- C5: the UVG-shaped sweep sharded by GOP over the ranks (strong scaling) + NCCL gather of the checksums ----
     peak, peak_src = _peaks()
+    c5 = None
+    if not args.no_c5:
+        del tin, metric, flow, out
+        torch.cuda.empty_cache()
+        try:
+            c5 = _uvg_sweep(torch, d, dev, rank, world, peak)
+        except Exception as e:
+            c5 = {"error": repr(e)}
+    clocks = sampler.stop() if rank == 0 else None
+
     if rank == 0:
         achieved = ALG_BYTES_PER_PX * px_per_step / ms_step / 1e6          # GB/s per GPU (weak scaling: per-rank time)
+        fb_gbs = 112 * nb * H * W / ms_fb / 1e6
         line = {
             "metric": "softsplat soft-mode forward throughput, 1080p fp32 frames", "value": round(value, 1), "unit": "Mpixel/s",
             "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": round(ms_step, 4),
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD.format(F=F),
-                       "frames_per_gpu": F, "l2_policy": f"inputs+outputs per step = {(36 * px_per_step) >> 20} MiB per GPU, larger than the 126 MB L2; no flush needed",
-                       "partition": "frames sharded by rank, no data-path collective"},
+            "config": _config(F),
             "roofline": {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),
-                         "traffic": 132.06e6, "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of one k_splat_step launch, ncu --set full --cache-control none, profiles/r01/ncu_step_final.txt (compulsory: 74.6e6)",
-                         "kernel": "k_splat_step (one launch per frame: scatter of frame k + normalise of frame k-1)",
+                         "traffic": 65.5e6, "traffic_kind": "recorded, not measured in this run",
+                         "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of the two k_splat_step launches of one frame (scatter 50.4 + 2.1 MB, normalise 0.2 + 12.8 MB; the rest of the 24.9 MB of output drains after the kernel), ncu --cache-control none, profiles/r02/ncu_step_slots.txt; algorithmic 74.65e6",
+                         "kernel": "k_splat_step (two launches per 1080p frame: scatter into one L2-resident accumulator slot, then normalise)",
                          "algorithmic_bytes_per_px": ALG_BYTES_PER_PX, "peak_source": peak_src, "frac_of_nominal_8TBs": round(achieved / 8000.0, 4)},
-            "e2e": {"value": round(e2e_value, 1), "unit": "Mpixel/s", "h2d_bytes_per_step": Fe * (C + 3) * H * W * 4,
-                    "d2h_bytes_per_step": Fe * C * H * W * 4, "frames_per_step": Fe, "api": "diffcodec_b200.softsplat_host(tenIn, tenFlow, tenMetric, 'soft', out=pinned) -- pinned host tensors in and out, copies inside the timed region"},
-            "gpu_launches": int(launches), "clocks": clocks,
+            "fwd_bwd": {"metric": "softsplat soft-mode forward + backward (gradIn, gradFlow, gradMetric), 1080p fp32 frames",
+                        "value": round(world * nb * H * W / ms_fb / 1e3, 1), "unit": "Mpixel/s", "ms_per_step": round(ms_fb, 3), "frames_per_gpu": nb,
+                        "algorithmic_bytes_per_px": 112, "achieved_gbs_per_gpu": round(fb_gbs, 1), "frac": round(fb_gbs / peak, 4)},
+            "e2e": {"value": round(e2e_compact, 1), "unit": "Mpixel/s", "h2d_bytes_per_step": Fe * (C + 2 * 3) * H * W,
+                    "d2h_bytes_per_step": Fe * C * H * W * 2, "frames_per_step": Fe,
+                    "api": "diffcodec_b200.softsplat_host(frames uint8, flow fp16, metric fp16, 'soft', out=pinned bf16): pinned host tensors in and out, "
+                           "copies and the on-device widening to fp32 inside the timed region, synchronous return",
+                    "element_types": "uint8 frames (decoded video), fp16 flow and metric, bf16 result (the latent dtype); the splat runs in fp32",
+                    "mean_abs_diff_vs_fp32_path_over_mean_abs": round(e2e_check, 5),
+                    "fp32_host_tensors": {"value": round(e2e_fp32, 1), "unit": "Mpixel/s", "h2d_bytes_per_step": Fe * (C + 3) * H * W * 4,
+                                          "d2h_bytes_per_step": Fe * C * H * W * 4}},
+            "gpu_launches": int(launches), "clocks": clocks, "numa": numa,
+            "c5_uvg_sweep": c5,
         }
         if world == 1 and not args.no_cpu:
             from oracle import oracle as orc
@@ -433,16 +582,25 @@ def run_ours(args):
             line["cpu_baseline"] = {"value": round(v, 2), "unit": "Mpixel/s", "cores": threads, "kind": "port",
                                     "sample": f"{nsample} of the step's {F} 1080p frames, soft fwd fp32, best of 2 runs of {secs:.1f} s = "
                                               f"{secs * threads:.0f} core-seconds (oracle C kernel over {threads} pthreads + torch CPU pre/post ops)"}
+            # the oracle as CHECKER of what was timed: frame 0 of the timed step's inputs, CPU port vs the GPU result
+            try:
+                g0 = torch.Generator(device=dev).manual_seed(1234 + rank)
+                t0 = torch.rand(F, C, H, W, device=dev, generator=g0)[:1].cpu(); m0 = (-torch.rand(F, 1, H, W, device=dev, generator=g0))[:1].cpu()
+                f0 = _smooth_flow(torch, F, H, W, 8.0, dev, g0)[:1].cpu()
+                ref0 = orc.softsplat(t0, f0, m0, "soft")
+                line["output_check"] = {"what": "frame 0 of the timed step vs the CPU oracle", "max_abs_diff_over_max": float((out0.cpu() - ref0).abs().max() / ref0.abs().max()),
+                                        "tolerance": 1e-5}
+            except Exception as e:
+                line["output_check"] = {"error": repr(e)}
         else:
             line["cpu_baseline"] = None
         if world == 1 and not args.no_extra:
-            del tin, metric, flow, out
             torch.cuda.empty_cache()
             line["extra"] = _extras(torch, d, dev, gen, peak)
             try:
-                line["extra"]["C5_uvg_sweep_recipe_2925x1080p_f32"] = _uvg_sweep(torch, d, dev, 0, 1, peak)
+                line["extra"]["reference_gpu"] = _reference_gpu(torch, d, dev, gen)
             except Exception as e:
-                line["extra"]["C5_uvg_sweep_recipe_2925x1080p_f32"] = {"error": repr(e)}
+                line["extra"]["reference_gpu"] = {"error": repr(e)}
         print(json.dumps(line))
     if world > 1:
         dist.barrier()
@@ -460,6 +618,7 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-extra", action="store_true")
+    ap.add_argument("--no-c5", action="store_true", help="skip the UVG-shaped sweep (C5)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -16,7 +16,7 @@ from .warp import WarpingLayerBWFlow, backwarp, backwarp_residual
 from .extractors import bidir_fuse, bidirectional_warp_fuse
 from .residual_utils import residual_conditioning, ResidueDataset, WarpingDatasetWrapper
 from .sharding import UVG_SEQUENCES, GopUnit, enumerate_gops, shard_units, gather_checksums, gather_outputs, checksum
-from .host import softsplat_host
+from .host import softsplat_host, bind_to_gpu_numa
 from .patch_utils import merge_latent_tiles_from_pixel_coords, crop_into_tiles
 from . import flow_io
 from .dropin import install

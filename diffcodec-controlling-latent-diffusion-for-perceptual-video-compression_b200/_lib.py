@@ -18,6 +18,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("DCB_LIB_PATH") or os.path.join(_HERE, "libdiffcodec_b200.so")   # override: A/B builds only
 
 DCB_F32, DCB_BF16, DCB_F64 = 0, 1, 2
+DCB_U8, DCB_F16 = 3, 4          # storage types of dcb_convert only
 MODE_SUM, MODE_AVG, MODE_LINEAR, MODE_SOFT = 0, 1, 2, 3
 EPS_ADD, EPS_ZERO, EPS_CLIP = 0, 1, 2
 FLAG_DETERMINISTIC, FLAG_WS_CLEAN = 1, 2
@@ -73,6 +74,7 @@ SYMBOLS = {
     "dcb_tile_merge_workspace_bytes": (ctypes.c_int64, [ctypes.c_int64] * 3 + [ctypes.c_int32]),
     "dcb_tile_merge": (ctypes.c_int, [_P, ctypes.c_void_p, ctypes.c_int32, _P, ctypes.c_int64, ctypes.c_int64, ctypes.c_double,
                                       ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p]),
+    "dcb_convert": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int32, ctypes.c_void_p, ctypes.c_int32, ctypes.c_int64, ctypes.c_float, ctypes.c_void_p]),
     "dcb_residual_fused": (ctypes.c_int, [_P] * 8 + [ctypes.c_void_p, ctypes.c_int64, ctypes.c_int32, ctypes.c_int32, ctypes.c_void_p]),
 }
 
@@ -130,6 +132,18 @@ def fwd_is_scratch(n, c, h, w, dt, mode, flags=0) -> bool:
     if v is None:
         v = _scratch_cache[key] = bool(lib().dcb_splat_fwd_workspace_is_scratch(n, c, h, w, dt, mode, flags))
     return v
+
+
+_CONVERT_DTYPES = {torch.uint8: DCB_U8, torch.float16: DCB_F16, torch.bfloat16: DCB_BF16, torch.float32: DCB_F32}
+
+
+def convert(src: torch.Tensor, dst: torch.Tensor, scale: float = 1.0) -> torch.Tensor:
+    """dst = scale * src with a change of element type, on the device, in the native library (dcb_convert)."""
+    assert src.is_cuda and dst.is_cuda and src.is_contiguous() and dst.is_contiguous() and src.numel() == dst.numel()
+    with on_device(src.device):
+        check(lib().dcb_convert(src.data_ptr(), _CONVERT_DTYPES[src.dtype], dst.data_ptr(), _CONVERT_DTYPES[dst.dtype],
+                                src.numel(), float(scale), stream_ptr(src.device)), "dcb_convert")
+    return dst
 
 
 class DcbError(RuntimeError):

@@ -56,6 +56,7 @@ int bidir_fuse_bwd_impl(const DcbTensor*, const DcbTensor*, const DcbTensor*, co
                         const DcbTensor*, const DcbTensor*, const DcbTensor*, const DcbTensor*, const DcbTensor*,
                         const DcbTensor*, cudaStream_t);
 
+int convert_impl(const void* src, int src_dtype, void* dst, int dst_dtype, long long n, float scale, cudaStream_t st);
 extern int g_fwd_path;
 bool use_owner(int dtype, int mode, long long C, long long H, long long W);
 void owner_set_group_bytes(long long b);
@@ -137,7 +138,7 @@ const char* dcb_build_info(void) {
     return "libdiffcodec_b200 " __DATE__ " nvcc " DCB_STR(__CUDACC_VER_MAJOR__) "." DCB_STR(__CUDACC_VER_MINOR__)
            " target sm_100a; kernels: k_splat_step k_planar_step k_list_count k_list_alloc k_list_fill k_list_gather k_scatter_planar k_normalize k_bwd_target k_bwd_source "
            "k_backwarp_rows k_backwarp_fwd k_backwarp_bwd k_cast_f32_bf16 k_recipe_fuse k_bidir_fuse_fwd k_bidir_fuse_bwd "
-           "k_det_emit k_det_reduce k_tile_merge";
+           "k_det_emit k_det_reduce k_tile_merge k_splat_owner k_strip_box k_convert";
 }
 
 int64_t dcb_splat_fwd_workspace_bytes(int64_t N, int64_t C, int64_t H, int64_t W, int32_t dtype, int32_t mode, int32_t flags) {
@@ -438,6 +439,15 @@ int dcb_tile_merge(const DcbTensor* tiles, const int64_t* pixel_coords, int32_t 
     }
     static_assert(sizeof(long long) == sizeof(int64_t), "int64_t coordinates");
     return tile_merge_impl(tiles, (const long long*)pixel_coords, n_tiles, out, H_px, W_px, eps, ws, ws_bytes, (cudaStream_t)stream);
+}
+
+int dcb_convert(const void* src, int32_t src_dtype, void* dst, int32_t dst_dtype, int64_t n, float scale, void* stream) {
+    const char* fn = "dcb_convert";
+    if (n < 0) return set_error(DCB_E_SHAPE, "%s: n = %lld", fn, (long long)n);
+    if (n > 0 && (!src || !dst)) return set_error(DCB_E_NULL, "%s: src and dst are required", fn);
+    const int ss = src_dtype == DCB_U8 ? 1 : (src_dtype == DCB_F32 ? 4 : 2), ds = dst_dtype == DCB_F32 ? 4 : 2;
+    if ((uintptr_t)src % (uintptr_t)ss || (uintptr_t)dst % (uintptr_t)ds) return set_error(DCB_E_ALIGN, "%s: pointer not aligned to its element size", fn);
+    return convert_impl(src, src_dtype, dst, dst_dtype, n, scale, (cudaStream_t)stream);
 }
 
 }  // extern "C"

@@ -34,7 +34,8 @@ extern "C" {
 #define DCB_VERSION 100 /* 0.1.0 */
 
 /* element types */
-enum { DCB_F32 = 0, DCB_BF16 = 1, DCB_F64 = 2 };
+enum { DCB_F32 = 0, DCB_BF16 = 1, DCB_F64 = 2,
+       DCB_U8 = 3, DCB_F16 = 4 /* storage types of dcb_convert only (host-buffer path); the splat kernels take the first three */ };
 
 /* splat modes: controlnet/softsplat.py:232-274 (strMode.split('-')[0]) */
 enum { DCB_MODE_SUM = 0, DCB_MODE_AVG = 1, DCB_MODE_LINEAR = 2, DCB_MODE_SOFT = 3 };
@@ -235,6 +236,15 @@ int dcb_bidir_fuse_bwd(const DcbTensor* grad_fused, const DcbTensor* A, const Dc
 int64_t dcb_tile_merge_workspace_bytes(int64_t C, int64_t H, int64_t W, int32_t n_tiles);
 int dcb_tile_merge(const DcbTensor* tiles, const int64_t* pixel_coords, int32_t n_tiles, const DcbTensor* out,
                    int64_t H_px, int64_t W_px, double eps, void* workspace, int64_t workspace_bytes, void* stream);
+
+/*
+ * Element-type conversion on the device: dst[i] = (dst type)(scale * (float)src[i]) over n contiguous elements.
+ * src: DCB_U8 | DCB_F16 | DCB_BF16 | DCB_F32; dst: DCB_F32 | DCB_BF16 | DCB_F16. The host-buffer entry point uploads
+ * 8-bit frames and half-precision flows / metrics (9 instead of 24 bytes per pixel over PCIe) and downloads a bf16
+ * result; the splat itself runs in fp32. Replaces the host-side `.astype(np.float32) / 255.0` of the reference's
+ * dataset code (controlnet/dataset.py:224-230 feeds float arrays prepared on the CPU).
+ */
+int dcb_convert(const void* src, int32_t src_dtype, void* dst, int32_t dst_dtype, int64_t n, float scale, void* stream);
 
 #ifdef __cplusplus
 }

@@ -67,6 +67,37 @@ def test_mode_wrapper_matches_reference(path, mode):
         assert np.array_equal(v, z[f"{mode}/{k}"], equal_nan=True), (mode, k)
 
 
+GPU_FIXTURES = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "ref_gpu_*.npz")))
+
+
+def test_gpu_fixtures_present():
+    assert len(GPU_FIXTURES) == 6
+
+
+@pytest.mark.parametrize("mode", MODES + ["func"])
+@pytest.mark.parametrize("path", GPU_FIXTURES, ids=[os.path.basename(p)[8:-4] for p in GPU_FIXTURES])
+def test_oracle_matches_the_reference_run_on_a_b200(path, mode):
+    """tests/golden/ref_gpu_*.npz: the UNMODIFIED controlnet/softsplat.py executed on a B200 (its three kernel
+    strings NVRTC-compiled for sm_100 through baseline/cupy_shim.py; minted by baseline/ref_gpu_golden.py on the
+    inputs of the emulation fixtures). Atomic order and torch's CUDA exp / div differ from the CPU by ulps, so this
+    pin is 'within 2e-6 of max' in fp32 (1e-12 in fp64), widened where the fp32 reference is itself
+    ill-conditioned (tests/util.assert_close); the bit-exact pin is the CPU emulation above."""
+    from tests.util import assert_close
+    z = np.load(path)
+    f64 = z["tin"].dtype == np.float64
+    if mode == "func":
+        r = {"out": orc.splat_fwd(z["tin"], z["flow"]), "gin": orc.splat_ingrad(z["flow"], z["gout"]),
+             "gflow": orc.splat_flowgrad(z["tin"], z["flow"], z["gout"])}
+        truth = None
+    else:
+        r = _run_oracle(z, mode)
+        z64 = {k: z[k].astype(np.float64) for k in ("tin", "flow", "metric", "gout")}
+        truth = None if f64 else _run_oracle(z64, mode)
+    for k, v in r.items():
+        assert_close(torch.from_numpy(np.asarray(v)), torch.from_numpy(z[f"{mode}/{k}"]), 1e-12 if f64 else 2e-6, f"{mode}/{k}",
+                     truth=None if truth is None else torch.from_numpy(truth[k]))
+
+
 TILE_GOLDEN = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "ref_tiles_*.npz")))
 
 

@@ -58,12 +58,13 @@ def test_forward_backward_fp64(dcb, orc, mode):
             assert_close(got[k], ref[k], 1e-12, f"{mode} fp64 {k}")
 
 
-FIXTURES = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "ref_emu_*_fast.npz")))
+FIXTURES = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "ref_emu_*_fast.npz")) +
+                  glob.glob(os.path.join(os.path.dirname(__file__), "golden", "ref_gpu_*.npz")))     # CPU emulation of, and a real B200 run of, the reference
 GOLDEN_MODES = ["sum", "avg", "linear", "soft", "avg-zeroeps", "linear-clipeps", "soft-zeroeps", "soft-clipeps", "soft-addeps"]
 
 
 @pytest.mark.parametrize("mode", GOLDEN_MODES)
-@pytest.mark.parametrize("path", FIXTURES, ids=[os.path.basename(p)[8:-9] for p in FIXTURES])
+@pytest.mark.parametrize("path", FIXTURES, ids=[os.path.basename(p)[4:-4] for p in FIXTURES])
 def test_golden_reference_vectors(dcb, path, mode):
     """Outputs of the reference's own kernel text (sequential CPU emulation): includes integer /
     half-integer / out-of-frame / NaN / +-Inf / 1e30 flows and an all-to-one-pixel collision."""
@@ -426,3 +427,34 @@ def test_softsplat_host_matches_device(dcb):
         got = dcb.softsplat_host(tin.pin_memory(), flow.pin_memory(), metric.pin_memory(), "soft", chunk_frames=4)
         torch.cuda.synchronize()
         assert_close(got, ref, 1e-5, "host ramped")
+
+
+def test_softsplat_host_compact_element_types(dcb, orc):
+    """8-bit frames, half-precision flow / metric, bf16 result: uploaded as they are, widened to fp32 on the device
+    (dcb_convert); within 1e-2 of the fp32 oracle on the same (up-cast) values. Also the synchronous return: the result
+    is complete when the call returns, without any torch.cuda.synchronize()."""
+    g = torch.Generator().manual_seed(61)
+    frames = torch.randint(0, 256, (9, 3, 40, 56), generator=g, dtype=torch.uint8)
+    flow = (torch.randn(9, 2, 40, 56, generator=g) * 2).half()
+    metric = (-torch.rand(9, 1, 40, 56, generator=g)).half()
+    ref = orc.softsplat(frames.float() / 255.0, flow.float(), metric.float(), "soft")
+    out = torch.empty(9, 3, 40, 56, dtype=torch.bfloat16).pin_memory()
+    got = dcb.softsplat_host(frames.pin_memory(), flow.pin_memory(), metric.pin_memory(), "soft", out=out, chunk_frames=4)
+    assert got is out                                   # no synchronize here on purpose
+    assert_close(got.float(), ref, 1e-2, "host compact bf16 result")
+    got32 = dcb.softsplat_host(frames.pin_memory(), flow.bfloat16().pin_memory(), None, "avg", chunk_frames=2)
+    assert got32.dtype == torch.float32
+    assert_close(got32, orc.softsplat(frames.float() / 255.0, flow.bfloat16().float(), None, "avg"), 1e-5, "host u8 -> fp32 result")
+
+
+def test_convert_kernel(dcb):
+    L = dcb._lib
+    g = torch.Generator(device="cuda").manual_seed(3)
+    for n in (1, 7, 8, 1000, 4099):
+        src = torch.randint(0, 256, (n,), device="cuda", generator=g, dtype=torch.uint8)
+        assert torch.equal(L.convert(src, torch.empty(n, device="cuda")), src.float())
+        assert torch.equal(L.convert(src, torch.empty(n, device="cuda"), 1 / 255.0), src.float() * (1 / 255.0))
+        x = torch.randn(n, device="cuda", generator=g)
+        assert torch.equal(L.convert(x, torch.empty(n, device="cuda", dtype=torch.bfloat16)), x.bfloat16())
+        assert torch.equal(L.convert(x.half(), torch.empty(n, device="cuda")), x.half().float())
+        assert torch.equal(L.convert(x[1:], torch.empty(max(n - 1, 0), device="cuda", dtype=torch.float16)), x[1:].half())   # unaligned source

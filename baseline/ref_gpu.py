@@ -15,17 +15,21 @@ import sys
 import warnings
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-_REF_SRC = os.path.join(os.environ.get("DCB_REFERENCE_ROOT", "/root/reference"), "controlnet", "softsplat.py")
+_REF_ROOT = os.path.join(os.environ.get("DCB_REFERENCE_ROOT", "/root/reference"), "controlnet")
+_REF_SRC = os.path.join(_REF_ROOT, "softsplat.py")
 _REF_DST = os.path.join(_HERE, "_ref", "controlnet", "softsplat.py")
+_STAGED = ("softsplat.py", "control_utils.py", "extractors.py")     # the op, its helpers, and the live consumer
 _module = None
+_package = None
 
 
 def stage() -> bool:
-    """Copy the reference file into baseline/_ref/ (git-ignored). Returns False when /root/reference is absent."""
+    """Copy the reference files into baseline/_ref/ (git-ignored). Returns False when /root/reference is absent."""
     if not os.path.exists(_REF_SRC):
         return os.path.exists(_REF_DST)
     os.makedirs(os.path.dirname(_REF_DST), exist_ok=True)
-    shutil.copyfile(_REF_SRC, _REF_DST)
+    for name in _STAGED:
+        shutil.copyfile(os.path.join(_REF_ROOT, name), os.path.join(os.path.dirname(_REF_DST), name))
     return True
 
 
@@ -60,6 +64,37 @@ def load():
             spec.loader.exec_module(mod)
         _module = mod
     return _module
+
+
+def load_package():
+    """The reference's ``controlnet.softsplat`` / ``control_utils`` / ``extractors`` as a namespace of module objects
+    (``.softsplat``, ``.control_utils``, ``.extractors``), imported from baseline/_ref behind the CuPy stand-in. The
+    ``controlnet*`` entries are removed from sys.modules again, so this never collides with diffcodec_b200.install()."""
+    global _package
+    if _package is None:
+        why = available()
+        if why:
+            raise RuntimeError("reference-on-GPU unavailable: " + why)
+        if _HERE not in sys.path:
+            sys.path.insert(0, _HERE)
+        import cupy_shim
+        import types
+        cupy_shim.install()
+        saved = {k: sys.modules.pop(k) for k in list(sys.modules) if k == "controlnet" or k.startswith("controlnet.")}
+        root = os.path.join(_HERE, "_ref")
+        sys.path.insert(0, root)
+        try:
+            import importlib
+            with warnings.catch_warnings():
+                warnings.simplefilter("ignore")
+                mods = {n: importlib.import_module("controlnet." + n) for n in ("softsplat", "control_utils", "extractors")}
+        finally:
+            sys.path.remove(root)
+            for k in [k for k in sys.modules if k == "controlnet" or k.startswith("controlnet.")]:
+                del sys.modules[k]
+            sys.modules.update(saved)
+        _package = types.SimpleNamespace(**mods)
+    return _package
 
 
 if __name__ == "__main__":

@@ -246,6 +246,13 @@ def _extras(torch, d, dev, gen, peak):
         with torch.no_grad():
             msp = _time_cuda(torch, pyramid, 50, 10)
         ex["controlnet_pyramid_16_splats_batch2_f32"] = {"us_per_forward": round(msp * 1e3, 1), "us_per_splat": round(msp * 1e3 / 16, 2)}
+        # the same 16 splats + the 4 fusions as FOUR fused calls (dcb_bidir_block_fwd: one library call per scale, learned-metric stand-in)
+        def pyramid_fused():
+            for feat, ff, fb, m_ in pyr:
+                d.bidirectional_block(feat, feat, ff, fb, m_, m_)
+        with torch.no_grad():
+            msf = _time_cuda(torch, pyramid_fused, 50, 10)
+        ex["controlnet_pyramid_4_fused_blocks_batch2_f32"] = {"us_per_forward": round(msf * 1e3, 1), "includes": "16 splats + 4 confidence fusions with hole fill"}
         # C3: 64-frame 1080p warp + residual: fused splat recipe and backwarp + residual
         n3 = 64
         img = torch.rand(n3, 3, H, W, device=dev, generator=gen); gt = torch.rand(n3, 3, H, W, device=dev, generator=gen)

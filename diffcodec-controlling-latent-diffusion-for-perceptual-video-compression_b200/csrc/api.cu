@@ -56,6 +56,16 @@ int bidir_fuse_bwd_impl(const DcbTensor*, const DcbTensor*, const DcbTensor*, co
                         const DcbTensor*, const DcbTensor*, const DcbTensor*, const DcbTensor*, const DcbTensor*,
                         const DcbTensor*, cudaStream_t);
 
+long long block_fwd_acc_bytes(long long N, long long C, long long H, long long W, int dtype);
+long long block_fwd_scratch_bytes(long long N, long long C, long long H, long long W, int dtype);
+long long block_bwd_scratch_bytes(long long N, long long C, long long H, long long W, int dtype);
+int bidir_block_fwd_impl(const DcbTensor*, const DcbTensor*, const DcbTensor*, const DcbTensor*, const DcbTensor*, const DcbTensor*,
+                         const DcbTensor*, const DcbTensor*, const DcbTensor*, const DcbTensor*, const DcbTensor*, const DcbTensor*,
+                         const DcbTensor*, void*, long long, void*, long long, int, cudaStream_t);
+int bidir_block_bwd_impl(const DcbTensor*, const DcbTensor*, const DcbTensor*, const DcbTensor*, const DcbTensor*, const DcbTensor*,
+                         const DcbTensor*, const DcbTensor*, const DcbTensor*, const DcbTensor*, const DcbTensor*, const DcbTensor*,
+                         const DcbTensor*, const DcbTensor*, const DcbTensor*, const DcbTensor*, const DcbTensor*, void*, long long,
+                         cudaStream_t);
 int convert_impl(const void* src, int src_dtype, void* dst, int dst_dtype, long long n, float scale, cudaStream_t st);
 extern int g_fwd_path;
 bool use_owner(int dtype, int mode, long long C, long long H, long long W);
@@ -439,6 +449,90 @@ int dcb_tile_merge(const DcbTensor* tiles, const int64_t* pixel_coords, int32_t 
     }
     static_assert(sizeof(long long) == sizeof(int64_t), "int64_t coordinates");
     return tile_merge_impl(tiles, (const long long*)pixel_coords, n_tiles, out, H_px, W_px, eps, ws, ws_bytes, (cudaStream_t)stream);
+}
+
+static int check_block_common(const char* fn, const DcbTensor* first, const DcbTensor* last, const DcbTensor* flow_f, const DcbTensor* flow_b,
+                              const DcbTensor* metric_f, const DcbTensor* metric_b) {
+    TRY(check_tensor(fn, "first", first, true));
+    TRY(check_tensor(fn, "last", last, true));
+    TRY(check_tensor(fn, "flow_f", flow_f, true));
+    TRY(check_tensor(fn, "flow_b", flow_b, true));
+    TRY(check_tensor(fn, "metric_f", metric_f, true));
+    TRY(check_tensor(fn, "metric_b", metric_b, true));
+    const long long N = first->size[0], C = first->size[1], H = first->size[2], W = first->size[3];
+    TRY(check_limits(fn, first));
+    TRY(check_shape(fn, "last", last, N, C, H, W));
+    TRY(check_shape(fn, "flow_f", flow_f, N, 2, H, W));
+    TRY(check_shape(fn, "flow_b", flow_b, N, 2, H, W));
+    TRY(check_shape(fn, "metric_f", metric_f, N, 1, H, W));
+    TRY(check_shape(fn, "metric_b", metric_b, N, 1, H, W));
+    const int dt = first->dtype;
+    if (dt != DCB_F32 && dt != DCB_BF16) return set_error(DCB_E_DTYPE, "%s: F32 or BF16 only, got %d", fn, dt);
+    if (last->dtype != dt || flow_f->dtype != dt || flow_b->dtype != dt || metric_f->dtype != dt || metric_b->dtype != dt)
+        return set_error(DCB_E_DTYPE, "%s: all tensors must share one dtype", fn);
+    return DCB_OK;
+}
+
+static int check_block_opt(const char* fn, const char* name, const DcbTensor* t, const DcbTensor* first, long long C, int dtype) {
+    TRY(check_tensor(fn, name, t, false));
+    TRY(check_shape(fn, name, t, first->size[0], C, first->size[2], first->size[3]));
+    TRY(check_out(fn, name, t, dtype, elem_size(dtype)));
+    return DCB_OK;
+}
+
+int64_t dcb_bidir_block_workspace_bytes(int64_t N, int64_t C, int64_t H, int64_t W, int32_t dtype, int32_t which) {
+    if (N < 0 || C < 0 || H < 0 || W < 0) return 0;
+    if (which == 0) return (int64_t)block_fwd_acc_bytes(N, C, H, W, dtype);
+    if (which == 1) return (int64_t)block_fwd_scratch_bytes(N, C, H, W, dtype);
+    return (int64_t)block_bwd_scratch_bytes(N, C, H, W, dtype);
+}
+
+int dcb_bidir_block_fwd(const DcbTensor* first, const DcbTensor* last, const DcbTensor* flow_f, const DcbTensor* flow_b,
+                        const DcbTensor* metric_f, const DcbTensor* metric_b, const DcbTensor* fused, const DcbTensor* warped_f,
+                        const DcbTensor* warped_b, const DcbTensor* norm_f, const DcbTensor* norm_b, const DcbTensor* occ_f,
+                        const DcbTensor* occ_b, void* ws_acc, int64_t ws_acc_bytes, void* ws_scratch, int64_t ws_scratch_bytes,
+                        int32_t flags, void* stream) {
+    const char* fn = "dcb_bidir_block_fwd";
+    TRY(check_block_common(fn, first, last, flow_f, flow_b, metric_f, metric_b));
+    if (flags & ~DCB_FLAG_WS_CLEAN) return set_error(DCB_E_MODE, "%s: unknown flags 0x%x", fn, flags);
+    const int dt = first->dtype;
+    const long long C = first->size[1];
+    TRY(check_tensor(fn, "fused", fused, true));
+    TRY(check_block_opt(fn, "fused", fused, first, C, dt));
+    TRY(check_block_opt(fn, "warped_f", warped_f, first, C, dt));
+    TRY(check_block_opt(fn, "warped_b", warped_b, first, C, dt));
+    TRY(check_block_opt(fn, "norm_f", norm_f, first, 1, DCB_F32));
+    TRY(check_block_opt(fn, "norm_b", norm_b, first, 1, DCB_F32));
+    TRY(check_block_opt(fn, "occ_f", occ_f, first, 1, dt));
+    TRY(check_block_opt(fn, "occ_b", occ_b, first, 1, dt));
+    return bidir_block_fwd_impl(first, last, flow_f, flow_b, metric_f, metric_b, fused, warped_f, warped_b, norm_f, norm_b, occ_f, occ_b,
+                                ws_acc, ws_acc_bytes, ws_scratch, ws_scratch_bytes, flags, (cudaStream_t)stream);
+}
+
+int dcb_bidir_block_bwd(const DcbTensor* grad_fused, const DcbTensor* first, const DcbTensor* last, const DcbTensor* flow_f,
+                        const DcbTensor* flow_b, const DcbTensor* metric_f, const DcbTensor* metric_b, const DcbTensor* warped_f,
+                        const DcbTensor* warped_b, const DcbTensor* norm_f, const DcbTensor* norm_b, const DcbTensor* occ_f,
+                        const DcbTensor* occ_b, const DcbTensor* grad_first, const DcbTensor* grad_last,
+                        const DcbTensor* grad_metric_f, const DcbTensor* grad_metric_b, void* ws, int64_t ws_bytes, void* stream) {
+    const char* fn = "dcb_bidir_block_bwd";
+    TRY(check_block_common(fn, first, last, flow_f, flow_b, metric_f, metric_b));
+    const int dt = first->dtype;
+    const long long N = first->size[0], C = first->size[1], H = first->size[2], W = first->size[3];
+    TRY(check_tensor(fn, "grad_fused", grad_fused, true));
+    TRY(check_shape(fn, "grad_fused", grad_fused, N, C, H, W));
+    if (grad_fused->dtype != dt) return set_error(DCB_E_DTYPE, "%s: grad_fused dtype differs", fn);
+    const DcbTensor* req[6] = {warped_f, warped_b, norm_f, norm_b, occ_f, occ_b};
+    const char* names[6] = {"warped_f", "warped_b", "norm_f", "norm_b", "occ_f", "occ_b"};
+    for (int i = 0; i < 6; ++i) {
+        if (!req[i]) return set_error(DCB_E_NULL, "%s: %s of the forward is required", fn, names[i]);
+        TRY(check_block_opt(fn, names[i], req[i], first, i < 2 ? C : 1, (i == 2 || i == 3) ? DCB_F32 : dt));
+    }
+    TRY(check_block_opt(fn, "grad_first", grad_first, first, C, dt));
+    TRY(check_block_opt(fn, "grad_last", grad_last, first, C, dt));
+    TRY(check_block_opt(fn, "grad_metric_f", grad_metric_f, first, 1, dt));
+    TRY(check_block_opt(fn, "grad_metric_b", grad_metric_b, first, 1, dt));
+    return bidir_block_bwd_impl(grad_fused, first, last, flow_f, flow_b, metric_f, metric_b, warped_f, warped_b, norm_f, norm_b, occ_f, occ_b,
+                                grad_first, grad_last, grad_metric_f, grad_metric_b, ws, ws_bytes, (cudaStream_t)stream);
 }
 
 int dcb_convert(const void* src, int32_t src_dtype, void* dst, int32_t dst_dtype, int64_t n, float scale, void* stream) {

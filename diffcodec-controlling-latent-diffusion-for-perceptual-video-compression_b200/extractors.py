@@ -14,11 +14,14 @@ no host sync:
 from __future__ import annotations
 
 import torch
+import torch.nn as nn
+import torch.nn.functional as F
 
 from . import _lib
-from .control_utils import compute_mask
+from .control_utils import FeatureWarperSoftsplat, compute_mask, resize_and_normalize_flow_batched, zero_module
 
-__all__ = ["bidir_fuse", "bidirectional_warp_fuse"]
+__all__ = ["bidir_fuse", "bidirectional_warp_fuse", "bidirectional_block", "Bi_Dir_FeatureExtractor", "Bi_Dir_ResidueExtractor",
+           "WarpExtractor", "ConvBlock"]
 
 
 def _fuse_forward(A, B, conf_a, conf_b, occ_a, occ_b):
@@ -77,63 +80,221 @@ def bidir_fuse(warped_a, warped_b, conf_a, conf_b, occ_a=None, occ_b=None):
     return _fuse_forward(warped_a, warped_b, conf_a, conf_b, occ_a, occ_b)[0]     # inference: no autograd.Function bookkeeping
 
 
+def _block_sizes(n, c, h, w, dt):
+    key = (n, c, h, w, dt)
+    v = _block_ws.get(key)
+    if v is None:
+        lib = _lib.lib()
+        v = _block_ws[key] = tuple(int(lib.dcb_bidir_block_workspace_bytes(n, c, h, w, dt, k)) for k in (0, 1, 2))
+    return v
+
+
+_block_ws: dict = {}
+_lib._option_hooks.append(_block_ws.clear)
+
+
 class _bidir_block_func(torch.autograd.Function):
-    """The whole block as ONE autograd node (metric = ones, flows without gradient): the same five
-    library calls forward and three backward as the composition below, without four of its five
-    autograd nodes and their bookkeeping -- the block is bound by Python, not by its kernels."""
+    """The whole block -- both occlusion masks, both masked soft splats, confidence fusion, double-hole fill -- as ONE
+    autograd node and ONE library call each way (dcb_bidir_block_fwd / _bwd), with the learned metric of the live
+    consumer (gradients reach the features and, through the splat weights AND the fusion weights, the metric)."""
 
     @staticmethod
     @torch.amp.custom_fwd(device_type="cuda", cast_inputs=torch.float32)       # the splats run in fp32 (control_utils.py:61)
-    def forward(ctx, first, last, flow_f, flow_b):
-        import importlib
-        ss = importlib.import_module(__package__ + ".softsplat")
-        dt = first.dtype
-        occ_fwd = compute_mask(flow_f, flow_b)
-        occ_bwd = compute_mask(flow_b, flow_f)
-        mf, mb = (occ_fwd, occ_bwd) if dt == torch.float32 else (occ_fwd.to(dt), occ_bwd.to(dt))
-        metric = torch.ones_like(flow_f[:, :1], dtype=dt)
-        need = ctx.needs_input_grad[0] or ctx.needs_input_grad[1]
-        ss._check_inputs(first, flow_f); ss._check_inputs(last, flow_b)
-        ff, fb = ss._match_flow(first, flow_f), ss._match_flow(last, flow_b)
-        det = ss.is_deterministic()
-        w1, n1 = ss._forward(first, ff, metric, mf, _lib.MODE_SOFT, _lib.EPS_ADD, det, need)
-        w2, n2 = ss._forward(last, fb, metric, mb, _lib.MODE_SOFT, _lib.EPS_ADD, det, need)
-        fused, _ = _fuse_forward(w1, w2, metric, metric, mf, mb)
+    def forward(ctx, first, last, flow_f, flow_b, metric_f, metric_b, holes):
+        lib = _lib.lib()
+        n, c, h, w = first.shape
+        dev, dt = first.device, first.dtype
+        need = any(ctx.needs_input_grad[i] for i in (0, 1, 4, 5))
+        fused = torch.empty((n, c, h, w), dtype=dt, device=dev)
+        saved = None
         if need:
-            ctx.save_for_backward(first, last, ff, fb, metric, mf, mb, w1, n1, w2, n2)
+            warped = torch.empty((2, n, c, h, w), dtype=dt, device=dev)
+            planes = torch.empty((2, n, 1, h, w), dtype=torch.float32, device=dev)
+            occ = torch.empty((2, n, 1, h, w), dtype=dt, device=dev)
+            saved = (warped[0], warped[1], planes[0], planes[1], occ[0], occ[1])
+        acc_b, scr_b, _ = _block_sizes(n, c, h, w, _lib._DTYPES[dt])
+        stream = _lib.stream_ptr(dev)
+        ws_acc = _lib.workspace(dev, acc_b, "acc", stream)
+        ws_scr = None if need else _lib.workspace(dev, scr_b, "scratch", stream)
+        D = _lib.desc
+        with _lib.on_device(dev):
+            rc = lib.dcb_bidir_block_fwd(D(first), D(last), D(flow_f), D(flow_b), D(metric_f), D(metric_b), D(fused),
+                                         *([D(t) for t in saved] if need else [None] * 6),
+                                         ws_acc.data_ptr(), ws_acc.numel(), None if need else ws_scr.data_ptr(), 0 if need else ws_scr.numel(),
+                                         _lib.FLAG_WS_CLEAN, stream)
+        if rc != 0:
+            _lib.invalidate_acc(dev)
+        _lib.check(rc, "dcb_bidir_block_fwd")
+        ctx.holes = holes
+        if need:
+            ctx.save_for_backward(first, last, flow_f, flow_b, metric_f, metric_b, *saved)
         return fused
 
     @staticmethod
     @torch.amp.custom_bwd(device_type="cuda")
     def backward(ctx, g):
-        import importlib
-        ss = importlib.import_module(__package__ + ".softsplat")
-        first, last, ff, fb, metric, mf, mb, w1, n1, w2, n2 = ctx.saved_tensors
+        first, last, flow_f, flow_b, metric_f, metric_b, wf, wb, nf, nb, of, ob = ctx.saved_tensors
         lib = _lib.lib()
-        dev = first.device
+        n, c, h, w = first.shape
+        dev, dt = first.device, first.dtype
         need = ctx.needs_input_grad
-        g = g.to(first.dtype)
-        gA = torch.empty_like(w1) if need[0] else None
-        gB = torch.empty_like(w2) if need[1] else None
+        g = g.to(dt)
+        g1 = torch.empty_like(first, memory_format=torch.contiguous_format) if need[0] else None
+        g2 = torch.empty_like(last, memory_format=torch.contiguous_format) if need[1] else None
+        gm1 = torch.empty((n, 1, h, w), dtype=dt, device=dev) if need[4] else None
+        gm2 = torch.empty((n, 1, h, w), dtype=dt, device=dev) if need[5] else None
+        ws = _lib.workspace(dev, _block_sizes(n, c, h, w, _lib._DTYPES[dt])[2], "scratch")
+        D = _lib.desc
         with _lib.on_device(dev):
-            rc = lib.dcb_bidir_fuse_bwd(_lib.desc(g), _lib.desc(w1), _lib.desc(w2), _lib.desc(metric), _lib.desc(metric),
-                                        _lib.desc(mf), _lib.desc(mb), _lib.desc(gA), _lib.desc(gB), None, None, _lib.stream_ptr(dev))
-        _lib.check(rc, "dcb_bidir_fuse_bwd")
-        g1 = ss._backward(gA, first, ff, metric, w1, n1, mf, _lib.MODE_SOFT, _lib.EPS_ADD, (True, False, False))[0] if need[0] else None
-        g2 = ss._backward(gB, last, fb, metric, w2, n2, mb, _lib.MODE_SOFT, _lib.EPS_ADD, (True, False, False))[0] if need[1] else None
-        return g1, g2, None, None
+            rc = lib.dcb_bidir_block_bwd(D(g), D(first), D(last), D(flow_f), D(flow_b), D(metric_f), D(metric_b), D(wf), D(wb), D(nf), D(nb),
+                                         D(of), D(ob), D(g1), D(g2), D(gm1), D(gm2), ws.data_ptr(), ws.numel(), _lib.stream_ptr(dev))
+        _lib.check(rc, "dcb_bidir_block_bwd")
+        return g1, g2, None, None, gm1, gm2, None
+
+
+def bidirectional_block(first_features, last_features, flow_f, flow_b, metric_f=None, metric_b=None):
+    """masks + both masked soft splats + confidence fusion + double-hole fill of ONE pyramid scale
+    (``extractors.py:289-310``), given the two metric maps (``metric_net`` outputs, or None for a warper without one).
+    One library call forward, one backward; no host sync. Flows must not require a gradient (they do not in
+    ``Bi_Dir_FeatureExtractor``); otherwise use ``bidirectional_warp_fuse``."""
+    dt = first_features.dtype
+    if metric_f is None:
+        metric_f = torch.ones_like(flow_f[:, :1], dtype=dt)
+    if metric_b is None:
+        metric_b = torch.ones_like(flow_b[:, :1], dtype=dt)
+    cast = lambda t: t if t.dtype == dt else t.to(dt)
+    return _bidir_block_func.apply(first_features, cast(last_features), cast(flow_f), cast(flow_b), cast(metric_f), cast(metric_b), True)
+
+
+def _block_fusable(first, last, flow_f, flow_b):
+    from .softsplat import is_deterministic
+    return (first.is_cuda and first.shape == last.shape and first.dtype in (torch.float32, torch.bfloat16, torch.float16)
+            and not (torch.is_grad_enabled() and (flow_f.requires_grad or flow_b.requires_grad)) and not is_deterministic())
 
 
 def bidirectional_warp_fuse(first_features, last_features, flow_f, flow_b, warper):
     """The per-scale block of ``Bi_Dir_FeatureExtractor.forward`` between the conv stacks
     (``extractors.py:289-310``): masks, both warps, fusion. ``warper`` is a ``FeatureWarperSoftsplat``."""
-    if (not getattr(warper, "with_learnable_metric", True) and not flow_f.requires_grad and not flow_b.requires_grad
-            and first_features.is_cuda and first_features.dtype == last_features.dtype
-            and flow_f.dtype in (torch.float32, torch.bfloat16) and flow_b.dtype == flow_f.dtype
-            and first_features.shape == last_features.shape):
-        return _bidir_block_func.apply(first_features, last_features, flow_f, flow_b)
+    if _block_fusable(first_features, last_features, flow_f, flow_b):
+        learn = getattr(warper, "with_learnable_metric", False)
+        mf = warper.metric_net(first_features) if learn else None
+        mb = warper.metric_net(last_features) if learn else None
+        with torch.autocast(device_type="cuda", enabled=False):
+            return bidirectional_block(first_features, last_features, flow_f, flow_b, mf, mb)
     occ_fwd = compute_mask(flow_f, flow_b)
     occ_bwd = compute_mask(flow_b, flow_f)
     warped_first, conf_fwd = warper(first_features, flow_f, mask=occ_fwd)
     warped_last, conf_bwd = warper(last_features, flow_b, mask=occ_bwd)
     return bidir_fuse(warped_first, warped_last, conf_fwd, conf_bwd, occ_fwd, occ_bwd)
+
+
+# -------------------------------------------------------------------------------------------------
+# Drop-in modules for ``controlnet/extractors.py``: same class names, constructor arguments, parameter names (checkpoints
+# load with ``load_state_dict``) and forward signatures. The conv stacks are plain cuDNN modules and are only declared
+# here so that the state_dict keys match; what changes is the motion-compensation part of ``forward``.
+# -------------------------------------------------------------------------------------------------
+def _silu_convs(*spec):
+    """nn.Sequential of (Conv2d 3x3 pad 1, SiLU) pairs; spec entries are (c_in, c_out, stride)."""
+    layers = []
+    for cin, cout, stride in spec:
+        layers += [nn.Conv2d(cin, cout, 3, padding=1, stride=stride), nn.SiLU()]
+    return nn.Sequential(*layers)
+
+
+class ConvBlock(nn.Module):                                   # extractors.py:14-24
+    def __init__(self, in_ch, out_ch, stride=1):
+        super().__init__()
+        self.block = _silu_convs((in_ch, out_ch, stride), (out_ch, out_ch, 1))
+
+    def forward(self, x):
+        return self.block(x)
+
+
+class WarpExtractor(nn.Module):                               # extractors.py:26-65 (no motion compensation inside)
+    def __init__(self, inject_channels=[320, 320, 640, 1280]):
+        super().__init__()
+        self.inject_channels = inject_channels
+        widths = (64, 320, 320, 640, 1280)
+        for i, (cin, cout, stride) in enumerate(zip((3,) + widths[:-1], widths, (4, 2, 2, 2, 2)), start=1):
+            setattr(self, f"enc{i}", ConvBlock(cin, cout, stride=stride))
+        self.zero_convs = nn.ModuleList([zero_module(nn.Conv2d(c, inject_channels[i], 3, padding=1)) for i, c in enumerate(widths[1:])])
+
+    def forward(self, x):
+        feats = []
+        for i in range(1, 6):
+            x = getattr(self, f"enc{i}")(x)
+            feats.append(x)
+        return [zc(f) for zc, f in zip(self.zero_convs, feats[1:])]
+
+
+class Bi_Dir_FeatureExtractor(nn.Module):
+    """``controlnet/extractors.py:209-316``. Per scale, everything between the stride-2 convs and the zero conv is ONE
+    fused call (``bidirectional_block``): no ``holes.any()`` host sync, ~9 launches instead of ~45."""
+
+    def __init__(self, inject_channels):
+        super().__init__()
+        self.inject = inject_channels
+        self.split_res = [int(i / 2) for i in self.inject]
+        pre = ((3, 16, 1), (16, 32, 2), (32, 32, 1), (32, 64, 2), (64, 64, 1))
+        self.first_pre_extractor = _silu_convs(*pre)
+        self.last_pre_extractor = _silu_convs(*pre)
+        self.wrapper = nn.ModuleList([FeatureWarperSoftsplat(with_learnable_metric=True, in_channels=c) for c in self.split_res])
+        chain = [64] + self.split_res
+        self.extractors_first = nn.ModuleList([_silu_convs((chain[i], chain[i + 1], 2)) for i in range(4)])
+        self.extractors_last = nn.ModuleList([_silu_convs((chain[i], chain[i + 1], 2)) for i in range(4)])
+        self.zero_convs = nn.ModuleList([zero_module(nn.Conv2d(c // 2, c, 3, padding=1)) for c in inject_channels])
+
+    def forward(self, local_conditions, flow):
+        first_features = self.first_pre_extractor(local_conditions[:, 3:])      # extractors.py:266-272
+        last_features = self.last_pre_extractor(local_conditions[:, :3])
+        flow_fwd, flow_bwd = flow[:, :2], flow[:, 2:]
+        outs = []
+        for idx, res in enumerate((64, 32, 16, 8)):                              # extractors.py:278
+            first_features = self.extractors_first[idx](first_features)
+            last_features = self.extractors_last[idx](last_features)
+            flow_f = resize_and_normalize_flow_batched(flow_fwd, res, res)
+            flow_b = resize_and_normalize_flow_batched(flow_bwd, res, res)
+            fused = bidirectional_warp_fuse(first_features, last_features, flow_f, flow_b, self.wrapper[idx])
+            outs.append(self.zero_convs[idx](fused))
+        return outs
+
+
+class Bi_Dir_ResidueExtractor(nn.Module):
+    """``controlnet/extractors.py:67-205``. The flows pass through learned refiners here, so they carry a gradient and
+    the block runs as masks + two differentiable splats + the fusion kernel (no hole branch in this class, :193-199)."""
+
+    def __init__(self, inject_channels):
+        super().__init__()
+        self.inject = inject_channels
+        self.split_res = [int(i // 2) for i in inject_channels]
+        c = self.split_res
+        pre = ((3, 32, 1), (32, 64, 2), (64, 64, 2))
+        self.prev_pre = _silu_convs(*pre)
+        self.next_pre = _silu_convs(*pre)
+        chain = [64] + c
+        self.prev_pyramids = nn.ModuleList([_silu_convs((chain[i], chain[i + 1], 2)) for i in range(4)])
+        self.next_pyramids = nn.ModuleList([_silu_convs((chain[i], chain[i + 1], 2)) for i in range(4)])
+        self.flow_refiners = nn.ModuleList([nn.Conv2d(2, 2, kernel_size=3, padding=1, groups=2) for _ in range(4)])
+        self.flow_feature_encoders = nn.ModuleList([nn.Conv2d(2, w, 3, padding=1) for w in (16, 16, 32, 32)])
+        self.warpers = nn.ModuleList([FeatureWarperSoftsplat(with_learnable_metric=True, in_channels=ci) for ci in c])
+        self.zero_convs = nn.ModuleList([zero_module(nn.Conv2d(ci, inject_channels[i], kernel_size=3, padding=1)) for i, ci in enumerate(c)])
+        self.resolutions = [64, 32, 16, 8]
+
+    def forward(self, prev_frame, next_frame, flow_fwd, flow_bwd, masks=None):
+        B, _, H, W = prev_frame.shape
+        assert H == 512 and W == 512, "expects 512x512 inputs"                   # extractors.py:157
+        x_prev, x_next = self.prev_pre(prev_frame), self.next_pre(next_frame)
+        prev_feats, next_feats = [], []
+        for enc_prev, enc_next in zip(self.prev_pyramids, self.next_pyramids):
+            x_prev, x_next = enc_prev(x_prev), enc_next(x_next)
+            prev_feats.append(x_prev); next_feats.append(x_next)
+        outs = []
+        for i, res in enumerate(self.resolutions):
+            factor = H // res                                                    # extractors.py:181-183: resize, then divide by the scale factor
+            flow_f = self.flow_refiners[i](F.interpolate(flow_fwd, size=(res, res), mode="bilinear", align_corners=False) / factor)
+            flow_b = self.flow_refiners[i](F.interpolate(flow_bwd, size=(res, res), mode="bilinear", align_corners=False) / factor)
+            occ_f, occ_b = compute_mask(flow_f, flow_b), compute_mask(flow_b, flow_f)
+            warped_prev, conf_prev = self.warpers[i](prev_feats[i], flow_f, mask=occ_f)
+            warped_next, conf_next = self.warpers[i](next_feats[i], flow_b, mask=occ_b)
+            outs.append(self.zero_convs[i](bidir_fuse(warped_prev, warped_next, conf_prev, conf_next)))
+        return outs

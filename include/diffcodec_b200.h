@@ -221,6 +221,36 @@ int dcb_bidir_fuse_bwd(const DcbTensor* grad_fused, const DcbTensor* A, const Dc
                        const DcbTensor* grad_conf_b, void* stream);
 
 /*
+ * One bi-directional conditioning block (one pyramid scale) in ONE call: both occlusion masks, both soft splats with
+ * their (1 - mask) product, the confidence fusion and the double-hole fill. Replaces, per scale, the body of
+ * Bi_Dir_FeatureExtractor.forward between the conv stacks -- controlnet/extractors.py:289-310 (also :181-205 of
+ * Bi_Dir_ResidueExtractor): compute_mask x2 (control_utils.py:11-17), FeatureWarperSoftsplat.forward x2
+ * (control_utils.py:49-72, the metric_net conv excluded: pass its output as metric_*), the fusion and the
+ * `holes.any()` host sync (extractors.py:298-310).
+ *
+ *   first, last   [N,C,H,W] feature maps;  flow_f, flow_b [N,2,H,W];  metric_f, metric_b [N,1,H,W] (the warper's
+ *                 metric = the fusion confidence; pass ones for a warper without metric_net)
+ *   fused         [N,C,H,W] contiguous: the block's result
+ *   warped_*, norm_* (F32), occ_*: optional outputs (NULL = kept in scratch / not produced); the backward needs all six
+ *   ws_acc        accumulator workspace (dcb_bidir_block_workspace_bytes(.., 0)); DCB_FLAG_WS_CLEAN protocol as dcb_splat_fwd
+ *   ws_scratch    plain scratch (.., 1) for the optional outputs the caller left NULL
+ * Backward: gradients w.r.t. both feature maps and both metrics (splat path + fusion path summed); flows carry no
+ * gradient in the extractors. ws: plain scratch (dcb_bidir_block_workspace_bytes(.., 2)).
+ */
+int64_t dcb_bidir_block_workspace_bytes(int64_t N, int64_t C, int64_t H, int64_t W, int32_t elem_dtype, int32_t which);
+int dcb_bidir_block_fwd(const DcbTensor* first, const DcbTensor* last, const DcbTensor* flow_f, const DcbTensor* flow_b,
+                        const DcbTensor* metric_f, const DcbTensor* metric_b, const DcbTensor* fused,
+                        const DcbTensor* warped_f, const DcbTensor* warped_b, const DcbTensor* norm_f, const DcbTensor* norm_b,
+                        const DcbTensor* occ_f, const DcbTensor* occ_b,
+                        void* ws_acc, int64_t ws_acc_bytes, void* ws_scratch, int64_t ws_scratch_bytes, int32_t flags, void* stream);
+int dcb_bidir_block_bwd(const DcbTensor* grad_fused, const DcbTensor* first, const DcbTensor* last,
+                        const DcbTensor* flow_f, const DcbTensor* flow_b, const DcbTensor* metric_f, const DcbTensor* metric_b,
+                        const DcbTensor* warped_f, const DcbTensor* warped_b, const DcbTensor* norm_f, const DcbTensor* norm_b,
+                        const DcbTensor* occ_f, const DcbTensor* occ_b,
+                        const DcbTensor* grad_first, const DcbTensor* grad_last, const DcbTensor* grad_metric_f,
+                        const DcbTensor* grad_metric_b, void* workspace, int64_t workspace_bytes, void* stream);
+
+/*
  * Hann-window merge of overlapping latent tiles into one canvas, in one gather kernel.
  * Replaces merge_latent_tiles_from_pixel_coords(), patch_utils.py:83-174:
  *   per tile (list order): pixel rectangle -> latent rectangle (int(round()), clamped; the 4-tuple is

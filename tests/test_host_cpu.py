@@ -191,3 +191,18 @@ def test_host_chunk_schedule():
             plan = _chunk_schedule(n, min(k, n))
             assert sum(plan) == n and min(plan) >= 1 and max(plan) <= max(1, min(k, n)), (n, k, plan)
     assert _chunk_schedule(64, 8)[:4] == [1, 2, 4, 8] and _chunk_schedule(64, 8)[-1] == 1
+
+
+def test_dropin_extractors_have_the_reference_state_dict():
+    """tests/golden/ref_extractors_state_dict.json: parameter names and shapes of the reference's classes
+    (controlnet/extractors.py, instantiated with inject_channels [32, 32, 64, 128]): checkpoints must load unchanged."""
+    import json
+    import diffcodec_b200 as d
+    want = json.load(open(os.path.join(ROOT, "tests", "golden", "ref_extractors_state_dict.json")))
+    for name, mod in (("Bi_Dir_FeatureExtractor", d.Bi_Dir_FeatureExtractor([32, 32, 64, 128])),
+                      ("Bi_Dir_ResidueExtractor", d.Bi_Dir_ResidueExtractor([32, 32, 64, 128])), ("WarpExtractor", d.WarpExtractor())):
+        got = {k: list(v.shape) for k, v in mod.state_dict().items()}
+        assert got == want[name], name
+    d.install()
+    from controlnet.extractors import Bi_Dir_FeatureExtractor      # flownet.py:8
+    assert Bi_Dir_FeatureExtractor is d.Bi_Dir_FeatureExtractor

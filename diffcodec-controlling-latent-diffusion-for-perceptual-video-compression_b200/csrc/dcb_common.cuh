@@ -132,6 +132,34 @@ __device__ __forceinline__ float floor_t(float v) { return floorf(v); }
 __device__ __forceinline__ double floor_t(double v) { return floor(v); }
 __device__ __forceinline__ float exp_t(float v) { return expf(v); }
 __device__ __forceinline__ double exp_t(double v) { return exp(v); }
+// exp() of the deterministic mode: IEEE double operations only (rint, fma, scalbn), spelled exactly like
+// orc_exp_det() in oracle/softsplat_oracle.c, so that the CUDA result and the CPU oracle agree BIT FOR BIT (libm's and
+// CUDA's expf differ by an ulp here and there). |relative error| < 2e-16 before the rounding to float.
+__device__ __forceinline__ double exp_det(double x) {
+    if (!(x == x)) return x;
+    if (x > 709.0) return __longlong_as_double(0x7ff0000000000000ll);
+    if (x < -745.0) return 0.0;
+    const double k = rint(x * 1.4426950408889634);
+    double r = fma(-k, 6.93147180369123816490e-01, x);
+    r = fma(-k, 1.90821492927058770002e-10, r);
+    double p = 1.6059043836821613e-10;                    // 1/13!
+    p = fma(p, r, 2.08767569878681e-09);                  // 1/12!
+    p = fma(p, r, 2.505210838544172e-08);
+    p = fma(p, r, 2.755731922398589e-07);
+    p = fma(p, r, 2.7557319223985893e-06);
+    p = fma(p, r, 2.48015873015873e-05);
+    p = fma(p, r, 0.0001984126984126984);
+    p = fma(p, r, 0.001388888888888889);
+    p = fma(p, r, 0.008333333333333333);
+    p = fma(p, r, 0.041666666666666664);
+    p = fma(p, r, 0.16666666666666666);
+    p = fma(p, r, 0.5);
+    p = fma(p, r, 1.0);
+    p = fma(p, r, 1.0);
+    return scalbn(p, (int)k);
+}
+__device__ __forceinline__ float exp_det_t(float v) { return (float)exp_det((double)v); }
+__device__ __forceinline__ double exp_det_t(double v) { return exp_det(v); }
 __device__ __forceinline__ int to_int_sat(float v) { return __float2int_rz(v); }   // cvt.rzi.s32.f32 saturates
 __device__ __forceinline__ int to_int_sat(double v) { return __double2int_rz(v); }
 __device__ __forceinline__ bool finite_t(float v) { return isfinite(v); }

@@ -84,7 +84,7 @@ __global__ void __launch_bounds__(256) k_det_reduce(const DetArgs a) {
             if (a.mode == DCB_MODE_LINEAR || a.mode == DCB_MODE_SOFT) {
                 const T* mp = (const T*)a.metric.p + n * a.metric.sN + y * a.metric.sH + x * a.metric.sW;
                 const A m = ld<A>(mp);
-                g = a.mode == DCB_MODE_SOFT ? exp_t(m) : m;
+                g = a.mode == DCB_MODE_SOFT ? exp_det_t(m) : m;     // portable exp: bit-identical to the oracle's orc_exp_det
             }
             const T* ip = (const T*)a.in.p + n * a.in.sN + y * a.in.sH + x * a.in.sW;
 #pragma unroll

@@ -134,8 +134,20 @@ class OracleSplatFunc(torch.autograd.Function):
         return gi, gf
 
 
-def softsplat(tenIn, tenFlow, tenMetric, strMode: str):
-    """Mode wrapper, restating controlnet/softsplat.py:232-274 on CPU tensors."""
+def exp_det(t: torch.Tensor) -> torch.Tensor:
+    """exp() as the library's DETERMINISTIC mode computes it (csrc/dcb_common.cuh exp_det: IEEE double operations only,
+    rounded once to the tensor's type): what makes the deterministic `soft` mode bit-comparable across CPU and GPU.
+    Within an ulp of torch's own exp (checked in tests/test_oracle_golden.py)."""
+    a = np.ascontiguousarray(t.detach().numpy())
+    out = np.empty_like(a)
+    fn = getattr(lib(), "orc_exp_det_" + _suffix(a.dtype))
+    fn(_ptr(a), _ptr(out), ctypes.c_longlong(a.size))
+    return torch.from_numpy(out)
+
+
+def softsplat(tenIn, tenFlow, tenMetric, strMode: str, exp_fn=None):
+    """Mode wrapper, restating controlnet/softsplat.py:232-274 on CPU tensors. `exp_fn` (default: torch's exp, as the
+    reference) lets the deterministic-mode tests substitute `exp_det`."""
     base = strMode.split("-")[0]
     assert base in ("sum", "avg", "linear", "soft")
     if strMode in ("sum", "avg"):
@@ -149,7 +161,8 @@ def softsplat(tenIn, tenFlow, tenMetric, strMode: str):
     elif base == "linear":
         tenIn = torch.cat([tenIn * tenMetric, tenMetric], 1)
     elif base == "soft":
-        tenIn = torch.cat([tenIn * tenMetric.exp(), tenMetric.exp()], 1)
+        e = tenMetric.exp() if exp_fn is None else exp_fn(tenMetric)
+        tenIn = torch.cat([tenIn * e, e], 1)
 
     tenOut = OracleSplatFunc.apply(tenIn, tenFlow)
 

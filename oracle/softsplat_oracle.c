@@ -202,6 +202,41 @@ static void* orc_mt_worker(void* arg) {
     return NULL;
 }
 
+/* exp() of the deterministic mode: the same IEEE double operations, in the same order, as exp_det() in the CUDA
+ * library (csrc/dcb_common.cuh): both sides round (float)exp_det((double)m) identically. Compiled with
+ * -ffp-contract=off; every fused operation is an explicit fma(). */
+double orc_exp_det(double x) {
+    if (!(x == x)) return x;
+    if (x > 709.0) return INFINITY;
+    if (x < -745.0) return 0.0;
+    const double k = rint(x * 1.4426950408889634);
+    double r = fma(-k, 6.93147180369123816490e-01, x);
+    r = fma(-k, 1.90821492927058770002e-10, r);
+    double p = 1.6059043836821613e-10;
+    p = fma(p, r, 2.08767569878681e-09);
+    p = fma(p, r, 2.505210838544172e-08);
+    p = fma(p, r, 2.755731922398589e-07);
+    p = fma(p, r, 2.7557319223985893e-06);
+    p = fma(p, r, 2.48015873015873e-05);
+    p = fma(p, r, 0.0001984126984126984);
+    p = fma(p, r, 0.001388888888888889);
+    p = fma(p, r, 0.008333333333333333);
+    p = fma(p, r, 0.041666666666666664);
+    p = fma(p, r, 0.16666666666666666);
+    p = fma(p, r, 0.5);
+    p = fma(p, r, 1.0);
+    p = fma(p, r, 1.0);
+    return scalbn(p, (int)k);
+}
+
+void orc_exp_det_f32(const float* m, float* out, long long n) {
+    for (long long i = 0; i < n; ++i) out[i] = (float)orc_exp_det((double)m[i]);
+}
+
+void orc_exp_det_f64(const double* m, double* out, long long n) {
+    for (long long i = 0; i < n; ++i) out[i] = orc_exp_det(m[i]);
+}
+
 int orc_max_threads(void) {
     long n = sysconf(_SC_NPROCESSORS_ONLN);
     return n > 0 ? (int)n : 1;

@@ -129,3 +129,16 @@ def test_crop_into_tiles_matches_oracle():
         a, ca, sa = d.crop_into_tiles(arr, ts, overlap=ov, order=order)
         b, cb, sb = orc.crop_into_tiles(arr, ts, overlap=ov, order=order)
         assert ca == cb and sa == sb and len(a) == len(b) and all(np.array_equal(x, y) for x, y in zip(a, b))
+
+
+def test_exp_det_is_within_an_ulp_of_libm():
+    """The portable exp of the deterministic mode (orc_exp_det == csrc exp_det): equals the correctly rounded value
+    (float)exp((double)x) on a dense grid and stays within one ulp of torch's float exp."""
+    x = torch.linspace(-40, 40, 100001)
+    a = orc.exp_det(x)
+    assert torch.equal(a, x.double().exp().float())
+    assert int((a.view(torch.int32) - x.exp().view(torch.int32)).abs().max()) <= 1
+    xd = torch.linspace(-700, 700, 20001, dtype=torch.float64)
+    assert float(((orc.exp_det(xd) - xd.exp()).abs() / xd.exp()).max()) < 4e-16
+    s = orc.exp_det(torch.tensor([float("nan"), float("inf"), -float("inf"), 0.0]))
+    assert torch.isnan(s[0]) and s[1] == float("inf") and s[2] == 0 and s[3] == 1

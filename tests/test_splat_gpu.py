@@ -127,16 +127,17 @@ def test_bf16_accumulates_in_fp32(dcb):
     assert out.sum().item() == 4096.0
 
 
-@pytest.mark.parametrize("mode", ["sum", "avg", "linear"])
+@pytest.mark.parametrize("mode", ["sum", "avg", "linear", "soft", "soft-clipeps"])
 def test_deterministic_bit_exact(dcb, orc, mode):
-    """sort-then-reduce mode: identical bits to the sequential oracle and from run to run."""
+    """sort-then-reduce mode: identical bits to the sequential oracle and from run to run -- `soft` included: the
+    deterministic kernels evaluate exp() with IEEE double operations only (exp_det), and so does the oracle here."""
     tin, flow, metric, gout = make_inputs(21, 2, 3, 31, 45, flow_scale=4.0)
     flow[0, :, :8, :8] = 0.0
     ys, xs = torch.meshgrid(torch.arange(31), torch.arange(45), indexing="ij")
     flow[1, 0] = (10.25 - xs).float()                       # frame 1: 1395-way collision
     flow[1, 1] = (9.5 - ys).float()
-    me = metric if mode == "linear" else None
-    ref = orc.softsplat(tin, flow, me, mode)
+    me = metric if mode.split("-")[0] in ("linear", "soft") else None
+    ref = orc.softsplat(tin, flow, me, mode, exp_fn=orc.exp_det)
     with dcb.deterministic(True):
         a = dcb.softsplat(tenIn=tin.cuda(), tenFlow=flow.cuda(), tenMetric=None if me is None else me.cuda(), strMode=mode)
         b = dcb.softsplat(tenIn=tin.cuda(), tenFlow=flow.cuda(), tenMetric=None if me is None else me.cuda(), strMode=mode)

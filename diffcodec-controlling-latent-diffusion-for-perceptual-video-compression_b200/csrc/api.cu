@@ -66,6 +66,7 @@ int bidir_block_bwd_impl(const DcbTensor*, const DcbTensor*, const DcbTensor*, c
                          const DcbTensor*, const DcbTensor*, const DcbTensor*, const DcbTensor*, const DcbTensor*, const DcbTensor*,
                          const DcbTensor*, const DcbTensor*, const DcbTensor*, const DcbTensor*, const DcbTensor*, void*, long long,
                          cudaStream_t);
+int flow_ingest_impl(const DcbTensor* flow, const DcbTensor* out, int mode, cudaStream_t st);
 int convert_impl(const void* src, int src_dtype, void* dst, int dst_dtype, long long n, float scale, cudaStream_t st);
 extern int g_fwd_path;
 bool use_owner(int dtype, int mode, long long C, long long H, long long W);
@@ -148,7 +149,7 @@ const char* dcb_build_info(void) {
     return "libdiffcodec_b200 " __DATE__ " nvcc " DCB_STR(__CUDACC_VER_MAJOR__) "." DCB_STR(__CUDACC_VER_MINOR__)
            " target sm_100a; kernels: k_splat_step k_planar_step k_list_count k_list_alloc k_list_fill k_list_gather k_scatter_planar k_normalize k_bwd_target k_bwd_source "
            "k_backwarp_rows k_backwarp_fwd k_backwarp_bwd k_cast_f32_bf16 k_recipe_fuse k_bidir_fuse_fwd k_bidir_fuse_bwd "
-           "k_det_emit k_det_reduce k_tile_merge k_splat_owner k_strip_box k_convert";
+           "k_det_emit k_det_reduce k_tile_merge k_splat_owner k_strip_box k_convert k_flow_ingest";
 }
 
 int64_t dcb_splat_fwd_workspace_bytes(int64_t N, int64_t C, int64_t H, int64_t W, int32_t dtype, int32_t mode, int32_t flags) {
@@ -533,6 +534,22 @@ int dcb_bidir_block_bwd(const DcbTensor* grad_fused, const DcbTensor* first, con
     TRY(check_block_opt(fn, "grad_metric_b", grad_metric_b, first, 1, dt));
     return bidir_block_bwd_impl(grad_fused, first, last, flow_f, flow_b, metric_f, metric_b, warped_f, warped_b, norm_f, norm_b, occ_f, occ_b,
                                 grad_first, grad_last, grad_metric_f, grad_metric_b, ws, ws_bytes, (cudaStream_t)stream);
+}
+
+int dcb_flow_resize(const DcbTensor* flow, const DcbTensor* out, int32_t convention, void* stream) {
+    const char* fn = "dcb_flow_resize";
+    TRY(check_tensor(fn, "flow", flow, true));
+    TRY(check_tensor(fn, "out", out, true));
+    if (convention < DCB_FLOW_BILINEAR_RESCALE || convention > DCB_FLOW_BILINEAR_NORMALIZE) return set_error(DCB_E_MODE, "%s: unknown convention %d", fn, convention);
+    if (flow->size[1] != 2 || out->size[1] != 2 || out->size[0] != flow->size[0])
+        return set_error(DCB_E_SHAPE, "%s: flow [N,2,H,W] -> out [N,2,th,tw] expected", fn);
+    if (flow->size[0] * flow->size[2] * flow->size[3] == 0 && out->size[0] * out->size[2] * out->size[3] > 0)
+        return set_error(DCB_E_SHAPE, "%s: empty source", fn);
+    TRY(check_limits(fn, flow));
+    TRY(check_limits(fn, out));
+    if (out->dtype != DCB_F32 && out->dtype != DCB_BF16) return set_error(DCB_E_DTYPE, "%s: out must be F32 or BF16", fn);
+    TRY(check_out(fn, "out", out, out->dtype, elem_size(out->dtype)));
+    return flow_ingest_impl(flow, out, convention, (cudaStream_t)stream);
 }
 
 int dcb_convert(const void* src, int32_t src_dtype, void* dst, int32_t dst_dtype, int64_t n, float scale, void* stream) {

@@ -56,6 +56,13 @@ enum {
     DCB_RECIPE_WRAPPER = 1  /* controlnet/residual_utils.py:159-199 (ones metrics + double-hole fill) */
 };
 
+/* flow resampling conventions of dcb_flow_resize */
+enum {
+    DCB_FLOW_BILINEAR_RESCALE = 0,   /* controlnet/utils.py:21-28: bilinear, align_corners=True, u *= tw/W, v *= th/H */
+    DCB_FLOW_ADAPTIVE_AVG = 1,       /* controlnet/dataset.py:43-50: adaptive average pooling, vectors not rescaled */
+    DCB_FLOW_BILINEAR_NORMALIZE = 2  /* controlnet/control_utils.py:74-97: bilinear, align_corners=False, u /= (tw-1)/2, v /= (th-1)/2 */
+};
+
 /* error codes */
 enum {
     DCB_OK = 0,
@@ -266,6 +273,15 @@ int dcb_bidir_block_bwd(const DcbTensor* grad_fused, const DcbTensor* first, con
 int64_t dcb_tile_merge_workspace_bytes(int64_t C, int64_t H, int64_t W, int32_t n_tiles);
 int dcb_tile_merge(const DcbTensor* tiles, const int64_t* pixel_coords, int32_t n_tiles, const DcbTensor* out,
                    int64_t H_px, int64_t W_px, double eps, void* workspace, int64_t workspace_bytes, void* stream);
+
+/*
+ * Flow ingest on the device: resample a flow field [N,2,H,W] (ANY strides -- a raw Middlebury .flo payload uploaded as it is
+ * is the view with strides (2HW, 1, 2W, 2); the dataset reader's planar mis-reshape, controlnet/dataset.py:15-24, is the
+ * view (2HW, HW, W, 1) of the same bytes) to out [N,2,th,tw] (contiguous, F32 or BF16) with one of the three conventions
+ * the reference uses (DCB_FLOW_*). Replaces read_flo + resize_flow_to (controlnet/utils.py:10-28), load_flo_file +
+ * fast_downsample_flow (controlnet/dataset.py:15-50) and resize_and_normalize_flow_batched (controlnet/control_utils.py:74-97).
+ */
+int dcb_flow_resize(const DcbTensor* flow, const DcbTensor* out, int32_t convention, void* stream);
 
 /*
  * Element-type conversion on the device: dst[i] = (dst type)(scale * (float)src[i]) over n contiguous elements.

@@ -399,3 +399,51 @@ def test_fused_block_equals_composition(dcb):
         assert_close(x, y, 2e-5, f"fused block grad {name}")
     with torch.no_grad():                                         # inference path: nothing saved, optional outputs in scratch
         assert_close(dcb.bidirectional_block(first, last, ff, fb, mf, mb), o2, 1e-5, "fused block, no grad")
+
+
+def test_flow_ingest_on_the_device(dcb, tmp_path):
+    """f-2 on the device: the raw .flo payload through ONE kernel (dcb_flow_resize) == the reference's host readers +
+    torch ops (its actual callees): read_flo + resize_flow_to (utils.py:10-28), load_flo_file + fast_downsample_flow
+    (dataset.py:15-50, with the planar mis-reshape), resize_and_normalize_flow_batched (control_utils.py:74-97)."""
+    fio = dcb.flow_io
+    g = torch.Generator().manual_seed(4)
+    for (h, w) in ((96, 160), (135, 241), (64, 64)):
+        flow_hw2 = (torch.randn(h, w, 2, generator=g) * 5).numpy()
+        path = str(tmp_path / f"f_{h}_{w}.flo")
+        fio.write_flo(path, flow_hw2)
+        # de-interleave only
+        assert torch.equal(fio.flo_to_device(path).cpu(), torch.from_numpy(flow_hw2).permute(2, 0, 1)[None])
+        for (th, tw) in ((64, 64), (33, 47), (h, w), (2 * h, 2 * w + 1)):
+            ref = fio.resize_flow_to(fio.read_flo(path), th, tw)                               # utils.py:21-28 on the host
+            assert_close(fio.flo_to_device(path, target_hw=(th, tw)), ref, 2e-6, f"bilinear rescale {h}x{w}->{th}x{tw}")
+            quirk = fio.read_flo(path, planar_quirk=True)                                      # dataset.py:15-24
+            ref = torch.from_numpy(fio.fast_downsample_flow(quirk, th, tw))[None] if th <= h and tw <= w else None
+            if ref is not None:
+                got = fio.flo_to_device(path, target_hw=(th, tw), convention="adaptive_avg", planar_quirk=True)
+                assert_close(got, ref, 2e-6, f"adaptive avg (planar quirk) {h}x{w}->{th}x{tw}")
+    flow = (torch.randn(3, 2, 512, 512, generator=g) * 9).cuda()
+    for r in (64, 32, 16, 8):
+        ref = dcb.resize_and_normalize_flow_batched(flow, r, r)                                # interpolate + 2 divisions + stack
+        assert_close(fio.resize_and_normalize_flow_device(flow, r, r), ref, 2e-6, f"normalise {r}")
+    sliced = torch.randn(2, 4, 70, 90, generator=g).cuda()[:, 1:3]                             # strided view, bf16 output
+    ref = torch.nn.functional.adaptive_avg_pool2d(sliced, (16, 24))
+    assert_close(fio.resize_flow_device(sliced, 16, 24, "adaptive_avg", torch.bfloat16).float(), ref, 1e-2, "strided, bf16 out")
+
+
+def test_flow_ingest_device_matches_reference_golden(dcb, tmp_path):
+    """The device ingest against tests/golden/ref_flow_io.npz (the reference's own functions, oracle/ref_flow_io.py)."""
+    import os
+    from oracle.ref_flow_io import CASES, case_flow
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    z = np.load(os.path.join(root, "tests", "golden", "ref_flow_io.npz"))
+    fio = dcb.flow_io
+    for i, (h, w, th, tw) in enumerate(CASES):
+        path = str(tmp_path / "x.flo")
+        fio.write_flo(path, case_flow(h, w, 100 + i))
+        assert_close(fio.flo_to_device(path, target_hw=(th, tw)), torch.from_numpy(z[f"{i}/resize_flow_to"]), 2e-6, f"case {i} resize_flow_to")
+        if f"{i}/fast_downsample_flow" in z.files:
+            got = fio.flo_to_device(path, target_hw=(th, tw), convention="adaptive_avg", planar_quirk=True)
+            assert_close(got[0], torch.from_numpy(z[f"{i}/fast_downsample_flow"]), 2e-6, f"case {i} fast_downsample_flow")
+    flow = torch.from_numpy(z["batched/in"]).cuda()
+    for r in (64, 32, 16, 8):
+        assert_close(fio.resize_and_normalize_flow_device(flow, r, r), torch.from_numpy(z[f"batched/normalize_{r}"]), 2e-6, f"normalise {r}")

@@ -206,3 +206,25 @@ def test_dropin_extractors_have_the_reference_state_dict():
     d.install()
     from controlnet.extractors import Bi_Dir_FeatureExtractor      # flownet.py:8
     assert Bi_Dir_FeatureExtractor is d.Bi_Dir_FeatureExtractor
+
+
+def test_flow_io_host_helpers_match_the_reference_functions(tmp_path):
+    """tests/golden/ref_flow_io.npz: outputs of the reference's OWN read_flo / resize_flow_to (controlnet/utils.py:10-28),
+    load_flo_file / fast_downsample_flow (controlnet/dataset.py:15-50) and resize_and_normalize_flow_batched
+    (controlnet/control_utils.py:74-97), executed from their source text by oracle/ref_flow_io.py."""
+    import numpy as np
+    import diffcodec_b200 as d
+    from oracle.ref_flow_io import CASES, case_flow
+    z = np.load(os.path.join(ROOT, "tests", "golden", "ref_flow_io.npz"))
+    fio = d.flow_io
+    for i, (h, w, th, tw) in enumerate(CASES):
+        path = str(tmp_path / "x.flo")
+        fio.write_flo(path, case_flow(h, w, 100 + i))
+        assert np.array_equal(fio.read_flo(path), z[f"{i}/read_flo"])
+        assert np.array_equal(fio.read_flo(path, planar_quirk=True), z[f"{i}/load_flo_file"])
+        assert np.array_equal(fio.resize_flow_to(fio.read_flo(path), th, tw).numpy(), z[f"{i}/resize_flow_to"])
+        if f"{i}/fast_downsample_flow" in z.files:
+            assert np.array_equal(fio.fast_downsample_flow(fio.read_flo(path, planar_quirk=True), th, tw), z[f"{i}/fast_downsample_flow"])
+    for r in (64, 32, 16, 8):
+        got = d.resize_and_normalize_flow_batched(torch.from_numpy(z["batched/in"]), r, r).numpy()
+        assert np.array_equal(got, z[f"batched/normalize_{r}"])

@@ -152,6 +152,26 @@ class _bidir_block_func(torch.autograd.Function):
         return g1, g2, None, None, gm1, gm2, None
 
 
+def _block_forward_nograd(first, last, flow_f, flow_b, metric_f, metric_b):
+    """Inference path of the fused block: no autograd node, nothing saved, intermediate maps in library scratch."""
+    lib = _lib.lib()
+    n, c, h, w = first.shape
+    dev, dt = first.device, first.dtype
+    fused = torch.empty((n, c, h, w), dtype=dt, device=dev)
+    acc_b, scr_b, _ = _block_sizes(n, c, h, w, _lib._DTYPES[dt])
+    stream = _lib.stream_ptr(dev)
+    ws_acc = _lib.workspace(dev, acc_b, "acc", stream)
+    ws_scr = _lib.workspace(dev, scr_b, "scratch", stream)
+    D = _lib.desc
+    with _lib.on_device(dev):
+        rc = lib.dcb_bidir_block_fwd(D(first), D(last), D(flow_f), D(flow_b), D(metric_f), D(metric_b), D(fused), None, None, None, None,
+                                     None, None, ws_acc.data_ptr(), ws_acc.numel(), ws_scr.data_ptr(), ws_scr.numel(), _lib.FLAG_WS_CLEAN, stream)
+    if rc != 0:
+        _lib.invalidate_acc(dev)
+    _lib.check(rc, "dcb_bidir_block_fwd")
+    return fused
+
+
 def bidirectional_block(first_features, last_features, flow_f, flow_b, metric_f=None, metric_b=None):
     """masks + both masked soft splats + confidence fusion + double-hole fill of ONE pyramid scale
     (``extractors.py:289-310``), given the two metric maps (``metric_net`` outputs, or None for a warper without one).
@@ -162,6 +182,10 @@ def bidirectional_block(first_features, last_features, flow_f, flow_b, metric_f=
         metric_f = torch.ones_like(flow_f[:, :1], dtype=dt)
     if metric_b is None:
         metric_b = torch.ones_like(flow_b[:, :1], dtype=dt)
+    needs_grad = torch.is_grad_enabled() and (first_features.requires_grad or last_features.requires_grad or metric_f.requires_grad or metric_b.requires_grad)
+    if (not needs_grad and not torch.is_autocast_enabled("cuda") and dt in (torch.float32, torch.bfloat16)
+            and last_features.dtype == dt and flow_f.dtype == dt and flow_b.dtype == dt and metric_f.dtype == dt and metric_b.dtype == dt):
+        return _block_forward_nograd(first_features, last_features, flow_f, flow_b, metric_f, metric_b)
     cast = lambda t: t if t.dtype == dt else t.to(dt)
     return _bidir_block_func.apply(first_features, cast(last_features), cast(flow_f), cast(flow_b), cast(metric_f), cast(metric_b), True)
 

@@ -64,10 +64,20 @@ def test_mode_wrapper_matches_reference(path, mode):
     z = np.load(path)
     r = _run_oracle(z, mode)
     for k, v in r.items():
-        assert np.array_equal(v, z[f"{mode}/{k}"], equal_nan=True), (mode, k)
+        g = z[f"{mode}/{k}"]
+        if k == "gmetric":
+            # the metric gradient ends in torch's own CPU channel reduction (autograd of the pre/post ops), whose summation
+            # order depends on the host's vector width and thread count: bit-exact on the machine that minted the fixtures,
+            # a few ulp elsewhere. Everything that comes out of the restated kernels stays bit-exact.
+            tol = 4e-7 if v.dtype == np.float32 else 1e-15
+            fin = np.isfinite(g)
+            assert np.array_equal(np.isfinite(v), fin), (mode, k)
+            assert np.abs(v[fin] - g[fin]).max(initial=0.0) <= tol * max(1.0, np.abs(g[fin]).max(initial=0.0)), (mode, k)
+            continue
+        assert np.array_equal(v, g, equal_nan=True), (mode, k)
 
 
-GPU_FIXTURES = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "ref_gpu_*.npz")))
+GPU_FIXTURES = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "ref_gpu_*_f??.npz")))
 
 
 def test_gpu_fixtures_present():

@@ -59,7 +59,7 @@ def test_forward_backward_fp64(dcb, orc, mode):
 
 
 FIXTURES = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "ref_emu_*_fast.npz")) +
-                  glob.glob(os.path.join(os.path.dirname(__file__), "golden", "ref_gpu_*.npz")))     # CPU emulation of, and a real B200 run of, the reference
+                  glob.glob(os.path.join(os.path.dirname(__file__), "golden", "ref_gpu_*_f??.npz")))     # CPU emulation of, and a real B200 run of, the reference
 GOLDEN_MODES = ["sum", "avg", "linear", "soft", "avg-zeroeps", "linear-clipeps", "soft-zeroeps", "soft-clipeps", "soft-addeps"]
 
 

@@ -13,8 +13,8 @@ from . import _lib
 from .softsplat import softsplat, softsplat_func, deterministic, is_deterministic
 from .control_utils import compute_mask, FeatureWarperSoftsplat, resize_and_normalize_flow_batched, FDN, zero_module
 from .warp import WarpingLayerBWFlow, backwarp, backwarp_residual
-from .extractors import (bidir_fuse, bidirectional_warp_fuse, bidirectional_block, Bi_Dir_FeatureExtractor, Bi_Dir_ResidueExtractor,
-                         WarpExtractor, ConvBlock)
+from .extractors import (bidir_fuse, bidirectional_warp_fuse, bidirectional_block, bidirectional_pyramid, pyramid_conditioning, resample_batch,
+                         Bi_Dir_FeatureExtractor, Bi_Dir_ResidueExtractor, WarpExtractor, ConvBlock)
 from .residual_utils import residual_conditioning, ResidueDataset, WarpingDatasetWrapper
 from .sharding import UVG_SEQUENCES, GopUnit, enumerate_gops, shard_units, gather_checksums, gather_outputs, checksum
 from .host import softsplat_host, bind_to_gpu_numa

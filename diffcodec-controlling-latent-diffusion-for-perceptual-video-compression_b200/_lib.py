@@ -24,6 +24,8 @@ EPS_ADD, EPS_ZERO, EPS_CLIP = 0, 1, 2
 FLAG_DETERMINISTIC, FLAG_WS_CLEAN = 1, 2
 RECIPE_DATASET, RECIPE_WRAPPER = 0, 1
 FLOW_BILINEAR_RESCALE, FLOW_ADAPTIVE_AVG, FLOW_BILINEAR_NORMALIZE = 0, 1, 2
+PYRAMID_NO_MASKS = 4
+RESAMPLE_NONE, RESAMPLE_MUL, RESAMPLE_DIV = 0, 1, 2
 
 E_NULL, E_SHAPE, E_DTYPE, E_MODE, E_WORKSPACE, E_LIMIT, E_ALIGN = -1, -2, -3, -4, -5, -6, -7
 
@@ -79,6 +81,9 @@ SYMBOLS = {
     "dcb_bidir_block_fwd": (ctypes.c_int, [_P] * 13 + [ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p, ctypes.c_int64, ctypes.c_int32, ctypes.c_void_p]),
     "dcb_bidir_block_bwd": (ctypes.c_int, [_P] * 17 + [ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p]),
     "dcb_flow_resize": (ctypes.c_int, [_P, _P, ctypes.c_int32, ctypes.c_void_p]),
+    "dcb_bidir_pyramid_workspace_bytes": (ctypes.c_int64, [ctypes.c_void_p, ctypes.c_int32]),
+    "dcb_bidir_pyramid_fwd": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int32, ctypes.c_void_p, ctypes.c_int64, ctypes.c_int32, ctypes.c_void_p]),
+    "dcb_resample_batch": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int32, ctypes.c_void_p]),
     "dcb_convert": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int32, ctypes.c_void_p, ctypes.c_int32, ctypes.c_int64, ctypes.c_float, ctypes.c_void_p]),
     "dcb_residual_fused": (ctypes.c_int, [_P] * 8 + [ctypes.c_void_p, ctypes.c_int64, ctypes.c_int32, ctypes.c_int32, ctypes.c_void_p]),
 }
@@ -178,6 +183,71 @@ def desc(t: torch.Tensor | None):
     if t.dtype not in _DTYPES:
         raise ValueError(f"unsupported dtype {t.dtype}: float32, bfloat16 and float64 are implemented")
     return _pack_desc(t.data_ptr(), _DTYPES[t.dtype], 0, *t.shape, *t.stride())
+
+
+# -------------------------------------------------------------------------------------------------
+# array arguments (DcbPyramidLevel[], DcbResampleJob[]): descriptors and the arrays that point at them live in one
+# per-thread ctypes buffer, so a whole pyramid costs one pack per tensor and no ctypes.Structure objects
+# -------------------------------------------------------------------------------------------------
+_tls = threading.local()
+_DESC_BYTES = _DESC_STRUCT.size            # 80
+_LEVEL_STRUCT = struct.Struct("13P")       # DcbPyramidLevel: 6 descriptor pointers + 7 raw output pointers
+_JOB_STRUCT = struct.Struct("PPiiff")      # DcbResampleJob
+_ARENA_BYTES = 1 << 14
+
+
+def _arena():
+    a = getattr(_tls, "arena", None)
+    if a is None:
+        buf = ctypes.create_string_buffer(_ARENA_BYTES)
+        a = _tls.arena = (buf, ctypes.addressof(buf))
+    return a
+
+
+def _tensor_fields(t: torch.Tensor):
+    if not t.is_cuda:
+        raise AssertionError("diffcodec_b200 runs on CUDA tensors only (the reference asserts the same, softsplat.py:347-348)")
+    if t.dim() != 4:
+        raise AssertionError(f"expected a 4-d NCHW tensor, got {tuple(t.shape)}")
+    if t.dtype not in _DTYPES:
+        raise ValueError(f"unsupported dtype {t.dtype}: float32, bfloat16 and float64 are implemented")
+    return (t.data_ptr(), _DTYPES[t.dtype], 0, *t.shape, *t.stride())
+
+
+def pack_pyramid(levels, outputs):
+    """levels: per scale (first, last, flow_f, flow_b, metric_f | None, metric_b | None); outputs: per scale 7 tensors or None
+    (fused, warped_f, warped_b, norm_f, norm_b, occ_f, occ_b). Returns the address of a DcbPyramidLevel[len(levels)] that
+    stays valid until the next pack_* call of this thread."""
+    buf, base = _arena()
+    n = len(levels)
+    off = n * _LEVEL_STRUCT.size
+    assert off + n * 6 * _DESC_BYTES <= _ARENA_BYTES
+    for l, (ins, outs) in enumerate(zip(levels, outputs)):
+        ptrs = []
+        for t in ins:
+            if t is None:
+                ptrs.append(0)
+            else:
+                _pack_desc_into(buf, off, *_tensor_fields(t))
+                ptrs.append(base + off)
+                off += _DESC_BYTES
+        ptrs += [0 if o is None else o.data_ptr() for o in outs]
+        _LEVEL_STRUCT.pack_into(buf, l * _LEVEL_STRUCT.size, *ptrs)
+    return base
+
+
+def pack_resample(jobs):
+    """jobs: (src, dst, align_corners, op, factor0, factor1). Returns the address of a DcbResampleJob[len(jobs)]."""
+    buf, base = _arena()
+    n = len(jobs)
+    off = (n * _JOB_STRUCT.size + 15) // 16 * 16
+    assert off + n * 2 * _DESC_BYTES <= _ARENA_BYTES
+    for j, (src, dst, align, op, f0, f1) in enumerate(jobs):
+        _pack_desc_into(buf, off, *_tensor_fields(src))
+        _pack_desc_into(buf, off + _DESC_BYTES, *_tensor_fields(dst))
+        _JOB_STRUCT.pack_into(buf, j * _JOB_STRUCT.size, base + off, base + off + _DESC_BYTES, int(bool(align)), int(op), float(f0), float(f1))
+        off += 2 * _DESC_BYTES
+    return base
 
 
 _raw_stream = getattr(torch._C, "_cuda_getCurrentRawStream", None)

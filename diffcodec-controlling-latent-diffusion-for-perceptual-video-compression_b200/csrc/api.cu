@@ -67,6 +67,9 @@ int bidir_block_bwd_impl(const DcbTensor*, const DcbTensor*, const DcbTensor*, c
                          const DcbTensor*, const DcbTensor*, const DcbTensor*, const DcbTensor*, const DcbTensor*, void*, long long,
                          cudaStream_t);
 int flow_ingest_impl(const DcbTensor* flow, const DcbTensor* out, int mode, cudaStream_t st);
+long long pyramid_workspace(const DcbPyramidLevel* lv, int n);
+int bidir_pyramid_fwd_impl(const DcbPyramidLevel* lv, int n, void* ws, int flags, cudaStream_t st);
+int resample_batch_impl(const DcbResampleJob* jobs, int n_jobs, cudaStream_t st);
 int convert_impl(const void* src, int src_dtype, void* dst, int dst_dtype, long long n, float scale, cudaStream_t st);
 extern int g_fwd_path;
 bool use_owner(int dtype, int mode, long long C, long long H, long long W);
@@ -149,7 +152,7 @@ const char* dcb_build_info(void) {
     return "libdiffcodec_b200 " __DATE__ " nvcc " DCB_STR(__CUDACC_VER_MAJOR__) "." DCB_STR(__CUDACC_VER_MINOR__)
            " target sm_100a; kernels: k_splat_step k_planar_step k_list_count k_list_alloc k_list_fill k_list_gather k_scatter_planar k_normalize k_bwd_target k_bwd_source "
            "k_backwarp_rows k_backwarp_fwd k_backwarp_bwd k_cast_f32_bf16 k_recipe_fuse k_bidir_fuse_fwd k_bidir_fuse_bwd "
-           "k_det_emit k_det_reduce k_tile_merge k_splat_owner k_strip_box k_convert k_flow_ingest";
+           "k_det_emit k_det_reduce k_tile_merge k_splat_owner k_strip_box k_convert k_flow_ingest k_pyr_scatter k_pyr_fuse k_resample_batch";
 }
 
 int64_t dcb_splat_fwd_workspace_bytes(int64_t N, int64_t C, int64_t H, int64_t W, int32_t dtype, int32_t mode, int32_t flags) {
@@ -534,6 +537,85 @@ int dcb_bidir_block_bwd(const DcbTensor* grad_fused, const DcbTensor* first, con
     TRY(check_block_opt(fn, "grad_metric_b", grad_metric_b, first, 1, dt));
     return bidir_block_bwd_impl(grad_fused, first, last, flow_f, flow_b, metric_f, metric_b, warped_f, warped_b, norm_f, norm_b, occ_f, occ_b,
                                 grad_first, grad_last, grad_metric_f, grad_metric_b, ws, ws_bytes, (cudaStream_t)stream);
+}
+
+static int check_pyramid(const char* fn, const DcbPyramidLevel* lv, int32_t n) {
+    if (n < 0 || n > 4) return set_error(DCB_E_LIMIT, "%s: %d levels (at most 4 per call)", fn, n);
+    if (n > 0 && !lv) return set_error(DCB_E_NULL, "%s: levels is required", fn);
+    for (int l = 0; l < n; ++l) {
+        const DcbPyramidLevel& d = lv[l];
+        TRY(check_tensor(fn, "first", d.first, true));
+        TRY(check_tensor(fn, "last", d.last, true));
+        TRY(check_tensor(fn, "flow_f", d.flow_f, true));
+        TRY(check_tensor(fn, "flow_b", d.flow_b, true));
+        TRY(check_tensor(fn, "metric_f", d.metric_f, false));
+        TRY(check_tensor(fn, "metric_b", d.metric_b, false));
+        const long long N = d.first->size[0], C = d.first->size[1], H = d.first->size[2], W = d.first->size[3];
+        TRY(check_limits(fn, d.first));
+        TRY(check_shape(fn, "last", d.last, N, C, H, W));
+        TRY(check_shape(fn, "flow_f", d.flow_f, N, 2, H, W));
+        TRY(check_shape(fn, "flow_b", d.flow_b, N, 2, H, W));
+        TRY(check_shape(fn, "metric_f", d.metric_f, N, 1, H, W));
+        TRY(check_shape(fn, "metric_b", d.metric_b, N, 1, H, W));
+        const int dt = d.first->dtype;
+        if (dt != DCB_F32 && dt != DCB_BF16) return set_error(DCB_E_DTYPE, "%s: F32 or BF16 only, got %d", fn, dt);
+        if (dt != lv[0].first->dtype || d.last->dtype != dt || d.flow_f->dtype != dt || d.flow_b->dtype != dt ||
+            (d.metric_f && d.metric_f->dtype != dt) || (d.metric_b && d.metric_b->dtype != dt))
+            return set_error(DCB_E_DTYPE, "%s: all tensors of all levels must share one dtype", fn);
+        const DcbTensor* in32[6] = {d.first, d.last, d.flow_f, d.flow_b, d.metric_f, d.metric_b};
+        for (int i = 0; i < 6; ++i) {
+            if (!in32[i]) continue;
+            long long span = 0;
+            for (int k = 0; k < 4; ++k) span += (in32[i]->size[k] - 1) * (in32[i]->stride[k] < 0 ? -in32[i]->stride[k] : in32[i]->stride[k]);
+            if (span >= (1ll << 31)) return set_error(DCB_E_LIMIT, "%s: level %d: a tensor spans 2^31 elements or more", fn, l);
+        }
+        if (N * C * H * W > 0 && !d.fused) return set_error(DCB_E_NULL, "%s: level %d: fused is required", fn, l);
+        void* outs[7] = {d.fused, d.warped_f, d.warped_b, d.norm_f, d.norm_b, d.occ_f, d.occ_b};
+        for (int i = 0; i < 7; ++i)                                   // norm_f / norm_b are fp32 whatever the tensor dtype
+            if ((uintptr_t)outs[i] % (uintptr_t)((i == 3 || i == 4) ? 4 : elem_size(dt)))
+                return set_error(DCB_E_ALIGN, "%s: level %d: output %d is not aligned to its element size", fn, l, i);
+    }
+    return DCB_OK;
+}
+
+int64_t dcb_bidir_pyramid_workspace_bytes(const DcbPyramidLevel* levels, int32_t n_levels) {
+    if (!levels || n_levels <= 0 || n_levels > 4) return 0;
+    for (int l = 0; l < n_levels; ++l)
+        if (!levels[l].first) return 0;
+    return (int64_t)pyramid_workspace(levels, n_levels);
+}
+
+int dcb_bidir_pyramid_fwd(const DcbPyramidLevel* levels, int32_t n_levels, void* ws, int64_t ws_bytes, int32_t flags, void* stream) {
+    const char* fn = "dcb_bidir_pyramid_fwd";
+    if (flags & ~(DCB_FLAG_WS_CLEAN | DCB_PYRAMID_NO_MASKS)) return set_error(DCB_E_MODE, "%s: unknown flags 0x%x", fn, flags);
+    TRY(check_pyramid(fn, levels, n_levels));
+    if (n_levels == 0) return DCB_OK;
+    const long long need = pyramid_workspace(levels, n_levels);
+    if (need > 0 && (!ws || ws_bytes < need || ((uintptr_t)ws & 255)))
+        return set_error(DCB_E_WORKSPACE, "%s: workspace of %lld bytes (256 B aligned) required, got %lld", fn, need, (long long)ws_bytes);
+    return bidir_pyramid_fwd_impl(levels, n_levels, ws, flags, (cudaStream_t)stream);
+}
+
+int dcb_resample_batch(const DcbResampleJob* jobs, int32_t n_jobs, void* stream) {
+    const char* fn = "dcb_resample_batch";
+    if (n_jobs < 0) return set_error(DCB_E_SHAPE, "%s: n_jobs = %d", fn, n_jobs);
+    if (n_jobs > 0 && !jobs) return set_error(DCB_E_NULL, "%s: jobs is required", fn);
+    for (int j = 0; j < n_jobs; ++j) {
+        const DcbTensor* s = jobs[j].src; const DcbTensor* d = jobs[j].dst;
+        TRY(check_tensor(fn, "src", s, true));
+        TRY(check_tensor(fn, "dst", d, true));
+        if ((s->dtype != DCB_F32 && s->dtype != DCB_BF16) || (d->dtype != DCB_F32 && d->dtype != DCB_BF16))
+            return set_error(DCB_E_DTYPE, "%s: job %d: F32 or BF16 only", fn, j);
+        if (s->size[0] != d->size[0] || s->size[1] != d->size[1])
+            return set_error(DCB_E_SHAPE, "%s: job %d: src [N,C,H,W] -> dst [N,C,th,tw] expected", fn, j);
+        if (s->size[2] * s->size[3] == 0 && d->size[0] * d->size[1] * d->size[2] * d->size[3] > 0)
+            return set_error(DCB_E_SHAPE, "%s: job %d: empty source", fn, j);
+        TRY(check_limits(fn, s));
+        TRY(check_limits(fn, d));
+        TRY(check_out(fn, "dst", d, d->dtype, elem_size(d->dtype)));
+        if (jobs[j].op < DCB_RESAMPLE_NONE || jobs[j].op > DCB_RESAMPLE_DIV) return set_error(DCB_E_MODE, "%s: job %d: unknown op %d", fn, j, jobs[j].op);
+    }
+    return resample_batch_impl(jobs, n_jobs, (cudaStream_t)stream);
 }
 
 int dcb_flow_resize(const DcbTensor* flow, const DcbTensor* out, int32_t convention, void* stream) {

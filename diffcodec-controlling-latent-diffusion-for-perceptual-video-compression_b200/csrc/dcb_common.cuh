@@ -175,6 +175,14 @@ __device__ __forceinline__ void red_add_v2(float* p, float a, float b) {
     asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(p), "f"(a), "f"(b) : "memory");
 }
 
+// occlusion test of compute_mask (controlnet/control_utils.py:15-16) on the soft splat (wx, wy) / (d + 1e-7) of one motion
+// field, compared with the other field (mx, my) at the same pixel: ||m + w|| > 0.3
+__device__ __forceinline__ float occlusion(float wx, float wy, float d, float mx, float my) {
+    const float n = add_rn(d, 0.0000001f);
+    const float ex = add_rn(mx, wx / n), ey = add_rn(my, wy / n);
+    return sqrtf(add_rn(mul_rn(ex, ex), mul_rn(ey, ey))) > 0.3f ? 1.f : 0.f;
+}
+
 // Bilinear footprint of one source pixel: softsplat.py:298-318 (and :386-404, :457-470).
 template <class A> struct Foot {
     A fx, fy;        // landing position

@@ -382,11 +382,7 @@ __device__ __forceinline__ void normalize_chunk_v2(const PipeArgs& a, int frame,
 // occlusion epilogue (compute_mask, controlnet/control_utils.py:11-17): the accumulators hold the
 // soft splat of a 2-channel flow (x*e, y*e, e); mask = (||motion + splat/(norm + 1e-7)||_2 > 0.3)
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ float occlusion(float wx, float wy, float d, float mx, float my) {
-    const float n = add_rn(d, 0.0000001f);
-    const float ex = add_rn(mx, wx / n), ey = add_rn(my, wy / n);
-    return sqrtf(add_rn(mul_rn(ex, ex), mul_rn(ey, ey))) > 0.3f ? 1.f : 0.f;
-}
+// occlusion(): dcb_common.cuh
 
 template <class T>
 __device__ __forceinline__ void mask_chunk(const PipeArgs& a, int frame, int chunk, float* acc, int lane) {

@@ -190,6 +190,164 @@ def bidirectional_block(first_features, last_features, flow_f, flow_b, metric_f=
     return _bidir_block_func.apply(first_features, cast(last_features), cast(flow_f), cast(flow_b), cast(metric_f), cast(metric_b), True)
 
 
+# -------------------------------------------------------------------------------------------------
+# whole pyramids: every scale of one forward in one library call (csrc/pyramid.cu)
+# -------------------------------------------------------------------------------------------------
+def resample_batch(jobs):
+    """Bilinear resampling of several tensors to several sizes in ONE launch (``dcb_resample_batch``).
+    jobs: (src [N,C,H,W], (th, tw), align_corners, op, factor0, factor1[, dtype]) with op one of ``_lib.RESAMPLE_*``;
+    returns the list of resampled tensors. No autograd (the pyramids resample inputs, not activations)."""
+    packed, outs = [], []
+    for job in jobs:
+        src, (th, tw), align, op, f0, f1 = job[:6]
+        dt = job[6] if len(job) > 6 else src.dtype
+        dst = torch.empty((src.shape[0], src.shape[1], th, tw), dtype=dt, device=src.device)
+        packed.append((src, dst, align, op, f0, f1)); outs.append(dst)
+    if packed:
+        dev = packed[0][0].device
+        with _lib.on_device(dev):
+            _lib.check(_lib.lib().dcb_resample_batch(_lib.pack_resample(packed), len(packed), _lib.stream_ptr(dev)), "dcb_resample_batch")
+    return outs
+
+
+_pyr_ws: dict = {}
+_lib._option_hooks.append(_pyr_ws.clear)
+
+
+def _pyramid_forward(levels, flags, want_saved, want_warped=False):
+    """levels: per scale (first, last, flow_f, flow_b, metric_f | None, metric_b | None), one dtype. One dcb_bidir_pyramid_fwd
+    call: two kernel launches for the whole pyramid. Returns (fused list, per-scale saved tensors or None)."""
+    lib = _lib.lib()
+    dev, dt = levels[0][0].device, levels[0][0].dtype
+    outs, fused, saved = [], [], []
+    for first, *_ in levels:
+        n, c, h, w = first.shape
+        f = torch.empty((n, c, h, w), dtype=dt, device=dev)
+        fused.append(f)
+        if want_saved:
+            warped = torch.empty((2, n, c, h, w), dtype=dt, device=dev)
+            planes = torch.empty((2, n, 1, h, w), dtype=torch.float32, device=dev)
+            occ = torch.empty((2, n, 1, h, w), dtype=dt, device=dev)
+            sv = (warped[0], warped[1], planes[0], planes[1], occ[0], occ[1])
+        elif want_warped:
+            warped = torch.empty((2, n, c, h, w), dtype=dt, device=dev)
+            sv = (warped[0], warped[1], None, None, None, None)
+        else:
+            sv = (None,) * 6
+        saved.append(sv)
+        outs.append((f,) + sv)
+    stream = _lib.stream_ptr(dev)
+    with _lib.on_device(dev):
+        arr = _lib.pack_pyramid(levels, outs)
+        key = (tuple(tuple(lv[0].shape) for lv in levels), dt)
+        need = _pyr_ws.get(key)
+        if need is None:
+            need = _pyr_ws[key] = int(lib.dcb_bidir_pyramid_workspace_bytes(arr, len(levels)))
+        ws = _lib.workspace(dev, need, "acc", stream)
+        rc = lib.dcb_bidir_pyramid_fwd(arr, len(levels), ws.data_ptr(), ws.numel(), flags | _lib.FLAG_WS_CLEAN, stream)
+    if rc != 0:
+        _lib.invalidate_acc(dev)
+    _lib.check(rc, "dcb_bidir_pyramid_fwd")
+    return fused, saved
+
+
+class _bidir_pyramid_func(torch.autograd.Function):
+    """All scales of a bi-directional conditioning pyramid as ONE autograd node: one library call forward (two launches),
+    one dcb_bidir_block_bwd call per scale backward. Inputs per scale: first, last, flow_f, flow_b, metric_f, metric_b."""
+
+    @staticmethod
+    @torch.amp.custom_fwd(device_type="cuda", cast_inputs=torch.float32)       # the splats run in fp32 (control_utils.py:61)
+    def forward(ctx, *tensors):
+        levels = [tuple(tensors[i:i + 6]) for i in range(0, len(tensors), 6)]
+        need = any(ctx.needs_input_grad[6 * l + k] for l in range(len(levels)) for k in (0, 1, 4, 5))
+        fused, saved = _pyramid_forward(levels, 0, need)
+        ctx.n_levels = len(levels)
+        if need:
+            flat = []
+            for lv, sv in zip(levels, saved):
+                flat += list(lv) + list(sv)
+            ctx.save_for_backward(*flat)
+        return tuple(fused)
+
+    @staticmethod
+    @torch.amp.custom_bwd(device_type="cuda")
+    def backward(ctx, *grads):
+        lib = _lib.lib()
+        t = ctx.saved_tensors
+        res = []
+        D = _lib.desc
+        for l in range(ctx.n_levels):
+            first, last, flow_f, flow_b, metric_f, metric_b, wf, wb, nf, nb, of, ob = t[12 * l:12 * l + 12]
+            need = ctx.needs_input_grad[6 * l:6 * l + 6]
+            g = grads[l]
+            if g is None or not any(need[k] for k in (0, 1, 4, 5)):
+                res += [None] * 6
+                continue
+            n, c, h, w = first.shape
+            dev, dt = first.device, first.dtype
+            g = g.to(dt)
+            g1 = torch.empty_like(first, memory_format=torch.contiguous_format) if need[0] else None
+            g2 = torch.empty_like(last, memory_format=torch.contiguous_format) if need[1] else None
+            gm1 = torch.empty((n, 1, h, w), dtype=dt, device=dev) if need[4] else None
+            gm2 = torch.empty((n, 1, h, w), dtype=dt, device=dev) if need[5] else None
+            ws = _lib.workspace(dev, _block_sizes(n, c, h, w, _lib._DTYPES[dt])[2], "scratch")
+            with _lib.on_device(dev):
+                rc = lib.dcb_bidir_block_bwd(D(g), D(first), D(last), D(flow_f), D(flow_b), D(metric_f), D(metric_b), D(wf), D(wb), D(nf), D(nb),
+                                             D(of), D(ob), D(g1), D(g2), D(gm1), D(gm2), ws.data_ptr(), ws.numel(), _lib.stream_ptr(dev))
+            _lib.check(rc, "dcb_bidir_block_bwd")
+            res += [g1, g2, None, None, gm1, gm2]
+        return tuple(res)
+
+
+_PYRAMID_MAX_LEVELS = 4
+
+
+def bidirectional_pyramid(levels):
+    """Every scale of ``Bi_Dir_FeatureExtractor.forward`` between the conv stacks (``extractors.py:282-310``) in one call:
+    levels = [(first, last, flow_f, flow_b, metric_f | None, metric_b | None), ...] -> [fused, ...]. Two kernel launches
+    for the whole pyramid, no host sync; gradients reach the features and the metrics (not the flows)."""
+    levels = [tuple(lv) for lv in levels]
+    if len(levels) > _PYRAMID_MAX_LEVELS:
+        return bidirectional_pyramid(levels[:_PYRAMID_MAX_LEVELS]) + bidirectional_pyramid(levels[_PYRAMID_MAX_LEVELS:])
+    dt = levels[0][0].dtype
+    grad = torch.is_grad_enabled() and any(t is not None and t.requires_grad for lv in levels for t in lv)
+    plain = (not grad and not torch.is_autocast_enabled("cuda") and dt in (torch.float32, torch.bfloat16)
+             and all(t is None or t.dtype == dt for lv in levels for t in lv))
+    if plain:
+        return _pyramid_forward(levels, 0, False)[0]
+    flat = []
+    for first, last, ff, fb, mf, mb in levels:
+        d = first.dtype
+        cast = lambda t: t if t.dtype == d else t.to(d)
+        mf = torch.ones_like(ff[:, :1], dtype=d) if mf is None else mf          # the backward entry wants the metric tensors
+        mb = torch.ones_like(fb[:, :1], dtype=d) if mb is None else mb
+        flat += [first, cast(last), cast(ff), cast(fb), cast(mf), cast(mb)]
+    return list(_bidir_pyramid_func.apply(*flat))
+
+
+def pyramid_conditioning(img1, img2, flow1, flow2, sizes=(128, 64, 32)):
+    """The multi-scale conditioning loop of ``improv_experiments.ipynb`` cell 5: per size,
+    both frames resized (bilinear, align_corners=False), both flows resized and scaled by size / W, each frame soft-splatted
+    by its flow with an all-ones metric, the two warps fused by ``soft_fuse`` with identity masks (cell 3). The reference runs
+    ~30 eager kernels and 2 NVRTC lookups per size; here: one resampling launch for all 4 x len(sizes) resizes, then ONE
+    pyramid call (two launches). Returns [(warped1, warped2, fused), ...] per size."""
+    assert img1.is_cuda and img1.shape == img2.shape and flow1.shape == flow2.shape
+    dt = img1.dtype
+    out = []
+    for s0 in range(0, len(sizes), _PYRAMID_MAX_LEVELS):
+        chunk = sizes[s0:s0 + _PYRAMID_MAX_LEVELS]
+        jobs = []
+        for size in chunk:
+            scale = float(size) / float(flow1.shape[-1])
+            jobs += [(img1, (size, size), False, _lib.RESAMPLE_NONE, 1.0, 1.0), (img2, (size, size), False, _lib.RESAMPLE_NONE, 1.0, 1.0),
+                     (flow1, (size, size), False, _lib.RESAMPLE_MUL, scale, scale, dt), (flow2, (size, size), False, _lib.RESAMPLE_MUL, scale, scale, dt)]
+        r = resample_batch(jobs)
+        levels = [(r[4 * i], r[4 * i + 1], r[4 * i + 2], r[4 * i + 3], None, None) for i in range(len(chunk))]
+        fused, saved = _pyramid_forward(levels, _lib.PYRAMID_NO_MASKS, False, want_warped=True)
+        out += [(sv[0], sv[1], f) for f, sv in zip(fused, saved)]
+    return out
+
+
 def _block_fusable(first, last, flow_f, flow_b):
     from .softsplat import is_deterministic
     return (first.is_cuda and first.shape == last.shape and first.dtype in (torch.float32, torch.bfloat16, torch.float16)
@@ -272,15 +430,44 @@ class Bi_Dir_FeatureExtractor(nn.Module):
         first_features = self.first_pre_extractor(local_conditions[:, 3:])      # extractors.py:266-272
         last_features = self.last_pre_extractor(local_conditions[:, :3])
         flow_fwd, flow_bwd = flow[:, :2], flow[:, 2:]
-        outs = []
-        for idx, res in enumerate((64, 32, 16, 8)):                              # extractors.py:278
+        flow_res = (64, 32, 16, 8)                                               # extractors.py:278
+        from .softsplat import is_deterministic
+        whole = (first_features.is_cuda and flow.dtype in (torch.float32, torch.bfloat16)
+                 and not (torch.is_grad_enabled() and flow.requires_grad) and not is_deterministic())
+        if not whole:                                                            # flows that carry a gradient: scale by scale
+            outs = []
+            for idx, res in enumerate(flow_res):
+                first_features = self.extractors_first[idx](first_features)
+                last_features = self.extractors_last[idx](last_features)
+                flow_f = resize_and_normalize_flow_batched(flow_fwd, res, res)
+                flow_b = resize_and_normalize_flow_batched(flow_bwd, res, res)
+                fused = bidirectional_warp_fuse(first_features, last_features, flow_f, flow_b, self.wrapper[idx])
+                outs.append(self.zero_convs[idx](fused))
+            return outs
+        # The conv chains of the two frames do not depend on the fused maps, so they run first; then all eight flow resizes are
+        # one launch (resize_and_normalize_flow_batched, control_utils.py:74-97: divide by ((w - 1) / 2, (h - 1) / 2)) and the
+        # motion compensation of all four scales is one call (two launches) instead of 16 splats + 4 host syncs.
+        feats = []
+        for idx in range(len(flow_res)):
             first_features = self.extractors_first[idx](first_features)
             last_features = self.extractors_last[idx](last_features)
-            flow_f = resize_and_normalize_flow_batched(flow_fwd, res, res)
-            flow_b = resize_and_normalize_flow_batched(flow_bwd, res, res)
-            fused = bidirectional_warp_fuse(first_features, last_features, flow_f, flow_b, self.wrapper[idx])
-            outs.append(self.zero_convs[idx](fused))
-        return outs
+            feats.append((first_features, last_features))
+        with torch.no_grad():
+            jobs = []
+            for (f, _), res in zip(feats, flow_res):
+                dt = torch.float32 if (torch.is_autocast_enabled("cuda") or f.dtype not in (torch.float32, torch.bfloat16)) else f.dtype
+                for fl in (flow_fwd, flow_bwd):
+                    jobs.append((fl, (res, res), False, _lib.RESAMPLE_DIV, (res - 1) / 2.0, (res - 1) / 2.0, dt))
+            flows = resample_batch(jobs)
+        levels = []
+        for idx, (f, l) in enumerate(feats):
+            learn = getattr(self.wrapper[idx], "with_learnable_metric", False)
+            mf = self.wrapper[idx].metric_net(f) if learn else None
+            mb = self.wrapper[idx].metric_net(l) if learn else None
+            levels.append((f, l, flows[2 * idx], flows[2 * idx + 1], mf, mb))
+        with torch.autocast(device_type="cuda", enabled=False):
+            fused = bidirectional_pyramid(levels)
+        return [zc(x) for zc, x in zip(self.zero_convs, fused)]
 
 
 class Bi_Dir_ResidueExtractor(nn.Module):

@@ -258,6 +258,46 @@ int dcb_bidir_block_bwd(const DcbTensor* grad_fused, const DcbTensor* first, con
                         const DcbTensor* grad_metric_b, void* workspace, int64_t workspace_bytes, void* stream);
 
 /*
+ * The motion compensation of a WHOLE conditioning pyramid -- every scale of one forward -- in ONE call and TWO kernel
+ * launches (all scatter jobs of all scales; then masks + normalisation + (1 - mask) + confidence fusion + hole fill of all
+ * scales), plus one memset. Per scale the arithmetic is that of dcb_bidir_block_fwd. Replaces, for the four scales of
+ * Bi_Dir_FeatureExtractor.forward, controlnet/extractors.py:282-310 (16 softsplat() calls, 4 host syncs), and with
+ * DCB_PYRAMID_NO_MASKS the multi-scale loop of improv_experiments.ipynb cell 5 (soft splat of both frames per scale +
+ * soft_fuse with identity masks, cell 3: no occlusion test, no (1 - mask), no holes).
+ *
+ *   levels[l].first, last [N,C,H,W]; flow_f, flow_b [N,2,H,W] at the level's resolution; metric_f, metric_b [N,1,H,W]
+ *   or NULL = all-ones (never materialised); one dtype (F32 or BF16) for all tensors of all levels
+ *   outputs are raw device pointers to NCHW-contiguous buffers of the level's shape and dtype (norm_*: F32):
+ *   fused (required); warped_*, norm_*, occ_* optional (NULL = never stored; dcb_bidir_block_bwd needs all six)
+ *   n_levels <= 4;  workspace: dcb_bidir_pyramid_workspace_bytes(), DCB_FLAG_WS_CLEAN protocol as dcb_splat_fwd
+ */
+typedef struct DcbPyramidLevel {
+    const DcbTensor *first, *last, *flow_f, *flow_b, *metric_f, *metric_b;
+    void *fused, *warped_f, *warped_b, *norm_f, *norm_b, *occ_f, *occ_b;
+} DcbPyramidLevel;
+enum { DCB_PYRAMID_NO_MASKS = 4 /* flag of dcb_bidir_pyramid_fwd */ };
+int64_t dcb_bidir_pyramid_workspace_bytes(const DcbPyramidLevel* levels, int32_t n_levels);
+int dcb_bidir_pyramid_fwd(const DcbPyramidLevel* levels, int32_t n_levels, void* workspace, int64_t workspace_bytes,
+                          int32_t flags, void* stream);
+
+/*
+ * Batched bilinear resampling: every (tensor, scale) pair of a pyramid in ONE launch. dst[j] [N,C,th,tw] (contiguous, F32
+ * or BF16) = bilinear(src[j] [N,C,H,W], any strides), then channel 0 (op) factor0 and every other channel (op) factor1.
+ * The index and weight arithmetic is torch's upsample_bilinear2d (fp32, same operation order). Replaces the
+ * F.interpolate calls in front of the splats: resize_and_normalize_flow_batched (controlnet/control_utils.py:74-97:
+ * align_corners = 0, DIV by ((tw - 1) / 2, (th - 1) / 2)), extractors.py:182-183 (align_corners = 0, DIV by H // res),
+ * improv_experiments.ipynb cell 5 (frames: NONE; flows: MUL by size / W), controlnet/utils.py:21-28 (align_corners = 1,
+ * MUL by (tw / W, th / H)).
+ */
+enum { DCB_RESAMPLE_NONE = 0, DCB_RESAMPLE_MUL = 1, DCB_RESAMPLE_DIV = 2 };
+typedef struct DcbResampleJob {
+    const DcbTensor *src, *dst;
+    int32_t align_corners, op;
+    float factor0, factor1;
+} DcbResampleJob;
+int dcb_resample_batch(const DcbResampleJob* jobs, int32_t n_jobs, void* stream);
+
+/*
  * Hann-window merge of overlapping latent tiles into one canvas, in one gather kernel.
  * Replaces merge_latent_tiles_from_pixel_coords(), patch_utils.py:83-174:
  *   per tile (list order): pixel rectangle -> latent rectangle (int(round()), clamped; the 4-tuple is

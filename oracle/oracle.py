@@ -217,6 +217,38 @@ def fuse(warped_a, warped_b, conf_a, conf_b, occ_a=None, occ_b=None):
     return fused
 
 
+def soft_fuse(W_fwd, W_bwd, M_fwd, M_bwd, conf_fwd=None, conf_bwd=None, eps: float = 1e-6):
+    """improv_experiments.ipynb cell 3: masks are VALID masks here (1 valid), holes where both are invalid."""
+    conf_fwd = M_fwd if conf_fwd is None else conf_fwd
+    conf_bwd = M_bwd if conf_bwd is None else conf_bwd
+    w = torch.clamp(torch.cat([conf_fwd, conf_bwd], dim=1), min=0)
+    w_norm = w / (w.sum(dim=1, keepdim=True) + eps)
+    out = w_norm[:, :1] * W_fwd + w_norm[:, 1:] * W_bwd
+    holes = (M_fwd + M_bwd) < 0.5
+    if holes.any():
+        out = torch.where(holes.expand_as(out), 0.5 * (W_fwd + W_bwd), out)
+    return out
+
+
+def pyramid_conditioning(img1, img2, flow1, flow2, sizes=(128, 64, 32)):
+    """improv_experiments.ipynb cell 5, restated on CPU tensors: per size both frames and
+    both flows resized (bilinear, align_corners=False; flows times size / W), both frames soft-splatted with an all-ones
+    metric, fused with identity masks. Returns [(warped1, warped2, fused), ...]."""
+    F = torch.nn.functional
+    out = []
+    for size in sizes:
+        a = F.interpolate(img1, size=(size, size), mode="bilinear", align_corners=False)
+        b = F.interpolate(img2, size=(size, size), mode="bilinear", align_corners=False)
+        k = float(size) / float(flow1.shape[-1])
+        f1 = F.interpolate(flow1, size=(size, size), mode="bilinear", align_corners=False) * k
+        f2 = F.interpolate(flow2, size=(size, size), mode="bilinear", align_corners=False) * k
+        ones = torch.ones(img1.shape[0], 1, size, size, dtype=img1.dtype)
+        w1 = softsplat(a, f1, ones, "soft")
+        w2 = softsplat(b, f2, ones, "soft")
+        out.append((w1, w2, soft_fuse(w1, w2, ones, ones)))
+    return out
+
+
 def residual_recipe(image1, flow1, flow2, gt, variant: str):
     """Conditioning builder.
 

@@ -26,6 +26,51 @@ with torch.no_grad():
     torch.cuda.synchronize()
 print(f"pyramid forward, 4 fused blocks: {a.elapsed_time(b) / 20 * 1e3:.1f} us per forward (device-timed), host enqueue time {host * 1e6:.1f} us")
 
+# the same four scales as ONE library call (dcb_bidir_pyramid_fwd: two launches + one memset)
+levels = [(feat, feat, ff, fb, m_, m_) for feat, ff, fb, m_ in pyr]
+def whole():
+    d.bidirectional_pyramid(levels)
+with torch.no_grad():
+    for _ in range(5): whole()
+    l0 = d.launch_count(); whole(); per = d.launch_count() - l0
+    torch.cuda.synchronize(); a.record()
+    for _ in range(50): whole()
+    b.record(); torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(50): whole()
+    host = (time.perf_counter() - t0) / 50
+    torch.cuda.synchronize()
+    s = torch.cuda.Stream(); s.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(s):
+        whole()
+        gr = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(gr, stream=s):
+            whole()
+    torch.cuda.synchronize(); a.record()
+    for _ in range(50): gr.replay()
+    b2 = torch.cuda.Event(enable_timing=True); b2.record(); torch.cuda.synchronize()
+print(f"pyramid forward, ONE call: {per} launches, {a.elapsed_time(b2) / 50 * 1e3:.1f} us per CUDA-graph replay; eager: host enqueue time {host * 1e6:.1f} us")
+with torch.no_grad():
+    torch.cuda.synchronize(); a.record()
+    for _ in range(50): whole()
+    b.record(); torch.cuda.synchronize()
+print(f"pyramid forward, ONE call, eager: {a.elapsed_time(b) / 50 * 1e3:.1f} us per forward (device-timed)")
+# with the eight flow resizes in front (one launch) -- what Bi_Dir_FeatureExtractor.forward does between the conv stacks
+flow_full = torch.randn(2, 4, 512, 512, device="cuda", generator=g) * 3
+def with_resize():
+    jobs = []
+    for res in (64, 32, 16, 8):
+        for fl in (flow_full[:, :2], flow_full[:, 2:]):
+            jobs.append((fl, (res, res), False, d._lib.RESAMPLE_DIV, (res - 1) / 2.0, (res - 1) / 2.0))
+    fl = d.resample_batch(jobs)
+    d.bidirectional_pyramid([(feat, feat, fl[2 * i], fl[2 * i + 1], m_, m_) for i, (feat, _, _, m_) in enumerate(pyr)])
+with torch.no_grad():
+    for _ in range(5): with_resize()
+    torch.cuda.synchronize(); a.record()
+    for _ in range(50): with_resize()
+    b.record(); torch.cuda.synchronize()
+print(f"8 flow resizes + pyramid forward: {a.elapsed_time(b) / 50 * 1e3:.1f} us per forward (device-timed, eager)")
+
 # where the host time goes: launches per block and the time of the C call alone
 lib = d._lib.lib()
 for feat, ff, fb, m_ in pyr:

@@ -447,3 +447,125 @@ def test_flow_ingest_device_matches_reference_golden(dcb, tmp_path):
     flow = torch.from_numpy(z["batched/in"]).cuda()
     for r in (64, 32, 16, 8):
         assert_close(fio.resize_and_normalize_flow_device(flow, r, r), torch.from_numpy(z[f"batched/normalize_{r}"]), 2e-6, f"normalise {r}")
+
+
+# ---------------------------------------------------------------------------------------------
+# whole pyramids in one call (csrc/pyramid.cu): f-1 as the survey defines it, the batched entry, f-4
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_resample_batch_matches_torch(dcb, dtype):
+    """dcb_resample_batch == F.interpolate(bilinear) followed by the per-channel factor, for every convention the reference
+    uses (control_utils.py:74-97, extractors.py:182-183, notebook cell 5, utils.py:21-28), all jobs in ONE launch."""
+    g = torch.Generator().manual_seed(21)
+    flow = (torch.randn(2, 2, 67, 121, generator=g) * 5).cuda().to(dtype)
+    img = torch.rand(2, 3, 96, 80, generator=g).cuda().to(dtype)
+    strided = torch.randn(1, 4, 40, 2 * 56, generator=g).cuda().to(dtype)[:, :, :, ::2]          # non-contiguous source
+    R = dcb._lib
+    jobs = [(flow, (32, 32), False, R.RESAMPLE_DIV, 15.5, 15.5), (flow, (17, 23), False, R.RESAMPLE_DIV, 8.0, 8.0),
+            (flow, (134, 200), True, R.RESAMPLE_MUL, 200 / 121, 134 / 67), (img, (48, 40), False, R.RESAMPLE_NONE, 1.0, 1.0),
+            (img, (1, 1), False, R.RESAMPLE_NONE, 1.0, 1.0), (strided, (64, 64), False, R.RESAMPLE_MUL, 0.5, 0.5),
+            (flow, (8, 8), False, R.RESAMPLE_MUL, 0.25, 0.25, torch.float32)]
+    before = dcb.launch_count()
+    got = dcb.resample_batch(jobs)
+    assert dcb.launch_count() - before == 1
+    for job, out in zip(jobs, got):
+        src, size, align, op, f0, f1 = job[:6]
+        ref = torch.nn.functional.interpolate(src.float(), size=size, mode="bilinear", align_corners=align)
+        fac = torch.tensor([f0] + [f1] * (src.shape[1] - 1), device="cuda").view(1, -1, 1, 1)
+        ref = ref * fac if op == R.RESAMPLE_MUL else (ref / fac if op == R.RESAMPLE_DIV else ref)
+        assert out.shape == ref.shape and out.dtype == (job[6] if len(job) > 6 else dtype)
+        assert_close(out.float(), ref, 2e-6 if out.dtype == torch.float32 else 1e-2, f"resample {size} align={align} op={op}")
+
+
+def _pyramid_inputs(seed, shapes, learned=True):
+    g = torch.Generator().manual_seed(seed)
+    levels = []
+    for n, c, r in shapes:
+        first, last = torch.randn(n, c, r, r, generator=g), torch.randn(n, c, r, r, generator=g)
+        ff = torch.randn(n, 2, r, r, generator=g) * 0.6
+        fb = -ff + 0.25 * torch.randn(n, 2, r, r, generator=g)
+        mf = torch.randn(n, 1, r, r, generator=g) * 0.5 + 0.1 if learned else None
+        mb = torch.randn(n, 1, r, r, generator=g) * 0.5 + 0.1 if learned else None
+        levels.append((first, last, ff, fb, mf, mb))
+    return levels
+
+
+def test_bidirectional_pyramid_two_launches_and_oracle(dcb, orc):
+    """The whole 4-scale pyramid of the live consumer's shapes (batch 2) in one call: exactly two kernel launches, and every
+    scale equal to the oracle's composition (compute_mask x2, feature_warper x2, fuse) away from mask flips at the 0.3
+    threshold; afterwards the accumulator workspace is all-zero again (WS_CLEAN protocol)."""
+    levels = _pyramid_inputs(31, [(2, 160, 64), (2, 160, 32), (2, 320, 16), (2, 640, 8)])
+    dev = [tuple(t.cuda() for t in lv) for lv in levels]
+    with torch.no_grad():
+        dcb.bidirectional_pyramid(dev)                      # warm: workspace allocation
+        before = dcb.launch_count()
+        fused = dcb.bidirectional_pyramid(dev)
+        assert dcb.launch_count() - before == 2
+    ws = dcb._lib.workspace(torch.device("cuda", torch.cuda.current_device()), 1, "acc")
+    assert int(ws.count_nonzero()) == 0, "accumulators not returned clean"
+    for (first, last, ff, fb, mf, mb), got in zip(levels, fused):
+        of, ob = orc.compute_mask(ff, fb), orc.compute_mask(fb, ff)
+        wa, ca = orc.feature_warper(first, ff, mf, of)
+        wb, cb = orc.feature_warper(last, fb, mb, ob)
+        ref = orc.fuse(wa, wb, ca, cb, of, ob)
+        same = (dcb.compute_mask(ff.cuda(), fb.cuda()).cpu() == of) & (dcb.compute_mask(fb.cuda(), ff.cuda()).cpu() == ob)
+        assert same.float().mean() > 0.995
+        assert_close(got.cpu()[same.expand_as(ref)], ref[same.expand_as(ref)], 1e-5, f"pyramid scale {tuple(first.shape)}")
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_bidirectional_pyramid_equals_blocks_with_gradients(dcb, dtype):
+    """One pyramid node == one fused block per scale (dcb_bidir_block_fwd / _bwd): values and all four gradients per scale,
+    odd sizes and a channel count that is no multiple of four included; plus the ones-metric (None) form."""
+    shapes = [(2, 48, 32), (1, 30, 19), (3, 8, 8)]
+    levels = _pyramid_inputs(32, shapes)
+    rel = 2e-5 if dtype == torch.float32 else 2e-2
+
+    def run(whole):
+        ts = [[None if t is None else t.cuda().to(dtype) for t in lv] for lv in levels]
+        for lv in ts:
+            for k in (0, 1, 4, 5):
+                lv[k].requires_grad_(True)
+        if whole:
+            outs = dcb.bidirectional_pyramid([tuple(lv) for lv in ts])
+        else:
+            outs = [dcb.bidirectional_block(*lv) for lv in ts]
+        g = torch.Generator().manual_seed(5)
+        torch.autograd.backward(list(outs), [torch.randn(o.shape, generator=g).cuda().to(dtype) for o in outs])   # one node: one backward
+        return outs, [[lv[k].grad for k in (0, 1, 4, 5)] for lv in ts]
+
+    (o1, g1), (o2, g2) = run(True), run(False)
+    for l, (a, b) in enumerate(zip(o1, o2)):
+        # the two paths compute the occlusion masks with different accumulator layouts: compare away from flipped pixels
+        ff, fb = levels[l][2].cuda().to(dtype), levels[l][3].cuda().to(dtype)
+        flips = int((a.detach() != b.detach()).any(dim=1).sum())
+        assert flips <= 3 or torch.allclose(a.float(), b.float(), rtol=rel, atol=rel), f"scale {l}: {flips} pixels differ"
+        if flips == 0 or dtype == torch.float32:
+            same = ~((a.detach() - b.detach()).abs().float().amax(dim=1, keepdim=True) > rel * 10 * float(b.detach().abs().max()))
+            assert same.float().mean() > 0.995
+            assert_close(a.detach().float()[same.expand_as(a)], b.detach().float()[same.expand_as(b)], rel, f"pyramid vs block, scale {l}")
+            if bool(same.all()):
+                for name, x, y in zip(("first", "last", "metric_f", "metric_b"), g1[l], g2[l]):
+                    assert_close(x.float(), y.float(), rel * 2, f"pyramid vs block grad {name}, scale {l}")
+    with torch.no_grad():                                       # all-ones metrics are never materialised
+        lv = [(t[0].cuda(), t[1].cuda(), t[2].cuda(), t[3].cuda(), None, None) for t in levels]
+        ones = [(t[0], t[1], t[2], t[3], torch.ones_like(t[2][:, :1]), torch.ones_like(t[2][:, :1])) for t in lv]
+        for a, b in zip(dcb.bidirectional_pyramid(lv), dcb.bidirectional_pyramid(ones)):
+            assert_close(a, b, 1e-6, "ones metric")
+
+
+def test_pyramid_conditioning_matches_notebook_golden(dcb):
+    """Row f-4: tests/golden/ref_notebook_pyramid.npz is the reference's own notebook loop (improv_experiments.ipynb cells 3
+    and 5, executed by oracle/ref_notebook.py). Here: one resampling launch + one pyramid call (two launches) for all scales."""
+    import os
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", "ref_notebook_pyramid.npz"))
+    img1, img2 = (torch.from_numpy(z[k]).float().cuda() / 255.0 for k in ("img1_u8", "img2_u8"))
+    f1, f2 = torch.from_numpy(z["flow1"]).cuda(), torch.from_numpy(z["flow2"]).cuda()
+    sizes = [int(s) for s in z["sizes"]]
+    dcb.pyramid_conditioning(img1, img2, f1, f2, sizes)
+    before = dcb.launch_count()
+    got = dcb.pyramid_conditioning(img1, img2, f1, f2, sizes)
+    assert dcb.launch_count() - before == 3
+    for size, (w1, w2, fused) in zip(sizes, got):
+        for name, t in (("warped1", w1), ("warped2", w2), ("fused", fused)):
+            assert_close(t, torch.from_numpy(z[f"{name}_{size}"]), 1e-5, f"notebook pyramid {name} at {size}")

@@ -152,3 +152,16 @@ def test_exp_det_is_within_an_ulp_of_libm():
     assert float(((orc.exp_det(xd) - xd.exp()).abs() / xd.exp()).max()) < 4e-16
     s = orc.exp_det(torch.tensor([float("nan"), float("inf"), -float("inf"), 0.0]))
     assert torch.isnan(s[0]) and s[1] == float("inf") and s[2] == 0 and s[3] == 1
+
+
+def test_pyramid_oracle_matches_the_notebook_execution():
+    """tests/golden/ref_notebook_pyramid.npz: cells 3 and 5 of the reference's improv_experiments.ipynb executed as they
+    are (oracle/ref_notebook.py) on the reference's own softsplat. The restated loop (oracle.pyramid_conditioning,
+    row f-4) reproduces all three tensors of every scale bit for bit."""
+    import torch
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", "ref_notebook_pyramid.npz"))
+    img1, img2 = (torch.from_numpy(z[k]).float() / 255.0 for k in ("img1_u8", "img2_u8"))
+    got = orc.pyramid_conditioning(img1, img2, torch.from_numpy(z["flow1"]), torch.from_numpy(z["flow2"]), [int(s) for s in z["sizes"]])
+    for size, (w1, w2, fused) in zip(z["sizes"], got):
+        for name, t in (("warped1", w1), ("warped2", w2), ("fused", fused)):
+            assert np.array_equal(t.numpy(), z[f"{name}_{size}"]), (int(size), name)

@@ -253,6 +253,21 @@ def _extras(torch, d, dev, gen, peak):
         with torch.no_grad():
             msf = _time_cuda(torch, pyramid_fused, 50, 10)
         ex["controlnet_pyramid_4_fused_blocks_batch2_f32"] = {"us_per_forward": round(msf * 1e3, 1), "includes": "16 splats + 4 confidence fusions with hole fill"}
+        # ... and as ONE call for the whole pyramid (dcb_bidir_pyramid_fwd: two launches + one memset for all four scales)
+        levels = [(feat, feat, ff, fb, m_, m_) for feat, ff, fb, m_ in pyr]
+        with torch.no_grad():
+            ms1 = _time_cuda(torch, lambda: d.bidirectional_pyramid(levels), 50, 10)
+            l0 = d.launch_count(); d.bidirectional_pyramid(levels); per = d.launch_count() - l0
+            gs = torch.cuda.Stream(); gs.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(gs):
+                d.bidirectional_pyramid(levels)
+                gp = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(gp, stream=gs):
+                    d.bidirectional_pyramid(levels)
+            torch.cuda.synchronize()
+            msgp = _time_cuda(torch, gp.replay, 100, 10)
+        ex["controlnet_pyramid_one_call_batch2_f32"] = {"us_per_forward": round(ms1 * 1e3, 1), "us_per_forward_cuda_graph": round(msgp * 1e3, 1),
+                                                        "kernel_launches": per, "includes": "16 splats + 4 confidence fusions with hole fill"}
         # C3: 64-frame 1080p warp + residual: fused splat recipe and backwarp + residual
         n3 = 64
         img = torch.rand(n3, 3, H, W, device=dev, generator=gen); gt = torch.rand(n3, 3, H, W, device=dev, generator=gen)

@@ -5,9 +5,9 @@
 // (control_utils.py:11-17), two FeatureWarperSoftsplat splats with (1 - mask) (control_utils.py:61-72), the confidence
 // fusion and the double-hole fill with its `holes.any()` host sync (extractors.py:298-310) -- in the reference ~45 eager
 // kernels, 4 NVRTC cache lookups and one device->host stall per scale; in round 1 five library calls from Python. Here
-// the host enters the library once: the kernels themselves are the ones of recipe.cu / splat_*.cu / fuse.cu, launched
-// back to back on the caller's stream (the pyramid levels are a few thousand pixels: the block is bound by host time
-// per call, not by its kernels -- profiles/r01/NOTES.md, "GPU time of every kernel of one bi-directional block").
+// the host enters the library once. Scales whose accumulators fit the L2 (every pyramid level of the live consumer) run
+// as TWO launches (pyramid.cu: all four scatter jobs, then masks + normalisation + fusion); bigger tensors run the
+// kernels of recipe.cu / splat_*.cu / fuse.cu back to back on the caller's stream.
 #include "dcb_common.cuh"
 
 namespace dcb {
@@ -25,6 +25,25 @@ int bidir_fuse_fwd_impl(const DcbTensor*, const DcbTensor*, const DcbTensor*, co
 int bidir_fuse_bwd_impl(const DcbTensor*, const DcbTensor*, const DcbTensor*, const DcbTensor*, const DcbTensor*, const DcbTensor*,
                         const DcbTensor*, const DcbTensor*, const DcbTensor*, const DcbTensor*, const DcbTensor*, cudaStream_t);
 
+// pyramid.cu: the two-launch form (every scatter job in one launch, everything else in a second)
+long long pyramid_workspace(const DcbPyramidLevel* lv, int n);
+int bidir_pyramid_fwd_impl(const DcbPyramidLevel* lv, int n, void* ws, int flags, cudaStream_t st);
+
+// One scale goes through the two-launch pyramid kernels when the accumulators of BOTH directions fit the L2 together
+// (every pyramid level of the live consumer does); bigger tensors keep the launch sequence below (frame-group pipeline
+// or per-target lists per splat).
+constexpr long long kFusedLevelBytes = 48ll << 20;
+static long long fused_level_bytes(long long N, long long C, long long H, long long W, int dtype) {
+    DcbTensor t = {};
+    t.dtype = dtype; t.size[0] = N; t.size[1] = C; t.size[2] = H; t.size[3] = W;
+    DcbPyramidLevel lv = {};
+    lv.first = &t;
+    return pyramid_workspace(&lv, 1);
+}
+static bool block_is_fused(long long N, long long C, long long H, long long W, int dtype) {
+    return (dtype == DCB_F32 || dtype == DCB_BF16) && fused_level_bytes(N, C, H, W, dtype) <= kFusedLevelBytes;
+}
+
 static DcbTensor contiguous_like(const DcbTensor* t, long long C, int dtype, void* ptr) {
     DcbTensor r = *t;
     r.ptr = ptr; r.dtype = dtype;
@@ -35,7 +54,8 @@ static DcbTensor contiguous_like(const DcbTensor* t, long long C, int dtype, voi
 
 long long block_fwd_acc_bytes(long long N, long long C, long long H, long long W, int dtype) {
     const long long a = mask_workspace(N, H, W), b = splat_fwd_workspace(N, C, H, W, dtype, DCB_MODE_SOFT);
-    return a > b ? a : b;
+    const long long c = block_is_fused(N, C, H, W, dtype) ? fused_level_bytes(N, C, H, W, dtype) : 0;
+    return a > b ? (a > c ? a : c) : (b > c ? b : c);
 }
 
 // scratch of the forward: whatever of {warped_f, warped_b, occ_f, occ_b} the caller does not want back
@@ -58,6 +78,19 @@ int bidir_block_fwd_impl(const DcbTensor* first, const DcbTensor* last, const Dc
     const long long N = first->size[0], C = first->size[1], H = first->size[2], W = first->size[3];
     if (N * C * H * W == 0) return DCB_OK;
     const int dt = first->dtype;
+    if (block_is_fused(N, C, H, W, dt)) {
+        // two launches for the scale: outputs the caller does not ask for are never stored
+        const long long need = block_fwd_acc_bytes(N, C, H, W, dt);
+        if (!ws_acc || acc_bytes < need || ((uintptr_t)ws_acc & 255))
+            return set_error(DCB_E_WORKSPACE, "bidir_block_fwd: accumulator workspace of %lld bytes (256 B aligned) required, got %lld", need, acc_bytes);
+        DcbPyramidLevel lv = {};
+        lv.first = first; lv.last = last; lv.flow_f = flow_f; lv.flow_b = flow_b; lv.metric_f = metric_f; lv.metric_b = metric_b;
+        lv.fused = fused->ptr;
+        lv.warped_f = warped_f ? warped_f->ptr : nullptr; lv.warped_b = warped_b ? warped_b->ptr : nullptr;
+        lv.norm_f = norm_f ? norm_f->ptr : nullptr; lv.norm_b = norm_b ? norm_b->ptr : nullptr;
+        lv.occ_f = occ_f ? occ_f->ptr : nullptr; lv.occ_b = occ_b ? occ_b->ptr : nullptr;
+        return bidir_pyramid_fwd_impl(&lv, 1, ws_acc, flags & DCB_FLAG_WS_CLEAN, st);
+    }
     const long long s = elem_size(dt), big = align_up(N * C * H * W * s, 256), plane = align_up(N * H * W * s, 256);
     char* sc = (char*)ws_scratch;
     long long used = 0;

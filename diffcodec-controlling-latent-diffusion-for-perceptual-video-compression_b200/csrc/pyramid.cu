@@ -131,6 +131,7 @@ struct PyrJob {              // one soft splat of `in` by `flow` into its own ac
     int tiles_x, ts;         // strips of 32 x 4 per frame
     int cg, ncg;             // channel quads per item, items per strip
     unsigned item0, items;
+    int vec_in;              // channels-last input: one vector load per channel quad
 };
 struct PyrScatterArgs {
     PyrJob job[kMaxJobs];
@@ -151,7 +152,7 @@ __global__ void __launch_bounds__(32, 16) k_pyr_scatter(const __grid_constant__ 
     PlanarArgs pa;                                   // only the fields planar_scatter_strip reads
     pa.in = b.in; pa.flow = b.flow; pa.metric = b.metric;
     pa.C = b.C; pa.Cq = b.Cq; pa.H = b.H; pa.W = b.W; pa.HW = b.HW;
-    pa.tiles_x = b.tiles_x; pa.mode = DCB_MODE_SOFT; pa.ones = b.metric.p == nullptr;
+    pa.tiles_x = b.tiles_x; pa.mode = DCB_MODE_SOFT; pa.ones = b.metric.p == nullptr; pa.vec_in = b.vec_in;
     float* acc = b.acc + (size_t)fi * b.Cq * b.HW * 4;
     float* dplane = b.dacc + (size_t)fi * b.HW;
     const int q0 = cgi * b.cg, q1 = min(b.Cq, (cgi + 1) * b.cg);
@@ -336,6 +337,7 @@ int bidir_pyramid_fwd_impl(const DcbPyramidLevel* lv, int n, void* ws, int flags
             b.acc = acc; b.dacc = dacc;
             b.C = (int)Cj; b.Cq = (int)((Cj + 3) / 4); b.H = (int)H; b.W = (int)W; b.HW = (unsigned)HW;
             b.tiles_x = tiles_x; b.ts = ts;
+            b.vec_in = planar_vec_ok(in) ? 1 : 0;
             split_quads(N * ts, b.Cq, &b.cg, &b.ncg);
             b.item0 = s_items; b.items = (unsigned)(N * ts * b.ncg);
             s_items += b.items;

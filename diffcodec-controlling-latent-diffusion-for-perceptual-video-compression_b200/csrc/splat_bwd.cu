@@ -288,6 +288,7 @@ __global__ void __launch_bounds__(256, DCB_BS_MINCTAS) k_bwd_source(const BwdArg
 // ---------------------------------------------------------------------------------------------
 template <class T>
 __global__ void __launch_bounds__(256) k_bwd_target4(const BwdArgs a) {
+    pdl_wait();                                                   // the packed cells are one slot shared by consecutive frame groups
     const unsigned p = blockIdx.x * 256 + threadIdx.x;
     if (p >= a.total) return;
     const unsigned n = p / a.HW, r = p - n * a.HW;
@@ -320,6 +321,7 @@ template <class T, class TF>
 #define DCB_B4_PF 1
 #endif
 __global__ void __launch_bounds__(256) k_bwd_source4(const BwdArgs a) {
+    pdl_wait();
     const int W = a.W, H = a.H;
 #if DCB_B4_TILE
     // 32 x 8 pixel tiles: the packed cells gathered by vertically adjacent pixels are the same rows (L1)
@@ -421,12 +423,24 @@ __global__ void __launch_bounds__(256) k_bwd_source4(const BwdArgs a) {
     }
 }
 
+// dcb_set_option("bwd_group_bytes"): packed cells per frame group of the C <= 3 backward; 0 restores the default = ONE group.
+// Measured on 16 x 1080p (profiles/scripts/run_frames_bwd.py, us per frame, backward only): one frame per group (cells stay in
+// L2, two launches per frame) 52.5; 2 frames 51.3; 4 frames 49.7; all frames in one group (cells round-trip through HBM) 48.6 --
+// the launch boundaries cost more than the 32 B/px of DRAM traffic they save, the same lesson as the forward's tails.
+constexpr long long kBwdOneGroup = 1ll << 50;
+long long g_bwd_group_bytes = kBwdOneGroup;
+void bwd_set_group_bytes(long long b) { g_bwd_group_bytes = b > 0 ? b : kBwdOneGroup; }
+
 static bool packed_bwd(int C, int dtype, int mode) { return C <= 3 && mode != DCB_MODE_SUM && dtype != DCB_F64; }
 
 // ---------------------------------------------------------------------------------------------
 long long splat_bwd_workspace(long long N, long long C, long long H, long long W, int dtype, int mode) {
     if (mode == DCB_MODE_SUM) return 0;
-    if (packed_bwd((int)(C > 3 ? 4 : C), dtype, mode)) return align_up(N * H * W * 16, 256);      // one float4 per target pixel
+    if (packed_bwd((int)(C > 3 ? 4 : C), dtype, mode)) {                                          // one float4 per target pixel of ONE frame group
+        long long G = g_bwd_group_bytes / (H * W * 16 > 0 ? H * W * 16 : 1);
+        if (G < 1) G = 1;
+        return align_up((N < G ? N : G) * H * W * 16, 256);
+    }
     return align_up(N * H * W * 2 * (dtype == DCB_F64 ? 8 : 4), 256);
 }
 
@@ -435,18 +449,34 @@ static int launch_bwd(BwdArgs& a, int dtype, cudaStream_t st) {
     using A = typename Acc<T>::type;
     if constexpr (!std::is_same<T, double>::value) {
         if (packed_bwd(a.C, dtype, a.mode)) {
-            const unsigned blocks = (a.total + 255) / 256;
-            k_bwd_target4<T><<<blocks, 256, 0, st>>>(a);
-            DCB_CHECK_LAUNCH("k_bwd_target4");
-#if DCB_B4_TILE
+            // Frame groups (dcb_set_option("bwd_group_bytes"); default: one group = all frames): target pass and source pass
+            // alternate on one slot of packed cells, chained by programmatic dependent launch.
             a.tiles_x = (unsigned)(a.W + 31) / 32;
             a.tiles = a.tiles_x * ((unsigned)(a.H + 7) / 8);
             a.pf_dist = (unsigned)(device_sm_count() * 5);      // 48 registers: 5 CTAs per SM
-            k_bwd_source4<T, TF><<<a.tiles * (unsigned)a.N, 256, 0, st>>>(a);
+            long long G = g_bwd_group_bytes / ((long long)a.HW * 16 > 0 ? (long long)a.HW * 16 : 1);
+            if (G < 1) G = 1;
+            const int es = (int)sizeof(T), fs = (int)sizeof(TF);
+            for (long long f0 = 0; f0 < a.N; f0 += G) {
+                const long long nf = a.N - f0 < G ? a.N - f0 : G;
+                BwdArgs g = a;
+                auto adv = [&](View& v, int e) { if (v.p) v.p = (const char*)v.p + f0 * v.sN * e; };
+                adv(g.gout, es); adv(g.in, es); adv(g.flow, fs); adv(g.metric, es); adv(g.mask, es);
+                if (a.out) g.out = (const char*)a.out + (size_t)f0 * a.C * a.HW * es;
+                if (a.norm) g.norm = (const char*)a.norm + (size_t)f0 * a.HW * sizeof(float);
+                if (a.gin) g.gin = (char*)a.gin + (size_t)f0 * a.C * a.HW * es;
+                if (a.gflow) g.gflow = (char*)a.gflow + (size_t)f0 * 2 * a.HW * fs;
+                if (a.gmetric) g.gmetric = (char*)a.gmetric + (size_t)f0 * a.HW * es;
+                g.N = (int)nf; g.total = (unsigned)(nf * a.HW);
+                DCB_CHECK_CUDA(launch_pdl(k_bwd_target4<T>, dim3((g.total + 255) / 256), dim3(256), 0, st, g));
+                count_launch();
+#if DCB_B4_TILE
+                DCB_CHECK_CUDA(launch_pdl(k_bwd_source4<T, TF>, dim3(g.tiles * (unsigned)g.N), dim3(256), 0, st, g));
 #else
-            k_bwd_source4<T, TF><<<blocks, 256, 0, st>>>(a);
+                DCB_CHECK_CUDA(launch_pdl(k_bwd_source4<T, TF>, dim3((g.total + 255) / 256), dim3(256), 0, st, g));
 #endif
-            DCB_CHECK_LAUNCH("k_bwd_source4");
+                count_launch();
+            }
             return DCB_OK;
         }
     }

@@ -184,6 +184,7 @@ int splat_planar_impl(const DcbTensor* in, const DcbTensor* flow, const DcbTenso
                       cudaStream_t st) {
     PlanarArgs a;
     a.ones = 0;
+    a.vec_in = planar_vec_ok(in) ? 1 : 0;
     a.in = make_view(in); a.flow = make_view(flow); a.metric = make_view(metric); a.mask = make_view(mask);
     a.N = (int)in->size[0]; a.C = (int)in->size[1]; a.H = (int)in->size[2]; a.W = (int)in->size[3];
     a.Cq = (a.C + 3) / 4;

@@ -38,7 +38,28 @@ struct PlanarArgs {
     int step;                // pipeline step k: scatter group k, normalise group k-1, re-zero normaliser slot (k+1) % 3
     int s_frame0, s_frames, n_frame0, n_frames;
     int ones;                // the metric is all-ones and not materialised (compute_mask, warpers without metric_net)
+    int vec_in;              // channels-last input (stride[1] == 1, C % 4 == 0, 16-byte aligned quads): one vector load per quad
 };
+
+// the four channels of a quad of a channels-last (NHWC) tensor in one load: 16 bytes fp32, 8 bytes bf16
+__device__ __forceinline__ void ld_quad(const float* p, float (&o)[4]) {
+    const float4 t = __ldcs((const float4*)p);
+    o[0] = t.x; o[1] = t.y; o[2] = t.z; o[3] = t.w;
+}
+__device__ __forceinline__ void ld_quad(const __nv_bfloat16* p, float (&o)[4]) {
+    const uint2 u = __ldcs((const uint2*)p);
+    o[0] = __uint_as_float(u.x << 16); o[1] = __uint_as_float(u.x & 0xffff0000u);
+    o[2] = __uint_as_float(u.y << 16); o[3] = __uint_as_float(u.y & 0xffff0000u);
+}
+
+// host: can `in` ([N,C,H,W] view) be read quad-wise?
+inline bool planar_vec_ok(const DcbTensor* in) {
+    const long long es = in->dtype == DCB_BF16 ? 2 : 4;
+    if (in->dtype != DCB_F32 && in->dtype != DCB_BF16) return false;
+    if (in->stride[1] != 1 || in->size[1] % 4 != 0 || in->size[1] < 4) return false;
+    if (((uintptr_t)in->ptr) % (uintptr_t)(4 * es)) return false;
+    return in->stride[0] % 4 == 0 && in->stride[2] % 4 == 0 && in->stride[3] % 4 == 0;
+}
 
 __device__ __forceinline__ void red1_if(bool p, float* addr, float v) {
     asm volatile(
@@ -122,14 +143,22 @@ __device__ __forceinline__ void planar_scatter_strip(const PlanarArgs& a, int fr
     const T* ibase = (const T*)a.in.p + frame * a.in.sN + (long long)xs * a.in.sW + (long long)yb * a.in.sH;
     for (int q = q_begin; q < q_end; ++q) {
         float v[kPRows][4];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const int c = 4 * q + j;
-            const T* ip = ibase + (long long)(c < C ? c : 0) * a.in.sC;
+        if (a.vec_in) {                                      // warp-uniform: NHWC, the quad is contiguous
 #pragma unroll
             for (int r = 0; r < kPRows; ++r) {
-                v[r][j] = 0.f;
-                if (c < C && xin && r < rows) v[r][j] = ld_stream(ip + (long long)r * a.in.sH);
+                v[r][0] = v[r][1] = v[r][2] = v[r][3] = 0.f;
+                if (xin && r < rows) ld_quad(ibase + 4 * q + (long long)r * a.in.sH, v[r]);
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int c = 4 * q + j;
+                const T* ip = ibase + (long long)(c < C ? c : 0) * a.in.sC;
+#pragma unroll
+                for (int r = 0; r < kPRows; ++r) {
+                    v[r][j] = 0.f;
+                    if (c < C && xin && r < rows) v[r][j] = ld_stream(ip + (long long)r * a.in.sH);
+                }
             }
         }
         float4* plane = (float4*)acc + (size_t)q * a.HW;

@@ -53,6 +53,7 @@ def path(request, dcb):
     L.set_option("pipe_ring_slots", 1)
     L.set_option("pipe_group_bytes", 0)
     L.set_option("owner_group_bytes", 0)
+    L.set_option("bwd_group_bytes", 0)
     L.release_workspaces()
 
 
@@ -203,6 +204,7 @@ def test_small_frames_many_ring_groups(dcb, orc, path):
     tin, flow, metric, gout = make_inputs(31, 7, 3, 70, 150, flow_scale=3.0)
     L.set_option("pipe_group_bytes", 70 * 150 * 16)
     L.set_option("owner_group_bytes", 70 * 150 * 8)
+    L.set_option("bwd_group_bytes", 70 * 150 * 16 * 2)      # packed backward: two frames per group -> 4 groups, the last one ragged
     L.release_workspaces()
     ref = oracle_run(orc, tin, flow, metric, gout, "soft")
     truth = oracle_run(orc, tin.double(), flow.double(), metric.double(), gout.double(), "soft")

@@ -547,6 +547,11 @@ def test_bidirectional_pyramid_equals_blocks_with_gradients(dcb, dtype):
             if bool(same.all()):
                 for name, x, y in zip(("first", "last", "metric_f", "metric_b"), g1[l], g2[l]):
                     assert_close(x.float(), y.float(), rel * 2, f"pyramid vs block grad {name}, scale {l}")
+    with torch.no_grad():                                       # channels_last feature maps (cuDNN's preferred layout): vector quad loads
+        cl = [tuple(None if t is None else t.cuda().to(dtype) for t in lv) for lv in levels]
+        nh = [(lv[0].to(memory_format=torch.channels_last), lv[1].to(memory_format=torch.channels_last)) + lv[2:] for lv in cl]
+        for a, b in zip(dcb.bidirectional_pyramid(nh), dcb.bidirectional_pyramid(cl)):
+            assert_close(a.float(), b.float(), 1e-5 if dtype == torch.float32 else 2e-2, "channels_last pyramid")
     with torch.no_grad():                                       # all-ones metrics are never materialised
         lv = [(t[0].cuda(), t[1].cuda(), t[2].cuda(), t[3].cuda(), None, None) for t in levels]
         ones = [(t[0], t[1], t[2], t[3], torch.ones_like(t[2][:, :1]), torch.ones_like(t[2][:, :1])) for t in lv]

@@ -459,3 +459,29 @@ def test_convert_kernel(dcb):
         assert torch.equal(L.convert(x, torch.empty(n, device="cuda", dtype=torch.bfloat16)), x.bfloat16())
         assert torch.equal(L.convert(x.half(), torch.empty(n, device="cuda")), x.half().float())
         assert torch.equal(L.convert(x[1:], torch.empty(max(n - 1, 0), device="cuda", dtype=torch.float16)), x[1:].half())   # unaligned source
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("shape", [(2, 32, 40, 56), (1, 160, 32, 32), (3, 8, 17, 23)])
+def test_channels_last_vector_path(dcb, orc, dtype, shape):
+    """NHWC (channels_last) feature maps: the many-channel scatter reads each channel quad with ONE 16-byte (fp32) / 8-byte
+    (bf16) load instead of four strided scalar loads (north_star: coalesced float4 / bf16 NHWC loads; the reference accepts
+    any strides, softsplat.py:170-207). Same values as the NCHW call and as the oracle; a sliced view whose quads are not
+    aligned falls back to the scalar loads."""
+    n, c, h, w = shape
+    tin, flow, metric, _ = make_inputs(71, n, c, h, w, flow_scale=1.5)
+    tin, flow, metric = (t.to(dtype).float() for t in (tin, flow, metric))        # the oracle sees the values the kernels see
+    ref = orc.softsplat(tin, flow, metric, "soft")
+    rel = 1e-5 if dtype == torch.float32 else 1e-2
+    x = tin.cuda().to(dtype)
+    fl, me = flow.cuda().to(dtype), metric.cuda().to(dtype)
+    nhwc = x.to(memory_format=torch.channels_last)
+    assert nhwc.stride(1) == 1
+    a = dcb.softsplat(x, fl, me, "soft")
+    b = dcb.softsplat(nhwc, fl, me, "soft")
+    assert b.is_contiguous()
+    assert_close(b.float(), a.float(), 2e-6 if dtype == torch.float32 else 1e-2, "channels_last vs NCHW")
+    assert_close(b.float().cpu(), ref, rel, "channels_last vs oracle")
+    odd = torch.zeros(n, h, w, c + 1, device="cuda", dtype=dtype)[..., 1:].permute(0, 3, 1, 2)      # quads start 1 element off: not aligned
+    odd.copy_(x)
+    assert_close(dcb.softsplat(odd, fl, me, "soft").float(), a.float(), 2e-6 if dtype == torch.float32 else 1e-2, "unaligned NHWC view")

@@ -52,6 +52,9 @@ constexpr int kStripH = kRows * kPasses;    // a scatter item: 32 columns x 16 r
 #ifndef DCB_NPER
 #define DCB_NPER 8
 #endif
+#ifndef DCB_TAIL_PERCENT
+#define DCB_TAIL_PERCENT 0
+#endif
 #ifndef DCB_NBATCH
 #define DCB_NBATCH (DCB_KROWS * DCB_KPASSES / DCB_NPER)
 #endif
@@ -81,6 +84,7 @@ struct PipeArgs {
     float* acc_s;            // accumulator slot of the frame group this launch scatters (frame s_frame0 at offset 0)
     float* acc_n;            // ... and of the group it normalises
     int vec4;                // H*W % 4 == 0 and out / norm 16-byte aligned: the normalise stage works on 4 pixels per lane
+    int ny_big;              // strip rows of full height (kStripH); the rows below them are single-pass strips (kRows)
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -98,7 +102,7 @@ __device__ __forceinline__ void red4_if(bool p, float* acc, int off, const float
 }
 
 template <class T, class TF, int MODE, int CA>
-__device__ __forceinline__ void scatter_strip(const PipeArgs& a, int frame, int tx, int ty, float* acc, int lane) {
+__device__ __forceinline__ void scatter_strip(const PipeArgs& a, int frame, int tx, int y_first, int passes, float* acc, int lane) {
     constexpr int C = CA - (MODE != DCB_MODE_SUM ? 1 : 0);
     const int x = tx * 32 + lane;
     const int W = a.W, H = a.H;
@@ -120,8 +124,8 @@ __device__ __forceinline__ void scatter_strip(const PipeArgs& a, int frame, int 
     const int f_x = xs * (int)a.flow.sW, i_x = xs * (int)a.in.sW, m_x = xs * (int)a.metric.sW;
 
 #pragma unroll 1
-    for (int pass = 0; pass < kPasses; ++pass) {
-        const int yb = ty * kStripH + pass * kRows;
+    for (int pass = 0; pass < passes; ++pass) {
+        const int yb = y_first + pass * kRows;
         if (yb >= H) break;                                              // warp-uniform
         const int rows = min(kRows, H - yb);
         // ---- every load of the pass in flight before the first use ----
@@ -441,7 +445,10 @@ __global__ void __launch_bounds__(kPipeThreads, kMinCtas) k_splat_step(const __g
     } else {
         const unsigned zs = z - (unsigned)a.n_frames;
         if (blockIdx.x >= (unsigned)a.tiles_x || blockIdx.y >= (unsigned)a.tiles_y) return;
-        scatter_strip<T, TF, MODE, CA>(a, a.s_frame0 + (int)zs, (int)blockIdx.x, (int)blockIdx.y, a.acc_s + zs * frame_floats, lane);
+        // the bottom rows of a frame (dispatched last) are cut into single-pass strips: the grid's tail drains in finer steps
+        const int by = (int)blockIdx.y;
+        const int y_first = by < a.ny_big ? by * kStripH : a.ny_big * kStripH + (by - a.ny_big) * kRows;
+        scatter_strip<T, TF, MODE, CA>(a, a.s_frame0 + (int)zs, (int)blockIdx.x, y_first, by < a.ny_big ? kPasses : 1, a.acc_s + zs * frame_floats, lane);
     }
 }
 
@@ -456,6 +463,8 @@ void pipe_set_group_bytes(long long b) { g_pipe_group_bytes = b > 0 ? b : 0; }
 // frames with `ncu --cache-control none` (profiles/r02/): two 33 MB slots do not stay in the 126 MB L2 next to the streaming
 // inputs / outputs (131-178 MB of DRAM traffic per 75 MB frame); ONE slot does (50.4 MB read by the scatter launch, 0.2 MB
 // read + the output written by the normalise launch: exactly the compulsory bytes), and it is as fast or faster.
+int g_pipe_tail_percent = DCB_TAIL_PERCENT;
+void pipe_set_tail_percent(long long p) { g_pipe_tail_percent = p < 0 ? DCB_TAIL_PERCENT : (p > 100 ? 100 : (int)p); }
 int g_pipe_ring_slots = 1;
 void pipe_set_ring_slots(long long n) { g_pipe_ring_slots = n == 1 ? 1 : 2; }
 
@@ -551,7 +560,12 @@ int splat_pipe_impl(const DcbTensor* in, const DcbTensor* flow, const DcbTensor*
     a.eps = eps;
     a.G = (int)group_frames(a.N, a.H, a.W);
     a.tiles_x = (a.W + 31) / 32;
-    a.tiles_y = (a.H + kStripH - 1) / kStripH;
+    {   // dcb_set_option("pipe_tail_percent"): share of a frame's rows (at the bottom) cut into single-pass strips
+        const int rows_fine = (int)((long long)a.H * g_pipe_tail_percent / 100) / kStripH * kStripH;
+        a.ny_big = (a.H - rows_fine) / kStripH;
+        const int rest = a.H - a.ny_big * kStripH;
+        a.tiles_y = a.ny_big + (rest + kRows - 1) / kRows;
+    }
     a.ts = a.tiles_x * a.tiles_y;
     a.tn = (int)((a.HW + kChunk - 1) / kChunk);
     a.out = out ? out->ptr : nullptr;

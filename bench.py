@@ -230,8 +230,9 @@ def _extras(torch, d, dev, gen, peak):
                 d.softsplat(lat, flb, met, "soft")
         torch.cuda.synchronize()
         msg = _time_cuda(torch, gr.replay, 200, 20)
+        l0 = d.launch_count(); d.softsplat(lat, flb, met, "soft"); c2_launches = d.launch_count() - l0
         ex["C2_soft_fwd_4x4x135x240_bf16"] = {"us_per_call": round(ms * 1e3, 2), "us_per_call_fp32_flow": round(ms32 * 1e3, 2),
-                                              "us_per_call_cuda_graph": round(msg * 1e3, 2), "launches_per_call": 2,
+                                              "us_per_call_cuda_graph": round(msg * 1e3, 2), "launches_per_call": c2_launches,
                                               "mpixel_s": round(4 * 135 * 240 / ms / 1e3, 1)}
         # the live consumer: the 16 splats of one DualFlowControlNet forward (extractors.py:280-314), batch 2
         pyr = []

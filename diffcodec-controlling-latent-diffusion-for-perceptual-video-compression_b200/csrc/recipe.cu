@@ -33,12 +33,22 @@ int splat_owner_impl(const DcbTensor* in, const DcbTensor* flow, const DcbTensor
                      const DcbTensor* norm, const DcbTensor* mask, void* ws, int mode, int eps, cudaStream_t st,
                      bool ones_metric, const DcbTensor* mask_out);
 
-// one soft splat with an all-ones metric through whichever forward applies (owner kernels, or the accumulator pipeline)
+// implemented in splat_small.cu / splat_fwd.cu: small frames take one launch, one thread-block cluster per frame
+bool small_frames(int dtype, int mode, long long N, long long C, long long H, long long W);
+long long cluster_workspace(long long N, long long C, long long H, long long W, int mode);
+int splat_cluster_impl(const DcbTensor* in, const DcbTensor* flow, const DcbTensor* metric, const DcbTensor* out,
+                       const DcbTensor* norm, const DcbTensor* mask, void* ws, int mode, int eps, bool ws_clean,
+                       cudaStream_t st, bool ones_metric, const DcbTensor* mask_out);
+
+// one soft splat with an all-ones metric through whichever forward applies (owner kernels, the cluster kernel for small
+// frames, or the accumulator pipeline)
 static int ones_splat(const DcbTensor* in, const DcbTensor* flow, const DcbTensor* out, const DcbTensor* mask_out, void* ws,
                       bool owner, bool ws_clean, cudaStream_t st) {
     if (!pipe_supported(in, flow, nullptr))
         return set_error(DCB_E_LIMIT, "conditioning: tensor spans beyond 2^31 elements are not supported (32-bit in-frame offsets)");
     if (owner) return splat_owner_impl(in, flow, nullptr, out, nullptr, nullptr, ws, DCB_MODE_SOFT, DCB_EPS_ADD, st, true, mask_out);
+    if (small_frames(in->dtype, DCB_MODE_SOFT, in->size[0], in->size[1], in->size[2], in->size[3]))
+        return splat_cluster_impl(in, flow, nullptr, out, nullptr, nullptr, ws, DCB_MODE_SOFT, DCB_EPS_ADD, ws_clean, st, true, mask_out);
     return splat_pipe_impl(in, flow, nullptr, out, nullptr, nullptr, ws, DCB_MODE_SOFT, DCB_EPS_ADD, ws_clean, st, true, mask_out);
 }
 
@@ -95,7 +105,9 @@ __global__ void __launch_bounds__(256) k_recipe_fuse(const FuseArgs a) {
 
 // ---------------------------------------------------------------------------------------------
 static long long splat_part(long long N, long long C, long long H, long long W) {
-    return use_owner(DCB_F32, DCB_MODE_SOFT, C, H, W) ? owner_workspace(N, H, W) : pipe_workspace(N, H, W);
+    if (use_owner(DCB_F32, DCB_MODE_SOFT, C, H, W)) return owner_workspace(N, H, W);
+    if (small_frames(DCB_F32, DCB_MODE_SOFT, N, C, H, W)) return cluster_workspace(N, C, H, W, DCB_MODE_SOFT);
+    return pipe_workspace(N, H, W);
 }
 
 long long mask_workspace(long long N, long long H, long long W) { return splat_part(N, 2, H, W); }

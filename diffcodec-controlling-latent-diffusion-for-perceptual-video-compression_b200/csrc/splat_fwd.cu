@@ -168,8 +168,19 @@ static bool use_pipe(int dtype, int mode, long long C) {
     return dtype != DCB_F64 && C + (mode == DCB_MODE_SUM ? 0 : 1) <= 4;
 }
 
-// dcb_set_option("fwd_path"): 0 = automatic, 1 = round-1 accumulator pipeline, 2 = target-tile owner wherever it applies
+// dcb_set_option("fwd_path"): 0 = automatic, 1 = accumulator pipelines only (no cluster kernel for small frames), 2 = target-tile
+// owner wherever it applies
 int g_fwd_path = 0;
+
+// small frames: one launch, one thread-block cluster per frame (splat_small.cu)
+bool use_cluster(int dtype, int mode, long long N, long long C, long long H, long long W);
+long long cluster_workspace(long long N, long long C, long long H, long long W, int mode);
+int splat_cluster_impl(const DcbTensor* in, const DcbTensor* flow, const DcbTensor* metric, const DcbTensor* out,
+                       const DcbTensor* norm, const DcbTensor* mask, void* ws, int mode, int eps, bool ws_clean,
+                       cudaStream_t st, bool ones_metric, const DcbTensor* mask_out);
+bool small_frames(int dtype, int mode, long long N, long long C, long long H, long long W) {
+    return g_fwd_path == 0 && use_cluster(dtype, mode, N, C, H, W);
+}
 
 // C+1 <= 8 channels in fp32 / bf16: target-tile ownership, accumulators in shared memory (splat_owner.cu)
 // Opt-in only: measured on B200 (profiles/r02/NOTES.md) it needs 2-3x the instructions of the accumulator pipeline and loses
@@ -181,6 +192,7 @@ bool use_owner(int dtype, int mode, long long C, long long H, long long W) {
 
 long long splat_fwd_workspace(long long N, long long C, long long H, long long W, int dtype, int mode) {
     if (use_owner(dtype, mode, C, H, W)) return owner_workspace(N, H, W);
+    if (small_frames(dtype, mode, N, C, H, W)) return cluster_workspace(N, C, H, W, mode);
     if (use_pipe(dtype, mode, C)) return pipe_workspace(N, H, W);
     if (dtype != DCB_F64) {
         const long long planar = planar_workspace(N, C, H, W, dtype, mode);
@@ -274,6 +286,12 @@ int splat_fwd_impl(const DcbTensor* in, const DcbTensor* flow, const DcbTensor* 
         // the flag promises an all-zero workspace on exit; callers that ask dcb_splat_fwd_workspace_is_scratch() never pass it here
         if (rc == DCB_OK && ws_clean && need > 0) DCB_CHECK_CUDA(cudaMemsetAsync(ws, 0, (size_t)need, st));
         return rc;
+    }
+    if (small_frames(in->dtype, mode, N, C, H, W)) {
+        const long long need = cluster_workspace(N, C, H, W, mode);
+        if (!ws || ws_bytes < need || ((uintptr_t)ws & 255))
+            return set_error(DCB_E_WORKSPACE, "splat_fwd: workspace of %lld bytes (256 B aligned) required, got %lld", need, ws_bytes);
+        return splat_cluster_impl(in, flow, metric, out, norm, mask, ws, mode, eps, ws_clean, st, false, nullptr);
     }
     const bool pipe = use_pipe(in->dtype, mode, C);
     if (pipe && !pipe_supported(in, flow, metric))

@@ -1,4 +1,4 @@
-"""Latency of small / single-frame forward calls per kernel family (fwd_path 1 = accumulator pipeline, 2 = target-tile owner):
+"""Latency of small / single-frame forward calls per kernel family (fwd_path 0 = automatic: cluster kernel for small frames, 1 = accumulator pipelines):
 C2 latents, C1 single 1080p frame, occlusion masks and feature splats at the ControlNet pyramid sizes. Eager and CUDA-graph replay."""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
@@ -51,7 +51,7 @@ cases["avg 4x3x256x256 f32"] = lambda: d.softsplat(f3, fl3, None, "avg")
 f5 = torch.rand(1, 3, 540, 960, device=dev, generator=g); fl5 = torch.randn(1, 2, 540, 960, device=dev, generator=g) * 3
 cases["avg 1x3x540x960 f32"] = lambda: d.softsplat(f5, fl5, None, "avg")
 
-for path in (1, 2):
+for path in (0, 1):
     d._lib.set_option("fwd_path", path)
     d._lib.release_workspaces()
     for name, fn in cases.items():

@@ -32,6 +32,19 @@ def orc():
     return oracle
 
 
+@pytest.fixture(params=["auto", "pipelines"], autouse=True)
+def kernel_family(request, dcb):
+    """Every test of this module runs twice: with the library's own dispatch (small frames take the single-launch cluster
+    kernel, csrc/splat_small.cu) and with the accumulator pipelines forced (dcb_set_option("fwd_path", 1): splat_pipe.cu /
+    splat_planar.cu / splat_lists.cu), so that both kernel families see every mode, eps rule, layout and special flow."""
+    L = dcb._lib
+    L.set_option("fwd_path", 0 if request.param == "auto" else 1)
+    L.release_workspaces()
+    yield request.param
+    L.set_option("fwd_path", 0)
+    L.release_workspaces()
+
+
 @pytest.mark.parametrize("mode", MODES)
 @pytest.mark.parametrize("shape", SHAPES, ids=lambda s: "x".join(map(str, s)))
 def test_forward_backward_fp32(dcb, orc, mode, shape):

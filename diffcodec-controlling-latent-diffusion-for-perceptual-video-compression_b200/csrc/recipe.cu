@@ -7,14 +7,16 @@
 // cat + memset + scatter + 3 post-ops), 2 norms, 2 compares and ~10 more eager kernels per frame,
 // for a batch of ONE frame. Here, for a whole batch:
 //
-//   pass 1  soft splat of image1 by flow1, all-ones metric never materialised  -> warped
-//   pass 2  soft splat of flow1 by flow2 with the occlusion epilogue           -> occ_fwd
-//   pass 3  soft splat of flow2 by flow1 with the occlusion epilogue           -> occ_bwd
-//   pass 4  one elementwise kernel: fusion weights, optional double-hole fill, residual
+//   pass A  soft splat of flow1 by flow2 with the occlusion epilogue                         -> occ_fwd
+//   pass B  soft splat of image1 AND of flow2 by flow1 in ONE scatter (same footprints, same all-ones metric, one shared
+//           weight channel: float4 + float2 cells per pixel), and one epilogue per target pixel: normalise, occlusion
+//           test (occ_bwd), fusion weights, optional double-hole fill, fused + residual stored once
 //
-// Passes 1-3 are the step pipeline of splat_pipe.cu (L2-resident accumulators, no memset); a first
-// version that scattered all three splats from one kernel into 40 B/px of accumulators was 7x
+// Both passes are the step pipeline of splat_pipe.cu (L2-resident accumulators, no memset, two launches per frame group).
+// Round 1 ran three pipeline passes and an elementwise kernel (flow1 read twice, the warped image written, re-read and
+// re-written); a first version that scattered all three splats from one kernel into 40 B/px of accumulators was 7x
 // slower on 64 x 1080p because those accumulators (5.3 GB) lived in HBM (profiles/r01/NOTES.md).
+// The three-pass composition remains for the forwards the recipe pass does not cover (owner kernels, small frames).
 #include "dcb_common.cuh"
 
 namespace dcb {
@@ -24,6 +26,11 @@ long long pipe_workspace(long long N, long long H, long long W);
 int splat_pipe_impl(const DcbTensor* in, const DcbTensor* flow, const DcbTensor* metric, const DcbTensor* out,
                     const DcbTensor* norm, const DcbTensor* mask, void* ws, int mode, int eps, bool ws_clean,
                     cudaStream_t st, bool ones_metric, const DcbTensor* mask_out);
+
+long long recipe_pipe_workspace(long long N, long long H, long long W);
+int recipe_pipe_impl(const DcbTensor* image1, const DcbTensor* flow1, const DcbTensor* flow2, const DcbTensor* gt,
+                     const DcbTensor* fused, const DcbTensor* residual, const DcbTensor* occ_fwd, const DcbTensor* occ_bwd,
+                     void* ws, int variant, cudaStream_t st);
 
 // implemented in splat_owner.cu / splat_fwd.cu
 long long owner_workspace(long long N, long long H, long long W);
@@ -112,10 +119,18 @@ static long long splat_part(long long N, long long C, long long H, long long W) 
 
 long long mask_workspace(long long N, long long H, long long W) { return splat_part(N, 2, H, W); }
 
+// the two-pass recipe runs when both forwards would take the accumulator pipeline
+static bool recipe_two_pass(int dtype, long long N, long long C, long long H, long long W) {
+    return !use_owner(dtype, DCB_MODE_SOFT, C, H, W) && !use_owner(dtype, DCB_MODE_SOFT, 2, H, W) &&
+           !small_frames(dtype, DCB_MODE_SOFT, N, C, H, W) && !small_frames(dtype, DCB_MODE_SOFT, N, 2, H, W);
+}
+
 long long recipe_workspace(long long N, long long C, long long H, long long W) {
     // splat workspace (landing boxes, or pipeline accumulators) + two mask planes (sized for fp32) when the caller does not want them
-    const long long a = splat_part(N, C, H, W), b = splat_part(N, 2, H, W);
-    return (a > b ? a : b) + 2 * align_up(N * H * W * 4, 256);
+    long long a = splat_part(N, C, H, W);
+    const long long b = splat_part(N, 2, H, W), c = recipe_pipe_workspace(N, H, W);
+    a = a > b ? a : b;
+    return (a > c ? a : c) + 2 * align_up(N * H * W * 4, 256);
 }
 
 int occlusion_mask_impl(const DcbTensor* flow_a, const DcbTensor* flow_b, const DcbTensor* mask, void* ws,
@@ -161,6 +176,17 @@ int residual_fused_impl(const DcbTensor* image1, const DcbTensor* flow1, const D
     m2.ptr = (char*)ws + pipe_bytes + plane;
     const DcbTensor* pf = occ_fwd ? occ_fwd : &m1;
     const DcbTensor* pb = occ_bwd ? occ_bwd : &m2;
+
+    if (recipe_two_pass(image1->dtype, N, C, H, W)) {
+        if (!pipe_supported(image1, flow1, nullptr) || !pipe_supported(flow2, flow1, nullptr) || !pipe_supported(gt, flow2, nullptr))
+            return set_error(DCB_E_LIMIT, "conditioning: tensor spans beyond 2^31 elements are not supported (32-bit in-frame offsets)");
+        if (!clean) DCB_CHECK_CUDA(cudaMemsetAsync(ws, 0, (size_t)pipe_bytes, st));
+        // pass A: compute_mask(flow1, flow2) = flow1 splatted by flow2
+        int rc = splat_pipe_impl(flow1, flow2, nullptr, nullptr, nullptr, nullptr, ws, DCB_MODE_SOFT, DCB_EPS_ADD, true, st, true, pf);
+        if (rc != DCB_OK) return rc;
+        // pass B: image1 and flow2 ride on flow1; compute_mask(flow2, flow1), fusion and residual in its epilogue
+        return recipe_pipe_impl(image1, flow1, flow2, gt, fused, residual, pf, occ_bwd, ws, variant, st);
+    }
 
     // a pipeline pass after an owner pass would find landing boxes where it expects all-zero accumulators
     const bool mixed = own_img != own_flow;

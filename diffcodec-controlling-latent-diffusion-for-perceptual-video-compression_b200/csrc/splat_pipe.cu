@@ -48,6 +48,7 @@ constexpr int kWarpsPerCta = kPipeThreads / 32;
 constexpr int kRows = DCB_KROWS;            // rows loaded at once by a warp
 constexpr int kPasses = DCB_KPASSES;        // consecutive row groups per strip (the vertical carry spans them)
 constexpr int kMinCtas = DCB_MINCTAS;       // register budget: 64 per thread -> 32 warps per SM
+constexpr int kMinCtasRecipe = 24;          // the recipe pass carries two more channels and a wider epilogue: 80 registers
 constexpr int kStripH = kRows * kPasses;    // a scatter item: 32 columns x 16 rows
 #ifndef DCB_NPER
 #define DCB_NPER 8
@@ -85,6 +86,15 @@ struct PipeArgs {
     float* acc_n;            // ... and of the group it normalises
     int vec4;                // H*W % 4 == 0 and out / norm 16-byte aligned: the normalise stage works on 4 pixels per lane
     int ny_big;              // strip rows of full height (kStripH); the rows below them are single-pass strips (kRows)
+    // conditioning recipe (recipe_pipe_impl): a 2-channel RIDER splatted by the same flow with the same weights, and the
+    // tensors of the two recipe epilogues (epi 2, 3)
+    View in2;                // rider input [N,2,H,W] (flow2 riding on flow1)
+    float* acc2_s;           // rider accumulators of the group this launch scatters: float2 cells [frame][HW]
+    float* acc2_n;           // ... and of the group it normalises
+    View gt;                 // epi 3: ground truth
+    void* residual;          // epi 3: [N,C,H,W]
+    const void* occ_other;   // epi 3: the occlusion plane computed by epi 2, [N,1,H,W] in T
+    int variant;             // epi 3: DCB_RECIPE_*
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -101,8 +111,19 @@ __device__ __forceinline__ void red4_if(bool p, float* acc, int off, const float
         ::"r"((int)p), "l"(addr), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]) : "memory");
 }
 
-template <class T, class TF, int MODE, int CA>
-__device__ __forceinline__ void scatter_strip(const PipeArgs& a, int frame, int tx, int y_first, int passes, float* acc, int lane) {
+__device__ __forceinline__ void red2_if(bool p, float* acc2, int off, const float (&v)[2]) {
+    float* addr = acc2 + (long long)off * 2;
+    asm volatile(
+        "{\n\t.reg .pred q;\n\t"
+        "setp.ne.s32 q, %0, 0;\n\t"
+        "@q red.global.add.v2.f32 [%1], {%2, %3};\n\t}"
+        ::"r"((int)p), "l"(addr), "f"(v[0]), "f"(v[1]) : "memory");
+}
+
+// RIDER: two more channels (a.in2) ride on the same footprints into float2 cells (acc2): the conditioning recipe splats
+// image1 AND flow2 by flow1 with the same all-ones metric, so flow, weights, merge decisions and the weight channel are shared
+template <class T, class TF, int MODE, int CA, bool RIDER>
+__device__ __forceinline__ void scatter_strip(const PipeArgs& a, int frame, int tx, int y_first, int passes, float* acc, float* acc2, int lane) {
     constexpr int C = CA - (MODE != DCB_MODE_SUM ? 1 : 0);
     const int x = tx * 32 + lane;
     const int W = a.W, H = a.H;
@@ -112,6 +133,7 @@ __device__ __forceinline__ void scatter_strip(const PipeArgs& a, int frame, int 
     const int pitch = W + 2;                       // key = (y0 + 1) * pitch + (x0 + 1) identifies a footprint
 
     float pend[4] = {0.f, 0.f, 0.f, 0.f};
+    float pend2[2] = {0.f, 0.f};
     int pend_key = kDead, pend_off = 0;
     bool pend_ok = false;
 
@@ -122,6 +144,8 @@ __device__ __forceinline__ void scatter_strip(const PipeArgs& a, int frame, int 
     // element offsets fit 32 bits (checked by the host)
     const int f_sH = (int)a.flow.sH, f_sC = (int)a.flow.sC, i_sH = (int)a.in.sH, i_sC = (int)a.in.sC, m_sH = (int)a.metric.sH;
     const int f_x = xs * (int)a.flow.sW, i_x = xs * (int)a.in.sW, m_x = xs * (int)a.metric.sW;
+    const TF* rbase = RIDER ? (const TF*)a.in2.p + frame * a.in2.sN : nullptr;
+    const int r_sH = (int)a.in2.sH, r_sC = (int)a.in2.sC, r_x = xs * (int)a.in2.sW;
 
 #pragma unroll 1
     for (int pass = 0; pass < passes; ++pass) {
@@ -129,12 +153,14 @@ __device__ __forceinline__ void scatter_strip(const PipeArgs& a, int frame, int 
         if (yb >= H) break;                                              // warp-uniform
         const int rows = min(kRows, H - yb);
         // ---- every load of the pass in flight before the first use ----
-        float flx[kRows], fly[kRows], mv[kRows], iv[kRows][C > 0 ? C : 1];
+        float flx[kRows], fly[kRows], mv[kRows], iv[kRows][C > 0 ? C : 1], rv[kRows][2];
 #pragma unroll
         for (int r = 0; r < kRows; ++r) {
             const bool on = xin && r < rows;
             const int y = yb + r;
             flx[r] = fly[r] = 0.f; mv[r] = 0.f;
+            rv[r][0] = rv[r][1] = 0.f;
+            if (RIDER && on) { const TF* rp = rbase + (y * r_sH + r_x); rv[r][0] = ld_stream(rp); rv[r][1] = ld_stream(rp + r_sC); }
 #pragma unroll
             for (int c = 0; c < C; ++c) iv[r][c] = 0.f;
             if (on) {
@@ -171,6 +197,14 @@ __device__ __forceinline__ void scatter_strip(const PipeArgs& a, int frame, int 
                 nw[c] = mul_rn(v, wnw); ne[c] = mul_rn(v, wne);
                 sw[c] = mul_rn(v, wsw); se[c] = mul_rn(v, wse);
             }
+            float nw2[2] = {0.f, 0.f}, ne2[2] = {0.f, 0.f}, sw2[2] = {0.f, 0.f}, se2[2] = {0.f, 0.f};
+            if (RIDER) {
+#pragma unroll
+                for (int c = 0; c < 2; ++c) {
+                    const float v = (MODE >= DCB_MODE_LINEAR) ? mul_rn(rv[r][c], g) : rv[r][c];
+                    nw2[c] = mul_rn(v, wnw); ne2[c] = mul_rn(v, wne); sw2[c] = mul_rn(v, wsw); se2[c] = mul_rn(v, wse);
+                }
+            }
             const int key = alive ? (y0 + 1) * pitch + (x0 + 1) : kDead;
             const int off = y0 * W + x0;
             const bool vx0 = x0 >= 0, vx1 = x0 < W - 1, vy0 = y0 >= 0, vy1 = y0 < H - 1;
@@ -187,15 +221,31 @@ __device__ __forceinline__ void scatter_strip(const PipeArgs& a, int frame, int 
                 nw[c] = take ? add_rn(nw[c], en) : nw[c];
                 sw[c] = take ? add_rn(sw[c], es) : sw[c];
             }
+            if (RIDER) {
+#pragma unroll
+                for (int c = 0; c < 2; ++c) {
+                    const float en = __shfl_up_sync(full, ne2[c], 1), es = __shfl_up_sync(full, se2[c], 1);
+                    nw2[c] = take ? add_rn(nw2[c], en) : nw2[c];
+                    sw2[c] = take ? add_rn(sw2[c], es) : sw2[c];
+                }
+            }
             const bool east = alive && !given && vx1;
             red4_if(east && vy0, acc, off + 1, ne);
             red4_if(east && vy1, acc, off + W + 1, se);
+            if (RIDER) { red2_if(east && vy0, acc2, off + 1, ne2); red2_if(east && vy1, acc2, off + W + 1, se2); }
             // ---- vertical carry: the previous row's south piece joins my north piece if they abut ----
             const bool join = pend_key == key && alive;            // kDead never equals a live key
 #pragma unroll
             for (int c = 0; c < CA; ++c) nw[c] = join ? add_rn(nw[c], pend[c]) : nw[c];
             red4_if(pend_ok && !join, acc, pend_off, pend);
             red4_if(alive && vx0 && vy0, acc, off, nw);
+            if (RIDER) {
+#pragma unroll
+                for (int c = 0; c < 2; ++c) nw2[c] = join ? add_rn(nw2[c], pend2[c]) : nw2[c];
+                red2_if(pend_ok && !join, acc2, pend_off, pend2);
+                red2_if(alive && vx0 && vy0, acc2, off, nw2);
+                pend2[0] = sw2[0]; pend2[1] = sw2[1];
+            }
 #pragma unroll
             for (int c = 0; c < CA; ++c) pend[c] = sw[c];
             pend_key = alive ? key + pitch : kDead;
@@ -204,6 +254,7 @@ __device__ __forceinline__ void scatter_strip(const PipeArgs& a, int frame, int 
         }
     }
     red4_if(pend_ok, acc, pend_off, pend);
+    if (RIDER) red2_if(pend_ok, acc2, pend_off, pend2);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -416,10 +467,84 @@ __device__ __forceinline__ void mask_chunk(const PipeArgs& a, int frame, int chu
 }
 
 // ---------------------------------------------------------------------------------------------
+// conditioning-recipe epilogue (dataset.py:233-265, residual_utils.py:159-199): the float4 cells hold the soft splat of
+// image1 by flow1 (C channels + weight), the float2 cells the soft splat of flow2 by the same flow1 (the weight is shared).
+// One pass per target pixel: warped = S / (D + 1e-7); occ_bwd = compute_mask(flow2, flow1); fusion weights from occ_fwd
+// (computed by the pass before) and occ_bwd; optional double-hole fill; fused and residual = gt - fused stored once.
+// ---------------------------------------------------------------------------------------------
+constexpr int kRPer = 4;                          // pixels per lane in flight
+template <class T, int CA>
+__device__ __forceinline__ void recipe_chunk(const PipeArgs& a, int frame, int chunk, float* acc, float* acc2, int lane) {
+    constexpr int C = CA - 1;
+    T* fo = (T*)a.out + (long long)frame * C * a.HW;
+    T* ro = (T*)a.residual + (long long)frame * C * a.HW;
+    const T* oo = (const T*)a.occ_other + (long long)frame * a.HW;
+    T* mo = a.mask_out ? (T*)a.mask_out + (long long)frame * a.HW : nullptr;
+    const T* fbase = (const T*)a.epi_flow.p + frame * a.epi_flow.sN;
+    const T* gbase = (const T*)a.gt.p + frame * a.gt.sN;
+#pragma unroll 1
+    for (int b = 0; b < kChunk / (32 * kRPer); ++b) {
+        const unsigned base = (unsigned)chunk * kChunk + b * (32 * kRPer) + lane;
+        if (base - lane >= a.HW) break;
+        float4 s[kRPer]; float2 q[kRPer]; float mx[kRPer], my[kRPer], of[kRPer], gv[kRPer][C > 0 ? C : 1];
+#pragma unroll
+        for (int i = 0; i < kRPer; ++i) {                                // every load of the batch in flight first
+            const unsigned r = base + i * 32;
+            s[i] = make_float4(0.f, 0.f, 0.f, 0.f); q[i] = make_float2(0.f, 0.f);
+            mx[i] = my[i] = of[i] = 0.f;
+#pragma unroll
+            for (int c = 0; c < C; ++c) gv[i][c] = 0.f;
+            if (r < a.HW) {
+                s[i] = __ldcg((const float4*)acc + r);
+                q[i] = __ldcg((const float2*)acc2 + r);
+                const int y = (int)(r / (unsigned)a.W), x = (int)(r - (unsigned)y * (unsigned)a.W);
+                const T* fp = fbase + (long long)y * a.epi_flow.sH + (long long)x * a.epi_flow.sW;
+                mx[i] = ld<float>(fp); my[i] = ld<float>(fp + a.epi_flow.sC);
+                of[i] = ld_stream(oo + r);
+                const T* gp = gbase + (long long)y * a.gt.sH + (long long)x * a.gt.sW;
+#pragma unroll
+                for (int c = 0; c < C; ++c) gv[i][c] = ld_stream(gp + (long long)c * a.gt.sC);
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < kRPer; ++i) {
+            const unsigned r = base + i * 32;
+            if (r < a.HW) {
+                __stcg((float4*)acc + r, make_float4(0.f, 0.f, 0.f, 0.f));   // accumulators leave the kernel all-zero
+                __stcg((float2*)acc2 + r, make_float2(0.f, 0.f));
+                const float sv[4] = {s[i].x, s[i].y, s[i].z, s[i].w};
+                const float d = sv[C];
+                const float ob = occlusion(q[i].x, q[i].y, d, mx[i], my[i]);          // control_utils.py:15-16
+                if (mo) st<T, float>(mo + r, ob);
+                const float scale = __frcp_rn(add_rn(d, 0.0000001f));                 // softsplat.py:256-258, :270
+                float w0, w1;
+                if (a.variant == DCB_RECIPE_DATASET) {        // dataset.py:255-259: masks are the confidences
+                    const float ws = add_rn(add_rn(of[i], ob), 0.000001f);
+                    w0 = of[i] / ws; w1 = ob / ws;
+                } else {                                      // residual_utils.py:181-185: ones are the confidences
+                    const float ws = add_rn(2.f, 0.000001f);
+                    w0 = 1.f / ws; w1 = w0;
+                }
+                const bool hole = a.variant == DCB_RECIPE_WRAPPER && add_rn(of[i], ob) > 1.5f;   // residual_utils.py:190-193
+#pragma unroll
+                for (int c = 0; c < C; ++c) {
+                    const float wv = round_as<T>(mul_rn(sv[c], scale));               // warped1 == warped2
+                    float fused = add_rn(mul_rn(w0, wv), mul_rn(w1, wv));
+                    if (hole) fused = mul_rn(0.5f, add_rn(wv, wv));
+                    st_stream(fo + (size_t)c * a.HW + r, fused);
+                    st_stream(ro + (size_t)c * a.HW + r, sub_rn(gv[i][c], round_as<T>(fused)));   // residual of the stored (rounded) value
+                }
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 // the step kernel: warp w of CTA b owns item 4b + w; normalise items first, then scatter items
 // ---------------------------------------------------------------------------------------------
-template <class T, class TF, int MODE, int CA>
-__global__ void __launch_bounds__(kPipeThreads, kMinCtas) k_splat_step(const __grid_constant__ PipeArgs a) {
+// KIND 0: softsplat / occlusion mask; KIND 1: the conditioning recipe's second pass (rider scatter + recipe epilogue)
+template <class T, class TF, int MODE, int CA, int KIND>
+__global__ void __launch_bounds__(kPipeThreads, KIND ? kMinCtasRecipe : kMinCtas) k_splat_step(const __grid_constant__ PipeArgs a) {
     // Programmatic dependent launch: let the next step's grid start being scheduled while this one
     // drains, and wait here until the previous step has completed and flushed (both steps touch
     // the same accumulator ring). The launch latency of 65 dependent launches is thereby hidden.
@@ -435,6 +560,7 @@ __global__ void __launch_bounds__(kPipeThreads, kMinCtas) k_splat_step(const __g
         if (chunk >= (unsigned)a.tn) return;
         const int f = a.n_frame0 + (int)z;
         float* acc = a.acc_n + z * frame_floats;
+        if (KIND == 1) { recipe_chunk<T, CA>(a, f, (int)chunk, acc, a.acc2_n + z * ((size_t)a.HW * 2), lane); return; }
         if (a.epi == 1) mask_chunk<T>(a, f, (int)chunk, acc, lane);
 #if DCB_NORM_V == 4
         else if (a.vec4 && a.mask.p == nullptr) normalize_chunk_v4<T, MODE, CA>(a, f, (int)chunk, acc, lane);
@@ -448,7 +574,8 @@ __global__ void __launch_bounds__(kPipeThreads, kMinCtas) k_splat_step(const __g
         // the bottom rows of a frame (dispatched last) are cut into single-pass strips: the grid's tail drains in finer steps
         const int by = (int)blockIdx.y;
         const int y_first = by < a.ny_big ? by * kStripH : a.ny_big * kStripH + (by - a.ny_big) * kRows;
-        scatter_strip<T, TF, MODE, CA>(a, a.s_frame0 + (int)zs, (int)blockIdx.x, y_first, by < a.ny_big ? kPasses : 1, a.acc_s + zs * frame_floats, lane);
+        scatter_strip<T, TF, MODE, CA, KIND == 1>(a, a.s_frame0 + (int)zs, (int)blockIdx.x, y_first, by < a.ny_big ? kPasses : 1, a.acc_s + zs * frame_floats,
+                                                  KIND == 1 ? a.acc2_s + zs * ((size_t)a.HW * 2) : nullptr, lane);
     }
 }
 
@@ -468,9 +595,10 @@ void pipe_set_tail_percent(long long p) { g_pipe_tail_percent = p < 0 ? DCB_TAIL
 int g_pipe_ring_slots = 1;
 void pipe_set_ring_slots(long long n) { g_pipe_ring_slots = n == 1 ? 1 : 2; }
 
-static long long group_frames(long long N, long long H, long long W) {
-    const long long gb = g_pipe_group_bytes > 0 ? g_pipe_group_bytes : kGroupBytes;
-    long long g = gb / (H * W * 16 > 0 ? H * W * 16 : 1);
+static long long group_frames(long long N, long long H, long long W, long long cell_bytes = 16) {
+    // the recipe pass keeps 24 bytes per pixel resident: its slot may be half as large again (one 1080p frame = 47.5 MiB)
+    const long long gb = (g_pipe_group_bytes > 0 ? g_pipe_group_bytes : kGroupBytes) * cell_bytes / 16;
+    long long g = gb / (H * W * cell_bytes > 0 ? H * W * cell_bytes : 1);
     if (g < 1) g = 1;
     if (g > 32767) g = 32767;                    // gridDim.z = frames normalised + frames scattered <= 65535
     return g > N ? (N < 1 ? 1 : N) : g;
@@ -484,14 +612,14 @@ long long pipe_acc_bytes(long long N, long long H, long long W) {
 
 long long pipe_workspace(long long N, long long H, long long W) { return pipe_acc_bytes(N, H, W); }
 
-template <class T, class TF, int MODE, int CA> static int launch_steps(PipeArgs& a, cudaStream_t st) {
+template <class T, class TF, int MODE, int CA, int KIND = 0> static int launch_steps(PipeArgs& a, cudaStream_t st) {
     const int groups = (a.N + a.G - 1) / a.G;
     const size_t slot_floats = (size_t)a.G * a.HW * 4;
     // both item kinds cover 32 * kStripH pixels, so one (x, y) extent serves the normalise chunks and the scatter strips
     const unsigned gx = (unsigned)a.tiles_x;
     const unsigned rows_n = (unsigned)((a.tn + a.tiles_x - 1) / a.tiles_x);
     const unsigned gy = rows_n > (unsigned)a.tiles_y ? rows_n : (unsigned)a.tiles_y;
-    const bool one_slot = g_pipe_ring_slots == 1;
+    const bool one_slot = g_pipe_ring_slots == 1 || KIND == 1;
     for (int k = 0; k <= (one_slot ? 2 * groups - 1 : groups); ++k) {
         // two slots: launch k = normalise(group k-1) + scatter(group k); one slot: launch 2g = scatter(g), launch 2g+1 = normalise(g)
         const int gs = one_slot ? ((k & 1) ? -1 : k / 2) : (k < groups ? k : -1);
@@ -508,7 +636,7 @@ template <class T, class TF, int MODE, int CA> static int launch_steps(PipeArgs&
         attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
         attr[0].val.programmaticStreamSerializationAllowed = 1;
         cfg.attrs = attr; cfg.numAttrs = 1;
-        DCB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, k_splat_step<T, TF, MODE, CA>, a));
+        DCB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, k_splat_step<T, TF, MODE, CA, KIND>, a));
         count_launch();
     }
     return DCB_OK;
@@ -549,7 +677,7 @@ bool pipe_supported(const DcbTensor* in, const DcbTensor* flow, const DcbTensor*
 int splat_pipe_impl(const DcbTensor* in, const DcbTensor* flow, const DcbTensor* metric, const DcbTensor* out,
                     const DcbTensor* norm, const DcbTensor* mask, void* ws, int mode, int eps, bool ws_clean,
                     cudaStream_t st, bool ones_metric, const DcbTensor* mask_out) {
-    PipeArgs a;
+    PipeArgs a = {};
     a.ones = ones_metric ? 1 : 0;
     a.epi = mask_out ? 1 : 0;
     a.epi_flow = make_view(mask_out ? flow : nullptr);
@@ -578,6 +706,55 @@ int splat_pipe_impl(const DcbTensor* in, const DcbTensor* flow, const DcbTensor*
     if (in->dtype == DCB_BF16)
         return ff ? launch_pipe<__nv_bfloat16, float>(a, mode, st) : launch_pipe<__nv_bfloat16, __nv_bfloat16>(a, mode, st);
     return set_error(DCB_E_DTYPE, "splat_pipe: unsupported dtype %d", in->dtype);
+}
+
+// ---------------------------------------------------------------------------------------------
+// conditioning recipe, second pass: image1 AND flow2 splatted by flow1 in one scatter (shared footprints, shared weight
+// channel), then one epilogue that normalises, tests occlusion, fuses and writes fused + residual.
+// Workspace: [G frames of float4 cells][G frames of float2 cells], all-zero on entry and on exit.
+// ---------------------------------------------------------------------------------------------
+long long recipe_pipe_workspace(long long N, long long H, long long W) {
+    const long long G = group_frames(N, H, W, 24);
+    return align_up(G * H * W * 16, 256) + align_up(G * H * W * 8, 256);
+}
+
+template <class T> static int launch_recipe(PipeArgs& a, cudaStream_t st) {
+    switch (a.C) {
+        case 1: return launch_steps<T, T, DCB_MODE_SOFT, 2, 1>(a, st);
+        case 2: return launch_steps<T, T, DCB_MODE_SOFT, 3, 1>(a, st);
+        case 3: return launch_steps<T, T, DCB_MODE_SOFT, 4, 1>(a, st);
+    }
+    return set_error(DCB_E_LIMIT, "recipe_pipe: %d image channels", a.C);
+}
+
+// Preconditions (checked by the caller): 1 <= C <= 3, one dtype (F32/BF16) for every tensor, contiguous outputs,
+// pipe_supported() for every strided input, workspace >= recipe_pipe_workspace() and all-zero.
+int recipe_pipe_impl(const DcbTensor* image1, const DcbTensor* flow1, const DcbTensor* flow2, const DcbTensor* gt,
+                     const DcbTensor* fused, const DcbTensor* residual, const DcbTensor* occ_fwd, const DcbTensor* occ_bwd,
+                     void* ws, int variant, cudaStream_t st) {
+    PipeArgs a = {};
+    a.ones = 1; a.epi = 3;
+    a.in = make_view(image1); a.flow = make_view(flow1); a.metric = make_view(nullptr); a.mask = make_view(nullptr);
+    a.in2 = make_view(flow2); a.epi_flow = make_view(flow1); a.gt = make_view(gt);
+    a.N = (int)image1->size[0]; a.C = (int)image1->size[1]; a.H = (int)image1->size[2]; a.W = (int)image1->size[3];
+    a.HW = (unsigned)(image1->size[2] * image1->size[3]);
+    a.eps = DCB_EPS_ADD;
+    a.G = (int)group_frames(a.N, a.H, a.W, 24);
+    a.tiles_x = (a.W + 31) / 32;
+    a.ny_big = a.H / kStripH;
+    a.tiles_y = a.ny_big + (a.H - a.ny_big * kStripH + kRows - 1) / kRows;
+    a.ts = a.tiles_x * a.tiles_y;
+    a.tn = (int)((a.HW + kChunk - 1) / kChunk);
+    a.out = fused->ptr; a.residual = residual->ptr; a.norm = nullptr;
+    a.occ_other = occ_fwd->ptr;
+    a.mask_out = occ_bwd ? occ_bwd->ptr : nullptr;
+    a.variant = variant;
+    a.vec4 = 0;
+    a.acc = (float*)ws;
+    a.acc2_s = a.acc2_n = (float*)((char*)ws + align_up((long long)a.G * a.HW * 16, 256));
+    if (image1->dtype == DCB_F32) return launch_recipe<float>(a, st);
+    if (image1->dtype == DCB_BF16) return launch_recipe<__nv_bfloat16>(a, st);
+    return set_error(DCB_E_DTYPE, "recipe_pipe: unsupported dtype %d", image1->dtype);
 }
 
 }  // namespace dcb

@@ -117,6 +117,58 @@ def test_residual_recipe(dcb, orc, variant, shape):
         assert_close(fused, fc, 1e-5, "fused vs composed")
 
 
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("variant", ["dataset", "wrapper"])
+@pytest.mark.parametrize("shape,group_frames", [((2, 3, 96, 120), 0), ((5, 3, 33, 47), 2), ((3, 1, 70, 150), 1), ((4, 2, 45, 64), 3)])
+def test_residual_recipe_two_pass_pipeline(dcb, orc, variant, shape, group_frames, dtype):
+    """The two-pass recipe (csrc/splat_pipe.cu recipe_pipe_impl: image1 and flow2 ride on flow1 in one scatter, recipe
+    epilogue) on frames the automatic dispatch would hand to the small-frame kernels: pinned to the accumulator pipeline,
+    through several (ragged) frame groups, vs the oracle and vs the composition of the single-op kernels, and the
+    kept-zero workspace afterwards (dataset.py:233-265, residual_utils.py:159-199)."""
+    n, c, h, w = shape
+    L = dcb._lib
+    L.set_option("fwd_path", 1)
+    L.set_option("pipe_group_bytes", group_frames * h * w * 16)
+    L.release_workspaces()
+    try:
+        g = torch.Generator().manual_seed(23)
+        img = torch.rand(n, c, h, w, generator=g); gt = torch.rand(n, c, h, w, generator=g)
+        f1, f2 = _flows(6, n, h, w, 2.0)
+        if dtype == torch.bfloat16:
+            img, gt, f1, f2 = (t.bfloat16().float() for t in (img, gt, f1, f2))
+        fused_r, res_r, of_r, ob_r = orc.residual_recipe(img, f1, f2, gt, variant)
+        dev = [t.cuda().to(dtype) for t in (img, f1, f2, gt)]
+        launches0 = dcb.launch_count()
+        fused, res, of, ob = dcb.residual_conditioning(*dev, variant, return_masks=True)
+        groups = 1 if group_frames == 0 else -(-n // group_frames)
+        assert dcb.launch_count() - launches0 == 4 * groups          # two passes, each one scatter + one epilogue launch per frame group
+        fused2, res2, of2, ob2 = dcb.residual_conditioning(*dev, variant, return_masks=True)
+        assert torch.equal(fused, fused2) or dtype == torch.float32          # fp32 atomics may reorder; bf16 rounds it away mostly
+        tol = 1e-5 if dtype == torch.float32 else 1.6e-2
+        agree = ((of.float().cpu() == of_r) & (ob.float().cpu() == ob_r))
+        if dtype == torch.float32:
+            assert _mask_mismatch(of, of_r, f1, f2, orc) + _mask_mismatch(ob, ob_r, f2, f1, orc) <= 2
+        else:
+            assert agree.float().mean() > 0.995
+        sel = agree.expand_as(fused_r)
+        assert_close(fused.float().cpu()[sel], fused_r[sel], tol, "fused")
+        assert_close(res.float().cpu()[sel], res_r[sel], tol, "residual")
+        if dtype == torch.float32:
+            from importlib import import_module
+            ru = import_module(dcb.__name__ + ".residual_utils")
+            fc, rc_, ofc, obc = ru._composed(*dev, variant)
+            if torch.equal(ofc, of) and torch.equal(obc, ob):
+                assert_close(fused, fc, 1e-5, "fused vs composed")
+                assert_close(res, rc_, 1e-5, "residual vs composed")
+        # the accumulators were left all-zero: the next splat through the same workspace is right
+        tin, flow, metric, _ = make_inputs(3, 2, 3, h, w)
+        assert_close(dcb.softsplat(tin.cuda(), flow.cuda(), metric.cuda(), "soft"), orc.softsplat(tin, flow, metric, "soft"), 1e-5, "after recipe")
+    finally:
+        L.set_option("fwd_path", 0)
+        L.set_option("pipe_group_bytes", 0)
+        L.release_workspaces()
+
+
 def test_residual_dataset_wrappers(dcb, orc):
     import numpy as np
     rng = np.random.default_rng(0)

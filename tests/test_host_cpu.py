@@ -69,7 +69,7 @@ def test_workspace_queries_need_no_gpu():
     assert lib.dcb_splat_bwd_workspace_bytes(64, 3, 1080, 1920, L.DCB_F32, L.MODE_SOFT, 0) == 64 * 1080 * 1920 * 16      # one packed float4 per target
     assert lib.dcb_splat_bwd_workspace_bytes(8, 64, 256, 256, L.DCB_F32, L.MODE_SOFT, 0) == 8 * 256 * 256 * 8
     assert lib.dcb_occlusion_mask_workspace_bytes(2, 64, 64) == 2 * 64 * 64 * 16
-    assert lib.dcb_residual_workspace_bytes(1, 3, 1080, 1920) == 1080 * 1920 * (16 + 8)
+    assert lib.dcb_residual_workspace_bytes(1, 3, 1080, 1920) == 1080 * 1920 * (24 + 8)      # float4 + float2 cells, two mask planes
 
 
 def test_cpu_tensors_are_refused_like_the_reference():

@@ -118,6 +118,13 @@ __device__ __forceinline__ float ld_stream(const __nv_bfloat16* p) { return __bf
 __device__ __forceinline__ void st_stream(float* p, float v) { __stcs(p, v); }
 __device__ __forceinline__ void st_stream(__nv_bfloat16* p, float v) { __stcs(p, __float2bfloat16_rn(v)); }
 
+// two neighbouring elements with one load (the address is aligned to the pair)
+__device__ __forceinline__ float2 ld2_stream(const float* p) { return __ldcs((const float2*)p); }
+__device__ __forceinline__ float2 ld2_stream(const __nv_bfloat16* p) {
+    const unsigned u = __ldcs((const unsigned*)p);
+    return __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u));
+}
+
 // rounded (non-contracted) arithmetic: the reference rounds every product before the atomic add
 __device__ __forceinline__ float mul_rn(float a, float b) { return __fmul_rn(a, b); }
 __device__ __forceinline__ double mul_rn(double a, double b) { return __dmul_rn(a, b); }
@@ -176,11 +183,13 @@ __device__ __forceinline__ void red_add_v2(float* p, float a, float b) {
 }
 
 // occlusion test of compute_mask (controlnet/control_utils.py:15-16) on the soft splat (wx, wy) / (d + 1e-7) of one motion
-// field, compared with the other field (mx, my) at the same pixel: ||m + w|| > 0.3
+// field, compared with the other field (mx, my) at the same pixel: ||m + w|| > 0.3.
+// The square root is never taken: sqrt is monotone and correctly rounded, so sqrtf(s) > 0.3f holds exactly when
+// s > 0x3DB851ED (0.09000001f, the largest float whose root still rounds to 0.3f or below; checked exhaustively around it).
 __device__ __forceinline__ float occlusion(float wx, float wy, float d, float mx, float my) {
     const float n = add_rn(d, 0.0000001f);
     const float ex = add_rn(mx, wx / n), ey = add_rn(my, wy / n);
-    return sqrtf(add_rn(mul_rn(ex, ex), mul_rn(ey, ey))) > 0.3f ? 1.f : 0.f;
+    return add_rn(mul_rn(ex, ex), mul_rn(ey, ey)) > __uint_as_float(0x3DB851EDu) ? 1.f : 0.f;
 }
 
 // Bilinear footprint of one source pixel: softsplat.py:298-318 (and :386-404, :457-470).

@@ -95,6 +95,7 @@ struct PipeArgs {
     void* residual;          // epi 3: [N,C,H,W]
     const void* occ_other;   // epi 3: the occlusion plane computed by epi 2, [N,1,H,W] in T
     int variant;             // epi 3: DCB_RECIPE_*
+    int flat2;               // epi 1, 3: two-pixel epilogue (even H*W; the tensors it reads are plain contiguous planes, pair-aligned)
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -466,6 +467,39 @@ __device__ __forceinline__ void mask_chunk(const PipeArgs& a, int frame, int chu
     }
 }
 
+// two consecutive pixels per lane (a.flat2: even H*W, the compared flow is a plain [N,2,H,W] plane pair whose pixel pairs are
+// aligned): one 256-bit accumulator load, one 64-bit load per flow plane, one paired store -- and no row / column arithmetic
+template <class T>
+__device__ __forceinline__ void mask_chunk_v2(const PipeArgs& a, int frame, int chunk, float* acc, int lane) {
+    constexpr int kGroups = 2;                                            // 4 pixels per lane in flight (register budget of the step kernel)
+    T* out = (T*)a.mask_out + (long long)frame * a.HW;
+    const T* fbase = (const T*)a.epi_flow.p + frame * a.epi_flow.sN;
+#pragma unroll 1
+    for (int b = 0; b < kChunk / (64 * kGroups); ++b) {
+        const unsigned base = (unsigned)chunk * kChunk + b * (64 * kGroups);
+        if (base >= a.HW) break;
+        float4 s[kGroups][2]; float2 mx[kGroups], my[kGroups];
+#pragma unroll
+        for (int g = 0; g < kGroups; ++g) {
+            const unsigned r = base + g * 64 + lane * 2;
+            s[g][0] = s[g][1] = make_float4(0.f, 0.f, 0.f, 0.f); mx[g] = my[g] = make_float2(0.f, 0.f);
+            if (r < a.HW) {
+                ld_cells2(acc + (size_t)r * 4, s[g][0], s[g][1]);
+                mx[g] = ld2_stream(fbase + r); my[g] = ld2_stream(fbase + a.epi_flow.sC + r);
+            }
+        }
+#pragma unroll
+        for (int g = 0; g < kGroups; ++g) {
+            const unsigned r = base + g * 64 + lane * 2;
+            if (r < a.HW) {
+                zero_cells2(acc + (size_t)r * 4);
+                st_stream2(out + r, occlusion(s[g][0].x, s[g][0].y, s[g][0].z, mx[g].x, my[g].x),
+                           occlusion(s[g][1].x, s[g][1].y, s[g][1].z, mx[g].y, my[g].y));
+            }
+        }
+    }
+}
+
 // ---------------------------------------------------------------------------------------------
 // conditioning-recipe epilogue (dataset.py:233-265, residual_utils.py:159-199): the float4 cells hold the soft splat of
 // image1 by flow1 (C channels + weight), the float2 cells the soft splat of flow2 by the same flow1 (the weight is shared).
@@ -539,6 +573,88 @@ __device__ __forceinline__ void recipe_chunk(const PipeArgs& a, int frame, int c
     }
 }
 
+// the recipe epilogue on two consecutive pixels per lane (a.flat2: see mask_chunk_v2; gt is a plain [N,C,H,W] tensor too)
+template <class T, int C> __device__ __forceinline__ void recipe_pixel(const PipeArgs& a, const float (&sv)[4], float qx, float qy, float mx, float my,
+                                                                      float of, const float* gv, float& ob, float* fused, float* resid) {
+    const float d = sv[C];
+    ob = occlusion(qx, qy, d, mx, my);                                   // control_utils.py:15-16
+    const float scale = __frcp_rn(add_rn(d, 0.0000001f));                // softsplat.py:256-258, :270
+    // masks are 0 or 1, so conf / (conf.sum() + 1e-6) takes one of three values: 0, 1 / (1 + 1e-6), 1 / (2 + 1e-6) -- the two
+    // quotients are IEEE divisions of constants (folded at compile time), exactly what the per-pixel division would give
+    const float one_of_one = 1.f / (1.f + 0.000001f), one_of_two = 1.f / (2.f + 0.000001f);
+    float w0, w1;
+    if (a.variant == DCB_RECIPE_DATASET) {            // dataset.py:255-259: masks are the confidences
+        const bool both = of != 0.f && ob != 0.f;
+        w0 = of != 0.f ? (both ? one_of_two : one_of_one) : 0.f;
+        w1 = ob != 0.f ? (both ? one_of_two : one_of_one) : 0.f;
+    } else {                                          // residual_utils.py:181-185: ones are the confidences
+        w0 = one_of_two; w1 = one_of_two;
+    }
+    const bool hole = a.variant == DCB_RECIPE_WRAPPER && of != 0.f && ob != 0.f;   // residual_utils.py:190-193: (occ_fwd + occ_bwd) > 1.5
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+        const float wv = round_as<T>(mul_rn(sv[c], scale));              // warped1 == warped2
+        float f = add_rn(mul_rn(w0, wv), mul_rn(w1, wv));
+        if (hole) f = mul_rn(0.5f, add_rn(wv, wv));
+        fused[c] = f;
+        resid[c] = sub_rn(gv[c], round_as<T>(f));                        // residual of the stored (rounded) value
+    }
+}
+
+template <class T, int CA>
+__device__ __forceinline__ void recipe_chunk_v2(const PipeArgs& a, int frame, int chunk, float* acc, float* acc2, int lane) {
+    constexpr int C = CA - 1;
+    constexpr int kGroups = kRPer / 2;
+    T* fo = (T*)a.out + (long long)frame * C * a.HW;
+    T* ro = (T*)a.residual + (long long)frame * C * a.HW;
+    const T* oo = (const T*)a.occ_other + (long long)frame * a.HW;
+    T* mo = a.mask_out ? (T*)a.mask_out + (long long)frame * a.HW : nullptr;
+    const T* fbase = (const T*)a.epi_flow.p + frame * a.epi_flow.sN;
+    const T* gbase = (const T*)a.gt.p + frame * a.gt.sN;
+#pragma unroll 1
+    for (int b = 0; b < kChunk / (32 * kRPer); ++b) {
+        const unsigned base = (unsigned)chunk * kChunk + b * (32 * kRPer);
+        if (base >= a.HW) break;
+        float4 s[kGroups][2], q[kGroups]; float2 mx[kGroups], my[kGroups], of[kGroups], gv[kGroups][C > 0 ? C : 1];
+#pragma unroll
+        for (int g = 0; g < kGroups; ++g) {                               // every load of the batch in flight first
+            const unsigned r = base + g * 64 + lane * 2;
+            s[g][0] = s[g][1] = q[g] = make_float4(0.f, 0.f, 0.f, 0.f);
+            mx[g] = my[g] = of[g] = make_float2(0.f, 0.f);
+#pragma unroll
+            for (int c = 0; c < C; ++c) gv[g][c] = make_float2(0.f, 0.f);
+            if (r < a.HW) {
+                ld_cells2(acc + (size_t)r * 4, s[g][0], s[g][1]);
+                q[g] = __ldcg((const float4*)(acc2 + (size_t)r * 2));
+                mx[g] = ld2_stream(fbase + r); my[g] = ld2_stream(fbase + a.epi_flow.sC + r);
+                of[g] = ld2_stream(oo + r);
+#pragma unroll
+                for (int c = 0; c < C; ++c) gv[g][c] = ld2_stream(gbase + (long long)c * a.gt.sC + r);
+            }
+        }
+#pragma unroll
+        for (int g = 0; g < kGroups; ++g) {
+            const unsigned r = base + g * 64 + lane * 2;
+            if (r < a.HW) {
+                zero_cells2(acc + (size_t)r * 4);                         // accumulators leave the kernel all-zero
+                __stcg((float4*)(acc2 + (size_t)r * 2), make_float4(0.f, 0.f, 0.f, 0.f));
+                const float s0[4] = {s[g][0].x, s[g][0].y, s[g][0].z, s[g][0].w}, s1[4] = {s[g][1].x, s[g][1].y, s[g][1].z, s[g][1].w};
+                float g0[C > 0 ? C : 1], g1[C > 0 ? C : 1], f0[C > 0 ? C : 1], f1[C > 0 ? C : 1], r0[C > 0 ? C : 1], r1[C > 0 ? C : 1], ob0, ob1;
+#pragma unroll
+                for (int c = 0; c < C; ++c) { g0[c] = gv[g][c].x; g1[c] = gv[g][c].y; }
+                recipe_pixel<T, C>(a, s0, q[g].x, q[g].y, mx[g].x, my[g].x, of[g].x, g0, ob0, f0, r0);
+                recipe_pixel<T, C>(a, s1, q[g].z, q[g].w, mx[g].y, my[g].y, of[g].y, g1, ob1, f1, r1);
+                if (mo) st_stream2(mo + r, ob0, ob1);
+#pragma unroll
+                for (int c = 0; c < C; ++c) {
+                    st_stream2(fo + (size_t)c * a.HW + r, f0[c], f1[c]);
+                    st_stream2(ro + (size_t)c * a.HW + r, r0[c], r1[c]);
+                }
+            }
+        }
+    }
+}
+
 // ---------------------------------------------------------------------------------------------
 // the step kernel: warp w of CTA b owns item 4b + w; normalise items first, then scatter items
 // ---------------------------------------------------------------------------------------------
@@ -560,8 +676,12 @@ __global__ void __launch_bounds__(kPipeThreads, KIND ? kMinCtasRecipe : kMinCtas
         if (chunk >= (unsigned)a.tn) return;
         const int f = a.n_frame0 + (int)z;
         float* acc = a.acc_n + z * frame_floats;
-        if (KIND == 1) { recipe_chunk<T, CA>(a, f, (int)chunk, acc, a.acc2_n + z * ((size_t)a.HW * 2), lane); return; }
-        if (a.epi == 1) mask_chunk<T>(a, f, (int)chunk, acc, lane);
+        if (KIND == 1) {
+            if (a.flat2) recipe_chunk_v2<T, CA>(a, f, (int)chunk, acc, a.acc2_n + z * ((size_t)a.HW * 2), lane);
+            else recipe_chunk<T, CA>(a, f, (int)chunk, acc, a.acc2_n + z * ((size_t)a.HW * 2), lane);
+            return;
+        }
+        if (a.epi == 1) { if (a.flat2) mask_chunk_v2<T>(a, f, (int)chunk, acc, lane); else mask_chunk<T>(a, f, (int)chunk, acc, lane); }
 #if DCB_NORM_V == 4
         else if (a.vec4 && a.mask.p == nullptr) normalize_chunk_v4<T, MODE, CA>(a, f, (int)chunk, acc, lane);
 #elif DCB_NORM_V == 2
@@ -673,6 +793,14 @@ bool pipe_supported(const DcbTensor* in, const DcbTensor* flow, const DcbTensor*
     return offsets_fit32(in) && offsets_fit32(flow) && offsets_fit32(metric) && in->size[2] * in->size[3] < (1ll << 28);
 }
 
+
+// a tensor whose H x W planes are contiguous and whose pixel pairs are aligned for one paired load / store
+static bool planes_pair_aligned(const DcbTensor* t, long long W) {
+    if (!t) return true;
+    const long long es = elem_size(t->dtype);
+    return t->stride[3] == 1 && t->stride[2] == W && t->stride[1] % 2 == 0 && t->stride[0] % 2 == 0 && ((uintptr_t)t->ptr % (2 * es)) == 0;
+}
+
 // Preconditions (checked by the caller): C + (mode != SUM) <= 4, dtype F32/BF16, workspace >= pipe_workspace().
 int splat_pipe_impl(const DcbTensor* in, const DcbTensor* flow, const DcbTensor* metric, const DcbTensor* out,
                     const DcbTensor* norm, const DcbTensor* mask, void* ws, int mode, int eps, bool ws_clean,
@@ -700,6 +828,7 @@ int splat_pipe_impl(const DcbTensor* in, const DcbTensor* flow, const DcbTensor*
     a.norm = norm ? norm->ptr : nullptr;
     a.acc = (float*)ws;
     a.vec4 = (a.HW % 4 == 0 && out && ((uintptr_t)out->ptr & 15) == 0 && (!norm || ((uintptr_t)norm->ptr & 15) == 0)) ? 1 : 0;
+    a.flat2 = (mask_out && a.HW % 2 == 0 && planes_pair_aligned(flow, a.W) && planes_pair_aligned(mask_out, a.W)) ? 1 : 0;
     if (!ws_clean) DCB_CHECK_CUDA(cudaMemsetAsync(ws, 0, (size_t)pipe_workspace(a.N, a.H, a.W), st));
     const bool ff = flow->dtype == DCB_F32;
     if (in->dtype == DCB_F32) return launch_pipe<float, float>(a, mode, st);
@@ -750,6 +879,9 @@ int recipe_pipe_impl(const DcbTensor* image1, const DcbTensor* flow1, const DcbT
     a.mask_out = occ_bwd ? occ_bwd->ptr : nullptr;
     a.variant = variant;
     a.vec4 = 0;
+    a.flat2 = (a.HW % 2 == 0 && planes_pair_aligned(flow1, a.W) && planes_pair_aligned(gt, a.W) && planes_pair_aligned(fused, a.W) &&
+               planes_pair_aligned(residual, a.W) && planes_pair_aligned(occ_fwd, a.W) && planes_pair_aligned(occ_bwd, a.W) &&
+               (((uintptr_t)ws + align_up((long long)a.G * a.HW * 16, 256)) & 15) == 0) ? 1 : 0;
     a.acc = (float*)ws;
     a.acc2_s = a.acc2_n = (float*)((char*)ws + align_up((long long)a.G * a.HW * 16, 256));
     if (image1->dtype == DCB_F32) return launch_recipe<float>(a, st);

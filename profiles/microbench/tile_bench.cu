@@ -176,6 +176,115 @@ __global__ void __launch_bounds__(32) k_window(const float* __restrict__ in, con
     if (spilled && nspill) atomicAdd(spilled, (unsigned long long)nspill);
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------------
+// round-2 probe 2: SLIDING window.  One warp walks down a 32-column strip of SEG rows; its private window is a ring of R
+// rows x WXC float4 cells that follows the walk (target rows [j, j + 2 MY] relative to the strip's landing row are live
+// while source row j is processed).  Contributions are added with PLAIN ld.shared / st.shared: lanes whose footprints
+// share a cell-key are ranked with match.any and take turns, so no instruction ever writes one address twice (no CAS
+// loops).  A ring row that falls out of the window is flushed once: consecutive lanes red consecutive non-empty cells
+// (full sectors), and zero them.  Pieces that land outside the window go straight to L2 (counted in `spilled`).
+// ---------------------------------------------------------------------------------------------------------------------
+template <int SEG, int MX, int MY, int R, int KR>
+__global__ void __launch_bounds__(32) k_slide(const float* __restrict__ in, const float* __restrict__ metric,
+                                              const float* __restrict__ flow, float* acc, unsigned long long* spilled) {
+    constexpr int WXC = 32 + 2 * MX;
+    static_assert((R & (R - 1)) == 0 && R >= 2 * MY + 2, "ring: power of two, at least one spare row");
+    static_assert(SEG % KR == 0, "whole load groups");
+    __shared__ float4 ring[R * WXC];
+    const int lane = threadIdx.x;
+    const unsigned full = 0xffffffffu;
+    const int tiles_x = (W + 31) / 32;
+    const int tx = blockIdx.x % tiles_x, ty = blockIdx.x / tiles_x;
+    const int x = tx * 32 + lane, y_first = ty * SEG;
+    const bool xin = x < W;
+    const int xs = xin ? x : W - 1;
+    for (int i = lane; i < R * WXC; i += 32) ring[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    // window offset: the flow in the middle of the strip
+    int cx, cy;
+    {
+        const int ym = min(y_first + SEG / 2, H - 1), xm = min(tx * 32 + 16, W - 1);
+        cx = (int)rintf(__ldg(flow + ym * W + xm)); cy = (int)rintf(__ldg(flow + HW + ym * W + xm));
+    }
+    const int colbase = tx * 32 + cx - MX;          // frame column of window column 0
+    const int row0 = y_first + cy - MY;             // frame row of ring time 0
+    unsigned nspill = 0;
+    __syncwarp();
+
+    auto flush = [&](int t) {                       // ring time t -> frame row row0 + t
+        const int gy = row0 + t;
+        float4* rowp = ring + (t & (R - 1)) * WXC;
+#pragma unroll
+        for (int it = 0; it < (WXC + 31) / 32; ++it) {
+            const int c = lane + 32 * it;
+            if (c < WXC) {
+                const float4 v = rowp[c];
+                if (v.x != 0.f || v.y != 0.f || v.z != 0.f || v.w != 0.f) {
+                    red4(acc + ((size_t)gy * W + (colbase + c)) * 4, v.x, v.y, v.z, v.w);
+                    rowp[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+            }
+        }
+    };
+
+#pragma unroll 1
+    for (int g = 0; g < SEG / KR; ++g) {
+        const int yb = y_first + g * KR;
+        if (yb >= H) break;
+        float fxv[KR], fyv[KR], mv[KR], iv[KR][3];
+#pragma unroll
+        for (int r = 0; r < KR; ++r) {
+            const int y = min(yb + r, H - 1);
+            const int o = y * W + xs;
+            fxv[r] = __ldcs(flow + o); fyv[r] = __ldcs(flow + HW + o); mv[r] = __ldcs(metric + o);
+            iv[r][0] = __ldcs(in + o); iv[r][1] = __ldcs(in + HW + o); iv[r][2] = __ldcs(in + 2 * HW + o);
+        }
+#pragma unroll
+        for (int r = 0; r < KR; ++r) {
+            const int y = yb + r, j = g * KR + r;
+            const bool live = xin && y < H;
+            Foot f = foot(x, y, fxv[r], fyv[r]);
+            const float gexp = expf(mv[r]);
+            const float v[4] = {iv[r][0] * gexp, iv[r][1] * gexp, iv[r][2] * gexp, gexp};
+            const bool any = live && (f.b[0] || f.b[1] || f.b[2] || f.b[3]);
+            const int col = f.x0 - colbase, tr = f.y0 - row0;          // window column, ring time of the NW corner
+            const bool inwin = any && col >= 0 && col <= WXC - 2 && tr >= j && tr + 1 <= j + 2 * MY;
+            if (any && !inwin) {                                        // outside the window: straight to L2
+                float* a = acc + ((size_t)f.y0 * W + f.x0) * 4;
+                const int off[4] = {0, 4, 4 * W, 4 * W + 4};
+#pragma unroll
+                for (int k = 0; k < 4; ++k) if (f.b[k]) red4(a + off[k], v[0] * f.w[k], v[1] * f.w[k], v[2] * f.w[k], v[3] * f.w[k]);
+                ++nspill;
+            }
+            // lanes that share a footprint take turns
+            const int key = inwin ? (tr - j) * 64 + col : 4096 + lane;
+            const unsigned same = __match_any_sync(full, key);
+            const int rank = __popc(same & ((1u << lane) - 1u));
+            const int rounds = __reduce_max_sync(full, inwin ? rank : 0);
+            float4* cN = ring + (tr & (R - 1)) * WXC + col;
+            float4* cS = ring + ((tr + 1) & (R - 1)) * WXC + col;
+            for (int rd = 0; rd <= rounds; ++rd) {
+                const bool mine = inwin && rank == rd;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    float4* c = ((k >> 1) ? cS : cN) + (k & 1);
+                    if (mine && f.b[k]) {
+                        float4 a = *c;
+                        a.x += v[0] * f.w[k]; a.y += v[1] * f.w[k]; a.z += v[2] * f.w[k]; a.w += v[3] * f.w[k];
+                        *c = a;
+                    }
+                    __syncwarp();
+                }
+            }
+            if (y < H) flush(j);                                        // ring time j is out of reach of every later row
+            __syncwarp();
+        }
+    }
+    const int rows_done = min(SEG, H - y_first);
+    for (int t = rows_done; t < rows_done + 2 * MY + 1; ++t) flush(t);
+    if (spilled && nspill) atomicAdd(spilled, (unsigned long long)nspill);
+}
+
 struct Timer {
     cudaEvent_t a, b;
     Timer() { CK(cudaEventCreate(&a)); CK(cudaEventCreate(&b)); }
@@ -200,6 +309,35 @@ static void bench_window(Timer& T, const char* name, const float* in, const floa
     printf("  window %-22s: %7.1f us/frame   %.2f %% of corners spilled past the window\n", name, ms * 1e3, 100.0 * sp / 36.0 / (4.0 * HW));
 }
 
+
+template <int SEG, int MX, int MY, int R, int KR>
+static void bench_slide(Timer& T, const char* name, const float* in, const float* metric, const float* flow, float* acc,
+                        unsigned long long* spilled, int POOL) {
+    const int strips = ((W + 31) / 32) * ((H + SEG - 1) / SEG);
+    CK(cudaMemset(spilled, 0, 8));
+    float ms = T.run([&](int i) { size_t s = i % POOL;
+        k_slide<SEG, MX, MY, R, KR><<<strips, 32>>>(in + s * 3 * HW, metric + s * HW, flow + s * 2 * HW, acc, spilled); }, 4, 32);
+    unsigned long long sp; CK(cudaMemcpy(&sp, spilled, 8, cudaMemcpyDeviceToHost));
+    printf("  slide  %-22s: %7.1f us/frame   %.2f %% of pixels spilled past the window\n", name, ms * 1e3, 100.0 * sp / 36.0 / (1.0 * HW));
+}
+
+// correctness of k_slide against k_naive on one frame (max |difference| relative to max |value|)
+template <int SEG, int MX, int MY, int R, int KR>
+static void check_slide(const float* in, const float* metric, const float* flow, float* acc, float* acc2) {
+    const int strips = ((W + 31) / 32) * ((H + SEG - 1) / SEG);
+    CK(cudaMemset(acc, 0, (size_t)HW * 16)); CK(cudaMemset(acc2, 0, (size_t)HW * 16));
+    k_naive<<<(HW + 255) / 256, 256>>>(in, metric, flow, acc);
+    k_slide<SEG, MX, MY, R, KR><<<strips, 32>>>(in, metric, flow, acc2, nullptr);
+    CK(cudaDeviceSynchronize());
+    float* a = (float*)malloc((size_t)HW * 16); float* b = (float*)malloc((size_t)HW * 16);
+    CK(cudaMemcpy(a, acc, (size_t)HW * 16, cudaMemcpyDeviceToHost)); CK(cudaMemcpy(b, acc2, (size_t)HW * 16, cudaMemcpyDeviceToHost));
+    double md = 0, mx = 0;
+    for (size_t i = 0; i < (size_t)HW * 4; ++i) { md = fmax(md, fabs((double)a[i] - b[i])); mx = fmax(mx, fabs((double)a[i])); }
+    printf("  check slide vs naive: max |diff| %.3g of max %.3g\n", md, mx);
+    free(a); free(b);
+    CK(cudaMemset(acc, 0, (size_t)HW * 16));
+}
+
 int main() {
     cudaDeviceProp prop; CK(cudaGetDeviceProperties(&prop, 0));
     printf("# device %s, %d SMs; one 1080p frame per launch into one 33 MB accumulator (L2-resident)\n", prop.name, prop.multiProcessorCount);
@@ -210,7 +348,10 @@ int main() {
     CK(cudaMalloc(&acc, (size_t)HW * 16)); CK(cudaMalloc(&spilled, 8));
     CK(cudaMemset(in, 0, (size_t)POOL * 3 * HW * 4)); CK(cudaMemset(metric, 0, (size_t)POOL * HW * 4)); CK(cudaMemset(acc, 0, (size_t)HW * 16));
     for (int pat = 0; pat < 3; ++pat) k_make_flow<<<(POOL * HW + 255) / 256, 256>>>(flow[pat], POOL, pat);
+    k_make_flow<<<(POOL * HW + 255) / 256, 256>>>(metric, POOL / 2, 0);          // metric / input values: any smooth non-zero pattern
+    k_make_flow<<<(POOL * HW + 255) / 256, 256>>>(in, POOL, 1);
     CK(cudaDeviceSynchronize());
+    float* acc2; CK(cudaMalloc(&acc2, (size_t)HW * 16));
     Timer T;
     const char* pname[3] = {"smooth (|d/dx| ~ 0.03)", "rough (|d/dx| ~ 0.25)", "random +-32 px"};
     const int blocks = (HW + 255) / 256;
@@ -220,6 +361,12 @@ int main() {
         printf("  naive 4 x red.v4              : %7.1f us/frame\n", ms * 1e3);
         ms = T.run([&](int i) { size_t s = i % POOL; k_merge_east<<<blocks, 256>>>(in + s * 3 * HW, metric + s * HW, flow[pat] + s * 2 * HW, acc); }, 4, 32);
         printf("  east merge by shuffle         : %7.1f us/frame\n", ms * 1e3);
+        check_slide<32, 8, 6, 16, 4>(in, metric, flow[pat], acc, acc2);
+        bench_slide<32, 8, 6, 16, 4>(T, "32x32, mx 8 my 6", in, metric, flow[pat], acc, spilled, POOL);
+        bench_slide<64, 8, 6, 16, 4>(T, "32x64, mx 8 my 6", in, metric, flow[pat], acc, spilled, POOL);
+        bench_slide<32, 8, 3, 8, 4>(T, "32x32, mx 8 my 3", in, metric, flow[pat], acc, spilled, POOL);
+        bench_slide<32, 4, 3, 8, 4>(T, "32x32, mx 4 my 3", in, metric, flow[pat], acc, spilled, POOL);
+        bench_slide<32, 8, 6, 16, 8>(T, "32x32, mx 8 my 6, kr 8", in, metric, flow[pat], acc, spilled, POOL);
         bench_window<32, 4, 40, 8>(T, "32x4 strip, 40x8", in, metric, flow[pat], acc, spilled, POOL);
         bench_window<32, 4, 48, 12>(T, "32x4 strip, 48x12", in, metric, flow[pat], acc, spilled, POOL);
         bench_window<32, 4, 48, 20>(T, "32x4 strip, 48x20", in, metric, flow[pat], acc, spilled, POOL);

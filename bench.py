@@ -309,7 +309,18 @@ def _extras(torch, d, dev, gen, peak):
         ms = _time_cuda(torch, lambda: d.softsplat(ti.detach(), fl.detach(), me.detach(), "soft"), 10, 3)
         ex["C4_soft_fwd_only_8x64x256x256_f32"] = {"us": round(ms * 1e3, 1), "mpixel_s": round(px / ms / 1e3, 1),
                                                    "alg_gbs": round(131 * 4 * px / ms / 1e6, 1), "frac_of_peak": round(131 * 4 * px / ms / 1e6 / peak, 3)}
-        del ti, me, fl, go
+        # the same forward on channels_last (NHWC) feature maps: the channel-quad gather (k_list_gather_nhwc); "nchw_gather"
+        # is what the same strided view cost before that kernel existed (dcb_set_option("lists_nhwc", 0))
+        tcl = ti.detach().to(memory_format=torch.channels_last)
+        ms = _time_cuda(torch, lambda: d.softsplat(tcl, fl.detach(), me.detach(), "soft"), 10, 3)
+        d._lib.set_option("lists_nhwc", 0)
+        ms0 = _time_cuda(torch, lambda: d.softsplat(tcl, fl.detach(), me.detach(), "soft"), 5, 2)
+        d._lib.set_option("lists_nhwc", 1)
+        ex["C4_soft_fwd_only_channels_last_8x64x256x256_f32"] = {"us": round(ms * 1e3, 1), "mpixel_s": round(px / ms / 1e3, 1),
+                                                                 "alg_gbs": round(131 * 4 * px / ms / 1e6, 1),
+                                                                 "frac_of_peak": round(131 * 4 * px / ms / 1e6 / peak, 3),
+                                                                 "us_through_nchw_gather": round(ms0 * 1e3, 1)}
+        del ti, me, fl, go, tcl
         # f-3: Hann-window tile merge (patch_utils.py:83-174): a 1080p canvas from 512^2 tiles with 64 px overlap
         # (patch_exp.ipynb cell 3), at pixel scale (3 channels) and at latent scale (4 channels, 8x smaller)
         def torch_eager_merge(tiles, rects, full):

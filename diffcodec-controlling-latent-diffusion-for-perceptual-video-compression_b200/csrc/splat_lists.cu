@@ -24,6 +24,11 @@
 // 1.5 ulp of the reference's round(round(in * g) * w) (softsplat.py:244-247, 320-334) -- the same
 // size as the run-to-run reordering of the reference's own atomicAdd, far inside the 1e-5 contract.
 // Frames are processed in groups whose lists (32 B per pixel) stay L2-resident.
+//
+// Channels-last (NHWC) input takes its own gather (k_list_gather_nhwc): eight lanes walk the CHANNELS of one target, so a
+// list entry is one 16-byte (fp32) / 8-byte (bf16) load per lane and channel quad, 128 contiguous bytes per group, and there
+// is one address computation per four channels; the entries of a list are read once and reused for all channels. The NCHW output the
+// reference's callers expect is written through a shared-memory transpose, 128 contiguous bytes per store.
 #include "dcb_common.cuh"
 
 namespace dcb {
@@ -52,6 +57,10 @@ __device__ __forceinline__ float ld_global_ro(const __nv_bfloat16* p) {
     return __uint_as_float((unsigned)v << 16);
 }
 
+// dcb_set_option("lists_nhwc", 0): A/B switch, channels-last input through the NCHW gather (strided scalar loads)
+int g_lists_nhwc = 1;
+void lists_set_nhwc(long long v) { g_lists_nhwc = v != 0; }
+
 struct ListArgs {
     View in, flow, metric, mask;
     int* cursor;             // [gtotal]: counts -> starts -> ends
@@ -63,8 +72,10 @@ struct ListArgs {
     int C, H, W;
     unsigned HW, gtotal;     // pixels per frame, pixels in this frame group
     unsigned tiles_x, tiles; // gather: 32 x 8 target tiles per row / per frame
+    unsigned row_tiles;      // channels-last gather: 32 x 1 target tiles per frame
     int frame0;              // first frame of the group
     int mode, eps;
+    int nhwc;                // channels-last input whose channel quads are aligned: k_list_gather_nhwc
 };
 
 // the four corners of a source pixel: target index inside the group, weight, in range or not
@@ -222,6 +233,106 @@ __global__ void __launch_bounds__(256, DCB_LMINCTAS) k_list_gather(const ListArg
     }
 }
 
+// the four channels of a quad of a channels-last tensor in one read-only load
+__device__ __forceinline__ void ld_quad_ro(const float* p, float (&o)[4]) {
+    asm("ld.global.nc.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(o[0]), "=f"(o[1]), "=f"(o[2]), "=f"(o[3]) : "l"(p));
+}
+__device__ __forceinline__ void ld_quad_ro(const __nv_bfloat16* p, float (&o)[4]) {
+    unsigned lo, hi;
+    asm("ld.global.nc.v2.u32 {%0,%1}, [%2];" : "=r"(lo), "=r"(hi) : "l"(p));
+    o[0] = __uint_as_float(lo << 16); o[1] = __uint_as_float(lo & 0xffff0000u);
+    o[2] = __uint_as_float(hi << 16); o[3] = __uint_as_float(hi & 0xffff0000u);
+}
+
+#ifndef DCB_LQ_CBLK
+#define DCB_LQ_CBLK 128       // channels per pass through the transpose tile (16.5 KB of shared memory)
+#endif
+#ifndef DCB_LQ_U
+#define DCB_LQ_U 4            // list entries whose loads are in flight together
+#endif
+
+// K7d for channels-last input. A CTA owns 32 consecutive targets of one row: 8 lanes share a target (4 targets per warp,
+// one pass per CTA), a lane owns up to 4 of the block's 32 channel quads (q = lane, lane + 8, ...: 128 contiguous bytes
+// per group and load). The entries of a list are read once per chunk of U and reused for every quad; the normaliser is
+// summed in the same pass. Output: NCHW-contiguous, through the transpose tile.
+template <class T>
+__global__ void __launch_bounds__(256) k_list_gather_nhwc(const ListArgs a) {
+    constexpr int CBLK = DCB_LQ_CBLK, U = DCB_LQ_U, G = 8, QPL = CBLK / 4 / G;
+    __shared__ float tile[CBLK][33];
+    pdl_wait();
+    const unsigned tile_id = blockIdx.x % a.row_tiles, n = blockIdx.x / a.row_tiles;
+    const unsigned tx = tile_id % a.tiles_x, y = tile_id / a.tiles_x;
+    const unsigned x0 = tx * 32;
+    const int frame = a.frame0 + (int)n;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int ql = lane % G;
+    const int tt = warp * (32 / G) + lane / G;                    // this group's target inside the tile
+    const unsigned x = x0 + (unsigned)tt;
+    const bool live = x < (unsigned)a.W;
+    const bool normalised = a.mode != DCB_MODE_SUM;
+    const T* ibase = (const T*)a.in.p + (long long)frame * a.in.sN;
+    T* obase = (T*)a.out + (long long)frame * a.C * a.HW + (size_t)y * a.W + x0;
+    const unsigned r = y * (unsigned)a.W + (live ? x : 0u), t = n * a.HW + r;
+    int beg = 0, end = 0;
+    if (live) { beg = __ldcg(a.start + t); end = __ldcg(a.cursor + t); }
+    float mscale = 1.f;
+    if (live && a.mask.p) {
+        const T* mp = (const T*)a.mask.p + (long long)frame * a.mask.sN + (long long)y * a.mask.sH + (long long)x * a.mask.sW;
+        mscale = sub_rn(1.f, ld<float>(mp));                      // control_utils.py:69-70
+    }
+
+    for (int c0 = 0; c0 < a.C; c0 += CBLK) {
+        const int quads = min(CBLK, a.C - c0) >> 2;               // C % 4 == 0 (checked by the host)
+        float acc[QPL][4];
+#pragma unroll
+        for (int i = 0; i < QPL; ++i) acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.f;
+        float d = 0.f;
+        const T* ip = ibase + (c0 + 4 * ql);
+        for (int e = beg; e < end; e += U) {
+            int2 en[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) en[u] = __ldcg(a.entries + min(e + u, end - 1));
+            float gw[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                gw[u] = e + u < end ? __int_as_float(en[u].y) : 0.f;                      // a repeated last entry adds nothing
+                if (e + u < end) d = add_rn(d, gw[u]);                                    // the appended channel, softsplat.py:243-247
+            }
+#pragma unroll
+            for (int i = 0; i < QPL; ++i) {
+                if (ql + i * G < quads) {
+                    float v[U][4];
+#pragma unroll
+                    for (int u = 0; u < U; ++u) ld_quad_ro(ip + ((unsigned)en[u].x + (unsigned)(4 * G * i)), v[u]);
+#pragma unroll
+                    for (int u = 0; u < U; ++u)
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) acc[i][k] = fma_rn(v[u][k], gw[u], acc[i][k]);
+                }
+            }
+        }
+        float scale = mscale;
+        if (normalised) {
+            // softsplat.py:256-266
+            if (a.eps == DCB_EPS_ADD) d = add_rn(d, 0.0000001f);
+            else if (a.eps == DCB_EPS_ZERO) d = (d == 0.f) ? 1.f : d;
+            else d = (d < 0.0000001f) ? 0.0000001f : d;
+            if (live && a.norm && c0 == 0 && ql == 0) __stcs((float*)a.norm + (long long)frame * a.HW + r, d);
+            scale = mul_rn(__frcp_rn(d), mscale);                 // <= 1 ulp from the true quotient of softsplat.py:270 (x 1.0f is exact)
+        }
+        const bool scaled = normalised || a.mask.p != nullptr;
+#pragma unroll
+        for (int i = 0; i < QPL; ++i)
+            if (ql + i * G < quads)
+#pragma unroll
+                for (int k = 0; k < 4; ++k) tile[4 * (ql + i * G) + k][tt] = scaled ? mul_rn(acc[i][k], scale) : acc[i][k];
+        __syncthreads();
+        if (x0 + (unsigned)lane < (unsigned)a.W)
+            for (int c = warp; c < 4 * quads; c += 8) st_stream(obase + (size_t)(c0 + c) * a.HW + lane, tile[c][lane]);
+        __syncthreads();
+    }
+}
+
 // ---------------------------------------------------------------------------------------------
 // host
 // ---------------------------------------------------------------------------------------------
@@ -285,7 +396,11 @@ static int launch_lists(ListArgs& a, const ListLayout& L, char* ws, int N, bool 
         DCB_CHECK_CUDA(launch_pdl(k_list_count<TF>, blocks, 256, 0, st, a));
         DCB_CHECK_CUDA(launch_pdl(k_list_alloc, blocks, 256, 0, st, a));
         DCB_CHECK_CUDA(launch_pdl(k_list_fill<T, TF>, blocks, 256, 0, st, a));
-        DCB_CHECK_CUDA(launch_pdl(k_list_gather<T>, a.tiles * (unsigned)frames, 256, 0, st, a));
+        if (a.nhwc) {
+            DCB_CHECK_CUDA(launch_pdl(k_list_gather_nhwc<T>, a.row_tiles * (unsigned)frames, 256, 0, st, a));
+        } else {
+            DCB_CHECK_CUDA(launch_pdl(k_list_gather<T>, a.tiles * (unsigned)frames, 256, 0, st, a));
+        }
         count_launch(4);
         // a shared all-zero workspace is handed back all-zero: one memset behind the gather (zeroing
         // the cells inside the kernel that reads them cost 10-60 % of its speed: the stores order
@@ -309,6 +424,12 @@ int splat_lists_impl(const DcbTensor* in, const DcbTensor* flow, const DcbTensor
     a.mode = mode; a.eps = eps;
     a.tiles_x = (unsigned)(a.W + 31) / 32;
     a.tiles = a.tiles_x * ((unsigned)(a.H + 7) / 8);
+    a.row_tiles = a.tiles_x * (unsigned)a.H;
+    {   // channels-last: unit channel stride, whole quads, every quad aligned to its vector load
+        const long long es = elem_size(in->dtype);
+        a.nhwc = (g_lists_nhwc && in->stride[1] == 1 && a.C % 4 == 0 && a.C >= 32 && ((uintptr_t)in->ptr % (uintptr_t)(4 * es)) == 0 &&
+                  in->stride[0] % 4 == 0 && in->stride[2] % 4 == 0 && in->stride[3] % 4 == 0) ? 1 : 0;
+    }
     a.out = out->ptr;
     a.norm = norm ? norm->ptr : nullptr;
     const ListLayout L = lists_layout(N, a.H, a.W);

@@ -498,3 +498,40 @@ def test_channels_last_vector_path(dcb, orc, dtype, shape):
     odd = torch.zeros(n, h, w, c + 1, device="cuda", dtype=dtype)[..., 1:].permute(0, 3, 1, 2)      # quads start 1 element off: not aligned
     odd.copy_(x)
     assert_close(dcb.softsplat(odd, fl, me, "soft").float(), a.float(), 2e-6 if dtype == torch.float32 else 1e-2, "unaligned NHWC view")
+
+
+@pytest.mark.parametrize("shape,dtype,mode", [((2, 64, 192, 200), torch.float32, "soft"), ((2, 64, 192, 200), torch.float32, "sum"),
+                                              ((3, 160, 150, 152), torch.float32, "avg"), ((2, 40, 230, 250), torch.float32, "linear"),
+                                              ((2, 96, 256, 260), torch.bfloat16, "soft")])
+def test_channels_last_list_gather(dcb, orc, shape, dtype, mode):
+    """Many channels on large tensors (the per-target list path, csrc/splat_lists.cu): channels_last input takes the
+    channel-quad gather (k_list_gather_nhwc: sub-warp groups over the channels of one target, NCHW output through a
+    shared-memory transpose). Same values as the NCHW call, as the NCHW gather on the same strided view, and as the oracle;
+    covers ragged row tiles (W % 32 != 0), quad counts that are no power of two and more channels than one transpose pass."""
+    n, c, h, w = shape
+    tin, flow, metric, _ = make_inputs(83, n, c, h, w, flow_scale=2.5, smooth=True)
+    tin, flow, metric = (t.to(dtype).float() for t in (tin, flow, metric))
+    if mode == "linear":
+        metric = metric.abs() + 0.1
+    me_ref = metric if mode in ("soft", "linear") else None
+    ref = orc.softsplat(tin, flow, me_ref, mode)
+    rel = 1e-5 if dtype == torch.float32 else 1e-2
+    x = tin.cuda().to(dtype)
+    fl = flow.cuda().to(dtype)
+    me = metric.cuda().to(dtype) if me_ref is not None else None
+    nhwc = x.to(memory_format=torch.channels_last)
+    assert nhwc.stride(1) == 1 and not nhwc.is_contiguous()
+    a = dcb.softsplat(x, fl, me, mode)
+    before = dcb.launch_count()
+    b = dcb.softsplat(nhwc, fl, me, mode)
+    assert dcb.launch_count() - before == 4          # count, alloc, fill, gather: the list path
+    assert b.is_contiguous()
+    dcb._lib.set_option("lists_nhwc", 0)
+    try:
+        b0 = dcb.softsplat(nhwc, fl, me, mode)
+    finally:
+        dcb._lib.set_option("lists_nhwc", 1)
+    tight = 2e-6 if dtype == torch.float32 else 1e-2
+    assert_close(b.float(), a.float(), tight, "channels_last vs NCHW")
+    assert_close(b.float(), b0.float(), tight, "quad gather vs NCHW gather on the same view")
+    assert_close(b.float().cpu(), ref, rel, "channels_last vs oracle")

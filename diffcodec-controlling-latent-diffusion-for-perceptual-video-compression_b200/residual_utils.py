@@ -5,7 +5,7 @@
 Per sample the reference issues 4 ``softsplat`` calls (two of them identical),
 two norms / compares, a cat / clamp / sum / div fusion and a subtraction: ~45 launches for a
 batch of ONE frame. ``residual_conditioning`` does the same arithmetic for N frames in two
-launches (dcb_residual_fused).
+pipeline passes (dcb_residual_fused: four launches per frame group).
 """
 from __future__ import annotations
 

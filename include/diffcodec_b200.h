@@ -201,11 +201,13 @@ int dcb_occlusion_mask(const DcbTensor* flow_a, const DcbTensor* flow_b, const D
 
 /*
  * Conditioning builder: warped frame, two occlusion masks, confidence fusion, residual, in two
- * launches. Replaces the arithmetic of ResidueDataset.__getitem__ (controlnet/dataset.py:233-265,
+ * pipeline passes (four launches per frame group: flow1 splatted by flow2 + occlusion epilogue; image1 and
+ * flow2 splatted together by flow1 + one epilogue that normalises, tests occlusion, fuses and subtracts).
+ * Replaces the arithmetic of ResidueDataset.__getitem__ (controlnet/dataset.py:233-265,
  * variant DCB_RECIPE_DATASET) and WarpingDatasetWrapper.__getitem__
  * (controlnet/residual_utils.py:159-199, variant DCB_RECIPE_WRAPPER), batched over N.
  *
- *   image1, gt [N,C,H,W] (C <= 3... any C); flow1, flow2 [N,2,H,W]
+ *   image1, gt [N,C,H,W] (1 <= C <= 3; one dtype, F32 or BF16, for every tensor); flow1, flow2 [N,2,H,W]
  *   fused, residual [N,C,H,W] contiguous; occ_fwd / occ_bwd [N,1,H,W] optional outputs
  */
 int64_t dcb_residual_workspace_bytes(int64_t N, int64_t C, int64_t H, int64_t W);

@@ -658,6 +658,40 @@ __device__ __forceinline__ void recipe_chunk_v2(const PipeArgs& a, int frame, in
 // ---------------------------------------------------------------------------------------------
 // the step kernel: warp w of CTA b owns item 4b + w; normalise items first, then scatter items
 // ---------------------------------------------------------------------------------------------
+// one epilogue item: chunk `chunk` of frame `z` of the group being normalised
+template <class T, int MODE, int CA, int KIND>
+__device__ __forceinline__ void epilogue_item(const PipeArgs& a, unsigned z, unsigned chunk, int lane) {
+    const int f = a.n_frame0 + (int)z;
+    float* acc = a.acc_n + z * ((size_t)a.HW * 4);
+    if (KIND == 1) {
+        if (a.flat2) recipe_chunk_v2<T, CA>(a, f, (int)chunk, acc, a.acc2_n + z * ((size_t)a.HW * 2), lane);
+        else recipe_chunk<T, CA>(a, f, (int)chunk, acc, a.acc2_n + z * ((size_t)a.HW * 2), lane);
+        return;
+    }
+    if (a.epi == 1) { if (a.flat2) mask_chunk_v2<T>(a, f, (int)chunk, acc, lane); else mask_chunk<T>(a, f, (int)chunk, acc, lane); }
+#if DCB_NORM_V == 4
+    else if (a.vec4 && a.mask.p == nullptr) normalize_chunk_v4<T, MODE, CA>(a, f, (int)chunk, acc, lane);
+#elif DCB_NORM_V == 2
+    else if (a.vec4 && a.mask.p == nullptr) normalize_chunk_v2<T, MODE, CA>(a, f, (int)chunk, acc, lane);
+#endif
+    else normalize_chunk<T, MODE, CA>(a, f, (int)chunk, acc, lane);
+}
+
+// An epilogue-only launch (one accumulator slot: every second launch) as CTAs of kEpiWarps warps, one chunk per warp:
+// the same per-warp work as in k_splat_step with a quarter of the CTAs to schedule.
+#ifndef DCB_EPI_WARPS
+#define DCB_EPI_WARPS 4
+#endif
+constexpr int kEpiWarps = DCB_EPI_WARPS;
+template <class T, int MODE, int CA, int KIND>
+__global__ void __launch_bounds__(32 * kEpiWarps, (KIND ? kMinCtasRecipe : kMinCtas) / kEpiWarps) k_splat_epilogue(const __grid_constant__ PipeArgs a) {
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    const unsigned chunk = blockIdx.x * kEpiWarps + (threadIdx.x >> 5);
+    if (chunk >= (unsigned)a.tn) return;
+    epilogue_item<T, MODE, CA, KIND>(a, blockIdx.y, chunk, threadIdx.x & 31);
+}
+
 // KIND 0: softsplat / occlusion mask; KIND 1: the conditioning recipe's second pass (rider scatter + recipe epilogue)
 template <class T, class TF, int MODE, int CA, int KIND>
 __global__ void __launch_bounds__(kPipeThreads, KIND ? kMinCtasRecipe : kMinCtas) k_splat_step(const __grid_constant__ PipeArgs a) {
@@ -674,20 +708,7 @@ __global__ void __launch_bounds__(kPipeThreads, KIND ? kMinCtasRecipe : kMinCtas
     if (z < (unsigned)a.n_frames) {
         const unsigned chunk = blockIdx.y * gridDim.x + blockIdx.x;
         if (chunk >= (unsigned)a.tn) return;
-        const int f = a.n_frame0 + (int)z;
-        float* acc = a.acc_n + z * frame_floats;
-        if (KIND == 1) {
-            if (a.flat2) recipe_chunk_v2<T, CA>(a, f, (int)chunk, acc, a.acc2_n + z * ((size_t)a.HW * 2), lane);
-            else recipe_chunk<T, CA>(a, f, (int)chunk, acc, a.acc2_n + z * ((size_t)a.HW * 2), lane);
-            return;
-        }
-        if (a.epi == 1) { if (a.flat2) mask_chunk_v2<T>(a, f, (int)chunk, acc, lane); else mask_chunk<T>(a, f, (int)chunk, acc, lane); }
-#if DCB_NORM_V == 4
-        else if (a.vec4 && a.mask.p == nullptr) normalize_chunk_v4<T, MODE, CA>(a, f, (int)chunk, acc, lane);
-#elif DCB_NORM_V == 2
-        else if (a.vec4 && a.mask.p == nullptr) normalize_chunk_v2<T, MODE, CA>(a, f, (int)chunk, acc, lane);
-#endif
-        else normalize_chunk<T, MODE, CA>(a, f, (int)chunk, acc, lane);
+        epilogue_item<T, MODE, CA, KIND>(a, z, chunk, lane);
     } else {
         const unsigned zs = z - (unsigned)a.n_frames;
         if (blockIdx.x >= (unsigned)a.tiles_x || blockIdx.y >= (unsigned)a.tiles_y) return;
@@ -756,6 +777,12 @@ template <class T, class TF, int MODE, int CA, int KIND = 0> static int launch_s
         attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
         attr[0].val.programmaticStreamSerializationAllowed = 1;
         cfg.attrs = attr; cfg.numAttrs = 1;
+        if (kEpiWarps > 1 && a.s_frames == 0) {          // epilogue-only launch
+            cfg.gridDim = dim3((unsigned)((a.tn + kEpiWarps - 1) / kEpiWarps), (unsigned)a.n_frames, 1); cfg.blockDim = dim3(32 * kEpiWarps);
+            DCB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, k_splat_epilogue<T, MODE, CA, KIND>, a));
+            count_launch();
+            continue;
+        }
         DCB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, k_splat_step<T, TF, MODE, CA, KIND>, a));
         count_launch();
     }

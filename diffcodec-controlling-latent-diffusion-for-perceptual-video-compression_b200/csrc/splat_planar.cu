@@ -117,6 +117,67 @@ __global__ void __launch_bounds__(kPThreads, DCB_PMINCTAS) k_planar_step(const _
 }
 
 // ---------------------------------------------------------------------------------------------
+// ONE launch for a call whose frames fit one group and whose warps are all resident at once (latents, small feature maps):
+// every warp scatters its strip, the grid meets at a counter in the workspace, every warp normalises its chunk(s). The second
+// launch of the pipeline and its dependency gap disappear -- and yet it is SLOWER on the B200: C2 latents 20.6-22.2 us per call
+// under CUDA-graph replay (20 / 200 / 1000 ns back-off in the spin) against 16.4 us for the two programmatically chained
+// launches (profiles/r02/NOTES.md section 11; round 1 measured the same with a cooperative launch). Opt-in only:
+// dcb_set_option("planar_one_launch", 1).
+// Safe because the host launches this kernel only when the whole grid is co-resident (at most half of the machine's CTA
+// slots); launch_dependents is issued first, so a dependent grid cannot take slots before every CTA of this one is resident.
+// The two counters are back at zero when the kernel ends (workspace protocol).
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned ld_acquire_gpu(const unsigned* p) {
+    unsigned v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+
+#ifndef DCB_BAR_SLEEP
+#define DCB_BAR_SLEEP 200
+#endif
+template <class T, class TF>
+__global__ void __launch_bounds__(kPThreads, DCB_PMINCTAS) k_planar_one(const __grid_constant__ PlanarArgs a) {
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    const int lane = threadIdx.x & 31;
+    const unsigned warps = gridDim.x * kPWarps;
+    const unsigned item = blockIdx.x * kPWarps + (threadIdx.x >> 5);
+    const size_t frame_floats = (size_t)a.Cq * a.HW * 4;
+    {
+        const unsigned per = (unsigned)a.ts * a.ncg_s;
+        if (item < (unsigned)a.N * per) {
+            const int fi = item / per, q = item % per;
+            const int strip = q % a.ts, cgi = q / a.ts;
+            planar_scatter_strip<T, TF>(a, fi, strip, cgi * a.cg_s, min(a.Cq, (cgi + 1) * a.cg_s), cgi == 0 && a.mode != DCB_MODE_SUM,
+                                        a.acc + (size_t)fi * frame_floats, a.dacc + (size_t)fi * a.HW, lane);
+        }
+    }
+    // ---- grid barrier: arrive (release), wait for everybody (acquire) ----
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        atomicAdd(a.bar, 1u);
+        while (ld_acquire_gpu(a.bar) < gridDim.x) __nanosleep(DCB_BAR_SLEEP);
+    }
+    __syncthreads();
+    {
+        const unsigned per = (unsigned)a.tn * a.ncg_n;
+        for (unsigned it = item; it < (unsigned)a.N * per; it += warps) {
+            const int fi = it / per, q = it % per;
+            const int chunk = q % a.tn, cgi = q / a.tn;
+            planar_normalize_chunk<T>(a, fi, chunk, cgi * a.cg_n, min(a.Cq, (cgi + 1) * a.cg_n), a.acc + (size_t)fi * frame_floats,
+                                      a.dacc + (size_t)fi * a.HW, lane);
+        }
+    }
+    // ---- depart: the last CTA to leave puts both counters back to zero ----
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        if (atomicAdd(a.bar + 1, 1u) == gridDim.x - 1) { a.bar[0] = 0u; a.bar[1] = 0u; }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 // host
 // ---------------------------------------------------------------------------------------------
 extern long long g_pipe_group_bytes;      // splat_pipe.cu: dcb_set_option("pipe_group_bytes")
@@ -137,7 +198,22 @@ long long planar_workspace(long long N, long long C, long long H, long long W, i
     (void)dtype;
     const long long G = planar_group_frames(N, C, H, W);
     const long long dbytes = mode == DCB_MODE_SUM ? 0 : align_up(3 * G * H * W * 4, 256);
-    return planar_chan_bytes(N, C, H, W) + dbytes;
+    return planar_chan_bytes(N, C, H, W) + dbytes + 256;          // + the two counters of the single-launch kernel
+}
+
+// dcb_set_option("planar_one_launch", 1): the single-launch kernel where it applies (measured slower: default off)
+int g_planar_one = 0;
+void planar_set_one_launch(long long v) { g_planar_one = v != 0; }
+
+// CTA slots of the device for k_planar_one (occupancy x SMs), queried once per instantiation
+template <class T, class TF> static long long one_launch_slots() {
+    static long long slots = -1;
+    if (slots < 0) {
+        int per_sm = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_planar_one<T, TF>, kPThreads, 0) != cudaSuccess) per_sm = 0;
+        slots = (long long)per_sm * device_sm_count();
+    }
+    return slots;
 }
 
 // split channels over several warps when the frames are too small to fill the machine
@@ -154,6 +230,18 @@ static void split_channels(long long items, int channels, int min_cg, int* cg, i
 template <class T, class TF> static int launch_planar(PlanarArgs& a, cudaStream_t st) {
     const int groups = (a.N + a.G - 1) / a.G;
     const bool normalised = a.mode != DCB_MODE_SUM;
+    if (g_planar_one && groups == 1) {
+        // every scatter item needs its own warp; the normalise items are looped over. Half of the CTA slots at most.
+        const long long s_items = (long long)a.N * a.ts * a.ncg_s;
+        const long long ctas = (s_items + kPWarps - 1) / kPWarps;
+        if (ctas > 0 && 2 * ctas <= one_launch_slots<T, TF>()) {
+            a.step = 0; a.s_frame0 = a.n_frame0 = 0; a.s_frames = a.n_frames = a.N;
+            DCB_CHECK_CUDA(launch_pdl(k_planar_one<T, TF>, dim3((unsigned)ctas), dim3(kPThreads), 0, st, a));
+            count_launch();
+            if (normalised && a.ncg_n > 1) DCB_CHECK_CUDA(cudaMemsetAsync(a.dacc, 0, (size_t)a.G * a.HW * 4, st));
+            return DCB_OK;
+        }
+    }
     for (int k = 0; k <= groups; ++k) {
         a.step = k;
         a.s_frame0 = k * a.G;
@@ -202,6 +290,7 @@ int splat_planar_impl(const DcbTensor* in, const DcbTensor* flow, const DcbTenso
     a.norm = norm ? norm->ptr : nullptr;
     a.acc = (float*)ws;
     a.dacc = (float*)((char*)ws + planar_chan_bytes(a.N, a.C, a.H, a.W));
+    a.bar = (unsigned*)((char*)ws + planar_workspace(a.N, a.C, a.H, a.W, in->dtype, mode) - 256);
     if (!ws_clean) DCB_CHECK_CUDA(cudaMemsetAsync(ws, 0, (size_t)planar_workspace(a.N, a.C, a.H, a.W, in->dtype, mode), st));
     const bool ff = flow->dtype == DCB_F32;
     if (in->dtype == DCB_F32) return launch_planar<float, float>(a, st);

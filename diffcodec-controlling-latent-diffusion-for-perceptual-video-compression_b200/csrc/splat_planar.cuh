@@ -39,6 +39,7 @@ struct PlanarArgs {
     int s_frame0, s_frames, n_frame0, n_frames;
     int ones;                // the metric is all-ones and not materialised (compute_mask, warpers without metric_net)
     int vec_in;              // channels-last input (stride[1] == 1, C % 4 == 0, 16-byte aligned quads): one vector load per quad
+    unsigned* bar;           // single-launch kernel (k_planar_one): arrive / depart counters in the workspace, zero between calls
 };
 
 // the four channels of a quad of a channels-last (NHWC) tensor in one load: 16 bytes fp32, 8 bytes bf16

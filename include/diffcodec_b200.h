@@ -123,6 +123,9 @@ int32_t dcb_splat_fwd_workspace_is_scratch(int64_t N, int64_t C, int64_t H, int6
  *   "owner_group_bytes" flow bytes per (pre-pass, owner) launch pair; 0 restores the default
  *   "pipe_tail_percent" share of a frame's rows (at the bottom) cut into single-pass 32 x 4 strips instead of 32 x 8
  *   "bwd_group_bytes"   packed-cell bytes per frame group of the packed backward; 0 = one group
+ *   "planar_one_launch" 0 (default) two chained launches | 1 a many-channel call whose frames fit one group and whose warps
+ *                       are all resident at once (latents, small feature maps) runs as ONE launch with a grid barrier
+ *                       (measured slower on B200: 20.6-22.2 us against 16.4 us for C2 under graph replay)
  *   "lists_nhwc"        1 (default) channels-last many-channel tensors take the channel-quad gather | 0 the NCHW gather
  * Returns DCB_OK, or DCB_E_MODE for an unknown name. There is no equivalent in the reference (its kernels are
  * re-specialised per shape by string templating, controlnet/softsplat.py:27-216).

@@ -298,6 +298,46 @@ struct Timer {
     }
 };
 
+
+// ---------------------------------------------------------------------------------------------------------------------
+// round-2 probe 3: what does the FLUSH of a staged tile cost if the TMA unit does it?  One elected lane reduces a row of
+// BYTES of shared memory into the L2-resident accumulator with cp.reduce.async.bulk (add.f32) -- whole lines, no per-lane
+// address -- against one red.v4 per lane over the same cells (k_lane_red).  Both touch every cell of the frame exactly once.
+// ---------------------------------------------------------------------------------------------------------------------
+template <int BYTES>
+__global__ void __launch_bounds__(32) k_bulk_red(float* acc, int rows_per_warp, size_t total_bytes) {
+    __shared__ __align__(128) float buf[BYTES / 4];
+    const int lane = threadIdx.x;
+    for (int i = lane; i < BYTES / 4; i += 32) buf[i] = 1.0f;
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncwarp();
+    if (lane == 0) {
+        const unsigned src = (unsigned)__cvta_generic_to_shared(buf);
+        char* dst = (char*)acc + (size_t)blockIdx.x * rows_per_warp * BYTES;
+        for (int r = 0; r < rows_per_warp; ++r) {
+            if ((size_t)(dst - (char*)acc) + BYTES <= total_bytes)
+                asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.f32 [%0], [%1], %2;" ::"l"(dst), "r"(src), "n"(BYTES) : "memory");
+            dst += BYTES;
+        }
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+    }
+    __syncwarp();
+}
+
+__global__ void __launch_bounds__(256) k_lane_red(float* acc) {
+    const int r = blockIdx.x * 256 + threadIdx.x;
+    if (r < HW) red4(acc + (size_t)r * 4, 1.f, 1.f, 1.f, 1.f);
+}
+
+template <int BYTES> static void bench_bulk(Timer& T, float* acc) {
+    const size_t total = (size_t)HW * 16;
+    const int rows_per_warp = 16;
+    const int warps = (int)((total + (size_t)BYTES * rows_per_warp - 1) / ((size_t)BYTES * rows_per_warp));
+    float ms = T.run([&](int) { k_bulk_red<BYTES><<<warps, 32>>>(acc, rows_per_warp, total); }, 4, 32);
+    printf("  cp.reduce.async.bulk add.f32, %4d-byte rows: %7.1f us/frame  (%.0f GB/s of reduced payload)\n", BYTES, ms * 1e3, total / ms / 1e6);
+}
+
 template <int SX, int SY, int WX, int WY>
 static void bench_window(Timer& T, const char* name, const float* in, const float* metric, const float* flow, float* acc,
                          unsigned long long* spilled, int POOL) {
@@ -353,6 +393,14 @@ int main() {
     CK(cudaDeviceSynchronize());
     float* acc2; CK(cudaMalloc(&acc2, (size_t)HW * 16));
     Timer T;
+    {
+        printf("--- flush of a staged tile: every cell of the frame reduced once ---\n");
+        float ms = T.run([&](int) { k_lane_red<<<(HW + 255) / 256, 256>>>(acc); }, 4, 32);
+        printf("  one red.v4 per lane, consecutive cells        : %7.1f us/frame  (%.0f GB/s of reduced payload)\n", ms * 1e3, (double)HW * 16 / ms / 1e6);
+        bench_bulk<256>(T, acc); bench_bulk<768>(T, acc); bench_bulk<2048>(T, acc); bench_bulk<8192>(T, acc);
+        CK(cudaDeviceSynchronize());
+        CK(cudaMemset(acc, 0, (size_t)HW * 16));
+    }
     const char* pname[3] = {"smooth (|d/dx| ~ 0.03)", "rough (|d/dx| ~ 0.25)", "random +-32 px"};
     const int blocks = (HW + 255) / 256;
     for (int pat = 0; pat < 3; ++pat) {

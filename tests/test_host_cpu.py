@@ -65,7 +65,7 @@ def test_workspace_queries_need_no_gpu():
         L.set_option("no_such_option", 1)
     assert lib.dcb_splat_workspace_bytes(1, 8, 64, 64, L.DCB_F64, L.MODE_SUM, 0) == 0        # fp64 reds go straight into out
     # many channels: planar accumulators, 2 slots x 2 frames x 64 planes + 3 slots x 2 normaliser planes
-    assert lib.dcb_splat_workspace_bytes(8, 64, 256, 256, L.DCB_F32, L.MODE_SOFT, 0) == (2 * 2 * 64 + 3 * 2) * 256 * 256 * 4
+    assert lib.dcb_splat_workspace_bytes(8, 64, 256, 256, L.DCB_F32, L.MODE_SOFT, 0) == (2 * 2 * 64 + 3 * 2) * 256 * 256 * 4 + 256    # + the counters of the single-launch kernel
     assert lib.dcb_splat_bwd_workspace_bytes(64, 3, 1080, 1920, L.DCB_F32, L.MODE_SOFT, 0) == 64 * 1080 * 1920 * 16      # one packed float4 per target
     assert lib.dcb_splat_bwd_workspace_bytes(8, 64, 256, 256, L.DCB_F32, L.MODE_SOFT, 0) == 8 * 256 * 256 * 8
     assert lib.dcb_occlusion_mask_workspace_bytes(2, 64, 64) == 2 * 64 * 64 * 16

@@ -535,3 +535,37 @@ def test_channels_last_list_gather(dcb, orc, shape, dtype, mode):
     assert_close(b.float(), a.float(), tight, "channels_last vs NCHW")
     assert_close(b.float(), b0.float(), tight, "quad gather vs NCHW gather on the same view")
     assert_close(b.float().cpu(), ref, rel, "channels_last vs oracle")
+
+
+@pytest.mark.parametrize("shape,dtype,mode", [((4, 4, 135, 240), torch.bfloat16, "soft"), ((2, 12, 40, 56), torch.float32, "avg"),
+                                              ((1, 160, 32, 32), torch.float32, "soft"), ((3, 7, 33, 47), torch.float32, "sum")])
+def test_planar_single_launch_kernel(dcb, orc, shape, dtype, mode):
+    """The opt-in single-launch form of the many-channel pipeline (k_planar_one: scatter, grid barrier on two counters in the
+    workspace, normalise): ONE launch, the same values as the two-launch pipeline and the oracle, and the counters back at
+    zero afterwards (a second call and a different call through the same kept-zero workspace are right)."""
+    n, c, h, w = shape
+    tin, flow, metric, _ = make_inputs(91, n, c, h, w, flow_scale=1.5)
+    tin, flow, metric = (t.to(dtype).float() for t in (tin, flow, metric))
+    me_ref = metric if mode in ("soft", "linear") else None
+    ref = orc.softsplat(tin, flow, me_ref, mode)
+    x, fl = tin.cuda().to(dtype), flow.cuda().to(dtype)
+    me = metric.cuda().to(dtype) if me_ref is not None else None
+    L = dcb._lib
+    L.set_option("fwd_path", 1)               # keep small frames off the cluster kernel
+    try:
+        two = dcb.softsplat(x, fl, me, mode)
+        L.set_option("planar_one_launch", 1)
+        before = dcb.launch_count()
+        one = dcb.softsplat(x, fl, me, mode)
+        assert dcb.launch_count() - before == 1
+        again = dcb.softsplat(x, fl, me, mode)
+        L.set_option("planar_one_launch", 0)
+        after = dcb.softsplat(x, fl, me, mode)
+    finally:
+        L.set_option("planar_one_launch", 0)
+        L.set_option("fwd_path", 0)
+    rel = 1e-5 if dtype == torch.float32 else 1e-2
+    assert_close(one.float().cpu(), ref, rel, "single launch vs oracle")
+    assert_close(again.float().cpu(), ref, rel, "second single launch vs oracle")
+    assert_close(after.float().cpu(), ref, rel, "two launches after the single-launch calls")
+    assert_close(one.float(), two.float(), 2e-6 if dtype == torch.float32 else 1e-2, "single launch vs two launches")

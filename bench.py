@@ -12,8 +12,9 @@ frames are C1/C3-shaped: 3 x 1080 x 1920, smooth synthetic flow of ~8 px). Print
   e2e          same metric through the public Python API from PINNED HOST buffers: H2D of the
                step's inputs, the op, D2H of the result, all inside the timed region
   roofline     algorithmic bytes (36 B/px) / measured duration of one
-               k_splat_step launch (F+1 launches per step of F frames; launch k scatters frame k
-               and normalises frame k-1) vs the measured HBM copy peak
+               frame's launch pair (k_splat_step scatters frame k into the L2-resident accumulator
+               slot, k_splat_epilogue normalises it; 2F launches per step of F frames) vs the
+               measured HBM copy peak
   cpu_baseline the oracle port (C + pthreads over frames) on a bounded sample, rank 0, N=1 only
   extra        secondary configs of BASELINE.json (C1 avg latency, C2 bf16 latents, C3 residual
                recipe + backwarp, C4 fwd+bwd), measured outside the timed region
@@ -591,8 +592,8 @@ def run_ours(args):
             "config": _config(F),
             "roofline": {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),
                          "traffic": 65.5e6, "traffic_kind": "recorded, not measured in this run",
-                         "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of the two k_splat_step launches of one frame (scatter 50.4 + 2.1 MB, normalise 0.2 + 12.8 MB; the rest of the 24.9 MB of output drains after the kernel), ncu --cache-control none, profiles/r02/ncu_step_slots.txt; algorithmic 74.65e6",
-                         "kernel": "k_splat_step (two launches per 1080p frame: scatter into one L2-resident accumulator slot, then normalise)",
+                         "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of the two launches of one frame (scatter 50.4 + 2.1 MB, normalise 0.2 + 12.8 MB; the rest of the 24.9 MB of output drains after the kernel), ncu --cache-control none, profiles/r02/ncu_step_slots.txt and ncu_step_r02_final.txt; algorithmic 74.65e6",
+                         "kernel": "k_splat_step + k_splat_epilogue (two launches per 1080p frame: scatter into one L2-resident accumulator slot, then normalise)",
                          "algorithmic_bytes_per_px": ALG_BYTES_PER_PX, "peak_source": peak_src, "frac_of_nominal_8TBs": round(achieved / 8000.0, 4)},
             "fwd_bwd": {"metric": "softsplat soft-mode forward + backward (gradIn, gradFlow, gradMetric), 1080p fp32 frames",
                         "value": round(world * nb * H * W / ms_fb / 1e3, 1), "unit": "Mpixel/s", "ms_per_step": round(ms_fb, 3), "frames_per_gpu": nb,

@@ -1,15 +1,15 @@
-// tile_bench.cu -- round-2 probe (not product code): does aggregating a warp's contributions in a PRIVATE
-// shared-memory window before they go to L2 beat register merging when the flow is rough?
+// tile_bench.cu -- round-2 probes (not product code): can target cells be aggregated ON CHIP before they reach L2?
 //
-// The forward splat is bound by the sectors its reductions touch in L2 (profiles/r01/NOTES.md, sections 2
-// and 6): ~0.7 sector-ops per pixel on smooth flow, 2.2-2.7 on the bench flow, because lone 16-byte reds cost
-// a whole sector-op each. A warp that owns a 32 x 4 strip could add all four corners of its 128 pixels into
-// a window in shared memory (fp32 shared atomics are CAS loops on sm_100a, but the window is private to the
-// warp, so they only ever retry on collisions inside one instruction) and then flush every touched cell ONCE,
-// neighbouring cells from neighbouring lanes (full sectors). This binary times, one 1080p frame per launch
-// into ONE L2-resident accumulator (the regime of the step pipeline):
-//     naive 4 x red.v4 | east-merge by shuffle | shared-memory window (several window sizes)
-// on a smooth, a rough (|dflow/dx| ~ 0.25, like bench.py) and a random flow.
+// The forward splat is bound by the reductions it sends to L2 (profiles/r01/NOTES.md sections 2 and 6; profiles/r02/NOTES.md
+// sections 8 and 12). This binary times, one 1080p frame per launch into ONE L2-resident accumulator (the regime of the step
+// pipeline), on a smooth, a rough (|dflow/dx| ~ 0.25, like bench.py) and a random flow:
+//     naive 4 x red.v4 | east-merge by shuffle (what the product does, plus a vertical carry)
+//   probe 1  k_window: a PRIVATE shared-memory window per warp and strip, fp32 shared atomics (CAS loops on sm_100a), every
+//            touched cell flushed once as full sectors                                              -> loses 2-3x
+//   probe 2  k_slide:  a window that SLIDES down a 32-column strip (ring of rows), plain ld/st.shared made conflict-free by
+//            ranking lanes with match.any, ring rows flushed once when they leave the window       -> loses 1.7-2.1x
+//   probe 3  k_bulk_red / k_lane_red: the flush alone -- cp.reduce.async.bulk (TMA reduce-add) of staged rows against one
+//            red.v4 per lane over the same cells                                                   -> both ~4 TB/s of payload
 //   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -o tile_bench tile_bench.cu
 #include <cuda_runtime.h>
 #include <stdio.h>

@@ -114,7 +114,7 @@ def lib() -> ctypes.CDLL:
                     fn = getattr(handle, name)
                     fn.restype, fn.argtypes = res, args
                 _lib = handle
-                for opt in ("fwd_path", "owner_group_bytes", "pipe_group_bytes", "pipe_ring_slots", "bwd_group_bytes", "pipe_tail_percent", "lists_nhwc", "planar_one_launch"):      # A/B knobs: DCB_FWD_PATH=1 python ...
+                for opt in ("fwd_path", "owner_group_bytes", "pipe_group_bytes", "pipe_ring_slots", "bwd_group_bytes", "pipe_tail_percent", "lists_nhwc", "planar_one_launch", "bwd_flat"):      # A/B knobs: DCB_FWD_PATH=1 python ...
                     v = os.environ.get("DCB_" + opt.upper())
                     if v:
                         handle.dcb_set_option(opt.encode(), int(v))

@@ -79,6 +79,7 @@ void pipe_set_ring_slots(long long n);
 void bwd_set_group_bytes(long long b);
 void pipe_set_tail_percent(long long p);
 void lists_set_nhwc(long long v);
+void bwd_set_flat(long long v);
 void planar_set_one_launch(long long v);
 
 long long tile_merge_workspace(long long C, long long H, long long W, int n_tiles);
@@ -184,6 +185,7 @@ int dcb_set_option(const char* name, int64_t value) {
     if (!strcmp(name, "bwd_group_bytes")) { bwd_set_group_bytes(value); return DCB_OK; }
     if (!strcmp(name, "pipe_tail_percent")) { pipe_set_tail_percent(value); return DCB_OK; }
     if (!strcmp(name, "lists_nhwc")) { lists_set_nhwc(value); return DCB_OK; }
+    if (!strcmp(name, "bwd_flat")) { bwd_set_flat(value); return DCB_OK; }
     if (!strcmp(name, "planar_one_launch")) { planar_set_one_launch(value); return DCB_OK; }
     return set_error(DCB_E_MODE, "dcb_set_option: unknown option '%s'", name);
 }

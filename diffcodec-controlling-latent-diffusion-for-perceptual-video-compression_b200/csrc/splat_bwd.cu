@@ -41,6 +41,7 @@ struct BwdArgs {
     int px, cs;          // block shape
     unsigned pf_dist;    // source pass: L2 prefetch distance in CTAs (one wave)
     unsigned tiles_x, tiles;   // packed source pass: 32 x 8 pixel tiles per row / per frame
+    unsigned pf_rows;          // packed source pass: prefetch distance in tile rows
 };
 
 #ifndef DCB_BS_PF
@@ -313,48 +314,44 @@ __global__ void __launch_bounds__(256) k_bwd_target4(const BwdArgs a) {
     __stcg((float4*)a.tscal + p, make_float4(av * gv[0], av * gv[1], av * gv[2], clipped ? 0.f : -dot / d));
 }
 
-template <class T, class TF>
-#ifndef DCB_B4_TILE
-#define DCB_B4_TILE 1
-#endif
 #ifndef DCB_B4_PF
 #define DCB_B4_PF 1
 #endif
+// grid = (32-pixel tile columns, 8-row tile rows, frames): no integer division anywhere; one 64-bit base per tensor and
+// frame, every in-frame offset in 32 bits (checked by the host: views whose in-frame span does not fit are refused, as in the
+// forward). 32 x 8 pixel tiles: the packed cells gathered by vertically adjacent pixels are the same rows (L1).
+// CT = 0: any strides, channel count and mode at run time. CT = 1..3: C = CT and mode = MT at compile time, `in`, `flow` and
+// `metric` NCHW-contiguous inside a frame, all three gradients wanted (the autograd call on frames / flows / latents): every
+// load offset is the pixel index plus a multiple of H*W, and the per-channel / per-mode tests disappear.
+template <class T, class TF, int CT, int MT>
 __global__ void __launch_bounds__(256) k_bwd_source4(const BwdArgs a) {
     pdl_wait();
+    constexpr bool kFlat = CT != 0;
+    const int C = kFlat ? CT : a.C, mode = kFlat ? MT : a.mode;
     const int W = a.W, H = a.H;
-#if DCB_B4_TILE
-    // 32 x 8 pixel tiles: the packed cells gathered by vertically adjacent pixels are the same rows (L1)
-    const unsigned tile = blockIdx.x % a.tiles, n = blockIdx.x / a.tiles;
-    const int x = (int)((tile % a.tiles_x) * 32 + (threadIdx.x & 31)), y = (int)((tile / a.tiles_x) * 8 + (threadIdx.x >> 5));
+    const unsigned n = blockIdx.z;
+    const int x = (int)(blockIdx.x * 32 + (threadIdx.x & 31)), y = (int)(blockIdx.y * 8 + (threadIdx.x >> 5));
 #if DCB_B4_PF
-    {   // L2 prefetch for the tile one wave ahead: flow (2), metric, in (3) and the packed cells at the zero-flow position
-        const unsigned pb = blockIdx.x + a.pf_dist;
-        if (pb < gridDim.x) {
-            const unsigned ptile = pb % a.tiles, pn = pb / a.tiles;
-            const int px0 = (int)((ptile % a.tiles_x) * 32), py = (int)((ptile / a.tiles_x) * 8 + (threadIdx.x & 7));
-            const int plane = threadIdx.x >> 3;
-            if (py < H) {
-                const void* q = nullptr;
-                if (plane < 2) q = (const TF*)a.flow.p + pn * a.flow.sN + plane * a.flow.sC + py * a.flow.sH + px0 * a.flow.sW;
-                else if (plane == 2 && a.metric.p) q = (const T*)a.metric.p + pn * a.metric.sN + py * a.metric.sH + px0 * a.metric.sW;
-                else if (plane >= 4 && plane < 4 + a.C) q = (const T*)a.in.p + pn * a.in.sN + (plane - 4) * a.in.sC + py * a.in.sH + px0 * a.in.sW;
-                else if (plane >= 8 && plane < 12) q = (const float4*)a.tscal + (size_t)pn * a.HW + (size_t)py * W + px0 + (plane - 8) * 8;
-                if (q) asm volatile("prefetch.global.L2 [%0];" ::"l"(q));
-            }
+    {   // L2 prefetch for the tile one wave ahead (pf_rows tile rows further down, wrapping into the next frame): flow (2),
+        // metric, in (3) and the packed cells at the zero-flow position; 8 rows x 12 planes, one line per thread
+        unsigned pty = blockIdx.y + a.pf_rows, pn = n;
+        if (pty >= gridDim.y) { pty -= gridDim.y; ++pn; }
+        const int py = (int)(pty * 8 + (threadIdx.x & 7)), px0 = (int)(blockIdx.x * 32);
+        const int plane = threadIdx.x >> 3;
+        if (pn < gridDim.z && pty < gridDim.y && py < H) {
+            const void* q = nullptr;
+            if (plane < 2) q = (const TF*)a.flow.p + (pn * a.flow.sN + plane * a.flow.sC) + (py * (int)a.flow.sH + px0 * (int)a.flow.sW);
+            else if (plane == 2 && a.metric.p) q = (const T*)a.metric.p + pn * a.metric.sN + (py * (int)a.metric.sH + px0 * (int)a.metric.sW);
+            else if (plane >= 4 && plane < 4 + a.C) q = (const T*)a.in.p + (pn * a.in.sN + (plane - 4) * a.in.sC) + (py * (int)a.in.sH + px0 * (int)a.in.sW);
+            else if (plane >= 8 && plane < 12) q = (const float4*)a.tscal + (size_t)pn * a.HW + (unsigned)(py * W + px0 + (plane - 8) * 8);
+            if (q) asm volatile("prefetch.global.L2 [%0];" ::"l"(q));
         }
     }
 #endif
     if (x >= W || y >= H) return;
     const unsigned r = (unsigned)y * (unsigned)W + (unsigned)x, p = n * a.HW + r;
-#else
-    const unsigned p = blockIdx.x * 256 + threadIdx.x;
-    if (p >= a.total) return;
-    const unsigned n = p / a.HW, r = p - n * a.HW;
-    const int y = (int)(r / (unsigned)a.W), x = (int)(r - (unsigned)y * (unsigned)a.W);
-#endif
-    const TF* fp = (const TF*)a.flow.p + n * a.flow.sN + y * a.flow.sH + x * a.flow.sW;
-    const Foot<float> f = make_foot<float>(x, y, (float)ld_stream(fp), (float)ld_stream(fp + a.flow.sC));
+    const TF* fp = (const TF*)a.flow.p + n * a.flow.sN + (kFlat ? (int)r : y * (int)a.flow.sH + x * (int)a.flow.sW);
+    const Foot<float> f = make_foot<float>(x, y, (float)ld_stream(fp), (float)ld_stream(fp + (kFlat ? (long long)a.HW : a.flow.sC)));
     const int x1 = (int)((unsigned)f.x0 + 1u), y1 = (int)((unsigned)f.y0 + 1u);
     const bool vx0 = (unsigned)f.x0 < (unsigned)W, vx1 = (unsigned)x1 < (unsigned)W;
     const bool vy0 = (unsigned)f.y0 < (unsigned)H, vy1 = (unsigned)y1 < (unsigned)H;
@@ -364,11 +361,11 @@ __global__ void __launch_bounds__(256) k_bwd_source4(const BwdArgs a) {
     const float w[4] = {f.wnw, f.wne, f.wsw, f.wse};
 
     float g = 1.f, gprime = 1.f;
-    if (a.mode == DCB_MODE_LINEAR || a.mode == DCB_MODE_SOFT) {
-        const T* mp = (const T*)a.metric.p + n * a.metric.sN + y * a.metric.sH + x * a.metric.sW;
+    if (mode == DCB_MODE_LINEAR || mode == DCB_MODE_SOFT) {
+        const T* mp = (const T*)a.metric.p + n * a.metric.sN + (kFlat ? (int)r : y * (int)a.metric.sH + x * (int)a.metric.sW);
         const float m = ld_stream(mp);
-        g = a.mode == DCB_MODE_SOFT ? expf(m) : m;
-        gprime = a.mode == DCB_MODE_SOFT ? g : 1.f;
+        g = mode == DCB_MODE_SOFT ? expf(m) : m;
+        gprime = mode == DCB_MODE_SOFT ? g : 1.f;
     }
     // the four target cells: one 16-byte gather each (element 0 of the frame stands in for a corner out of range)
     const float4* cell = (const float4*)a.tscal + (size_t)n * a.HW;
@@ -377,41 +374,41 @@ __global__ void __launch_bounds__(256) k_bwd_source4(const BwdArgs a) {
     float4 P[4];
 #pragma unroll
     for (int k = 0; k < 4; ++k) P[k] = __ldcg(cell + co[k]);
-    const T* ip = (const T*)a.in.p + n * a.in.sN + y * a.in.sH + x * a.in.sW;
+    const T* ip = (const T*)a.in.p + n * a.in.sN + (kFlat ? (int)r : y * (int)a.in.sH + x * (int)a.in.sW);
     float v[3] = {0.f, 0.f, 0.f};
-    const bool need_A = (a.gflow != nullptr) || (a.gmetric != nullptr);
+    const bool need_A = kFlat || (a.gflow != nullptr) || (a.gmetric != nullptr);
     if (need_A) {
 #pragma unroll
         for (int c = 0; c < 3; ++c)
-            if (c < a.C) v[c] = ld_stream(ip + (long long)c * a.in.sC);
+            if (c < C) v[c] = ld_stream(ip + (kFlat ? c * (int)a.HW : c * (int)a.in.sC));
     }
 #pragma unroll
     for (int k = 0; k < 4; ++k)
         if (!b[k]) P[k] = make_float4(0.f, 0.f, 0.f, 0.f);
 
-    if (a.gin) {
-        T* gi = (T*)a.gin + (long long)n * a.C * a.HW + r;
+    if (kFlat || a.gin) {
+        T* gi = (T*)a.gin + (long long)n * C * a.HW + r;
         // a dropped corner carries P = 0, but its weight may be inf (huge finite flow): keep 0 * inf out
         const float wz[4] = {b[0] ? w[0] : 0.f, b[1] ? w[1] : 0.f, b[2] ? w[2] : 0.f, b[3] ? w[3] : 0.f};
         const float s0 = fma_rn(P[3].x, wz[3], fma_rn(P[2].x, wz[2], fma_rn(P[1].x, wz[1], mul_rn(P[0].x, wz[0]))));
         const float s1 = fma_rn(P[3].y, wz[3], fma_rn(P[2].y, wz[2], fma_rn(P[1].y, wz[1], mul_rn(P[0].y, wz[0]))));
         const float s2 = fma_rn(P[3].z, wz[3], fma_rn(P[2].z, wz[2], fma_rn(P[1].z, wz[1], mul_rn(P[0].z, wz[0]))));
         st_stream(gi, (any ? s0 : 0.f) * g);
-        if (a.C > 1) st_stream(gi + a.HW, (any ? s1 : 0.f) * g);
-        if (a.C > 2) st_stream(gi + 2ll * a.HW, (any ? s2 : 0.f) * g);
+        if (C > 1) st_stream(gi + a.HW, (any ? s1 : 0.f) * g);
+        if (C > 2) st_stream(gi + 2ll * a.HW, (any ? s2 : 0.f) * g);
     }
     if (!need_A) return;
     float B[4];
 #pragma unroll
     for (int k = 0; k < 4; ++k)
         B[k] = b[k] ? fma_rn(P[k].x, v[0], fma_rn(P[k].y, v[1], fma_rn(P[k].z, v[2], P[k].w))) : 0.f;
-    if (a.gmetric) {
+    if (kFlat ? mode != DCB_MODE_AVG : a.gmetric != nullptr) {
         float s = 0.f;
 #pragma unroll
         for (int k = 0; k < 4; ++k) if (b[k]) s = fma_rn(w[k], B[k], s);
         st<T, float>((T*)a.gmetric + p, any ? s * gprime : 0.f);
     }
-    if (a.gflow) {
+    if (kFlat || a.gflow) {
         const float ey = sub_rn((float)y1, f.fy), dy = sub_rn(f.fy, (float)f.y0);      // d w / d flow, softsplat.py:477-487
         const float ex = sub_rn((float)x1, f.fx), dx = sub_rn(f.fx, (float)f.x0);
         float gx = (B[1] - B[0]) * ey + (B[3] - B[2]) * dy;
@@ -427,6 +424,9 @@ __global__ void __launch_bounds__(256) k_bwd_source4(const BwdArgs a) {
 // Measured on 16 x 1080p (profiles/scripts/run_frames_bwd.py, us per frame, backward only): one frame per group (cells stay in
 // L2, two launches per frame) 52.5; 2 frames 51.3; 4 frames 49.7; all frames in one group (cells round-trip through HBM) 48.6 --
 // the launch boundaries cost more than the 32 B/px of DRAM traffic they save, the same lesson as the forward's tails.
+// dcb_set_option("bwd_flat", 0): A/B switch, always the run-time (strided) form of the packed source pass
+int g_bwd_flat = 1;
+void bwd_set_flat(long long v) { g_bwd_flat = v != 0; }
 constexpr long long kBwdOneGroup = 1ll << 50;
 long long g_bwd_group_bytes = kBwdOneGroup;
 void bwd_set_group_bytes(long long b) { g_bwd_group_bytes = b > 0 ? b : kBwdOneGroup; }
@@ -444,6 +444,26 @@ long long splat_bwd_workspace(long long N, long long C, long long H, long long W
     return align_up(N * H * W * 2 * (dtype == DCB_F64 ? 8 : 4), 256);
 }
 
+template <class T, class TF, int CT>
+static cudaError_t launch_source4_c(const BwdArgs& g, const dim3& grid, cudaStream_t st) {
+    switch (g.mode) {
+        case DCB_MODE_AVG: return launch_pdl(k_bwd_source4<T, TF, CT, DCB_MODE_AVG>, grid, dim3(256), 0, st, g);
+        case DCB_MODE_LINEAR: return launch_pdl(k_bwd_source4<T, TF, CT, DCB_MODE_LINEAR>, grid, dim3(256), 0, st, g);
+        default: return launch_pdl(k_bwd_source4<T, TF, CT, DCB_MODE_SOFT>, grid, dim3(256), 0, st, g);
+    }
+}
+
+template <class T, class TF>
+static cudaError_t launch_source4(const BwdArgs& g, bool flat, cudaStream_t st) {
+    const dim3 grid(g.tiles_x, g.tiles / g.tiles_x, (unsigned)g.N);
+    if (flat) {
+        if (g.C == 1) return launch_source4_c<T, TF, 1>(g, grid, st);
+        if (g.C == 2) return launch_source4_c<T, TF, 2>(g, grid, st);
+        if (g.C == 3) return launch_source4_c<T, TF, 3>(g, grid, st);
+    }
+    return launch_pdl(k_bwd_source4<T, TF, 0, 0>, grid, dim3(256), 0, st, g);
+}
+
 template <class T, class TF>
 static int launch_bwd(BwdArgs& a, int dtype, cudaStream_t st) {
     using A = typename Acc<T>::type;
@@ -454,9 +474,25 @@ static int launch_bwd(BwdArgs& a, int dtype, cudaStream_t st) {
             a.tiles_x = (unsigned)(a.W + 31) / 32;
             a.tiles = a.tiles_x * ((unsigned)(a.H + 7) / 8);
             a.pf_dist = (unsigned)(device_sm_count() * 5);      // 48 registers: 5 CTAs per SM
+            a.pf_rows = a.pf_dist / a.tiles_x > 0 ? a.pf_dist / a.tiles_x : 1;
+            {   // in-frame element offsets are formed in 32 bits
+                auto fits = [&](const View& v, long long ch) {
+                    if (!v.p) return true;
+                    auto ab = [](long long q) { return q < 0 ? -q : q; };
+                    return (ch - 1) * ab(v.sC) + (long long)(a.H - 1) * ab(v.sH) + (long long)(a.W - 1) * ab(v.sW) < (1ll << 31);
+                };
+                if (!fits(a.in, a.C) || !fits(a.flow, 2) || !fits(a.metric, 1) || (long long)a.tiles / a.tiles_x > 65535 || a.N > 65535)
+                    return set_error(DCB_E_LIMIT, "splat_bwd: tensor spans beyond 2^31 elements (or more than 65535 frames / tile rows) are not supported by the packed path");
+            }
             long long G = g_bwd_group_bytes / ((long long)a.HW * 16 > 0 ? (long long)a.HW * 16 : 1);
             if (G < 1) G = 1;
             const int es = (int)sizeof(T), fs = (int)sizeof(TF);
+            // the compile-time form: frames contiguous inside (NCHW), every gradient wanted (a metric gradient exists in the
+            // linear / soft modes only)
+            auto plane_contig = [&](const View& v, long long ch) { return v.sW == 1 && v.sH == a.W && (ch == 1 || v.sC == (long long)a.HW); };
+            const bool has_metric = a.mode == DCB_MODE_LINEAR || a.mode == DCB_MODE_SOFT;
+            const bool flat = g_bwd_flat && plane_contig(a.in, a.C) && plane_contig(a.flow, 2) && (!has_metric || plane_contig(a.metric, 1)) &&
+                              a.gin && a.gflow && (has_metric ? a.gmetric != nullptr : a.gmetric == nullptr);
             for (long long f0 = 0; f0 < a.N; f0 += G) {
                 const long long nf = a.N - f0 < G ? a.N - f0 : G;
                 BwdArgs g = a;
@@ -470,11 +506,7 @@ static int launch_bwd(BwdArgs& a, int dtype, cudaStream_t st) {
                 g.N = (int)nf; g.total = (unsigned)(nf * a.HW);
                 DCB_CHECK_CUDA(launch_pdl(k_bwd_target4<T>, dim3((g.total + 255) / 256), dim3(256), 0, st, g));
                 count_launch();
-#if DCB_B4_TILE
-                DCB_CHECK_CUDA(launch_pdl(k_bwd_source4<T, TF>, dim3(g.tiles * (unsigned)g.N), dim3(256), 0, st, g));
-#else
-                DCB_CHECK_CUDA(launch_pdl(k_bwd_source4<T, TF>, dim3((g.total + 255) / 256), dim3(256), 0, st, g));
-#endif
+                DCB_CHECK_CUDA((launch_source4<T, TF>(g, flat, st)));
                 count_launch();
             }
             return DCB_OK;

@@ -126,6 +126,7 @@ int32_t dcb_splat_fwd_workspace_is_scratch(int64_t N, int64_t C, int64_t H, int6
  *   "planar_one_launch" 0 (default) two chained launches | 1 a many-channel call whose frames fit one group and whose warps
  *                       are all resident at once (latents, small feature maps) runs as ONE launch with a grid barrier
  *                       (measured slower on B200: 20.6-22.2 us against 16.4 us for C2 under graph replay)
+ *   "bwd_flat"          1 (default) contiguous frames take the compile-time (C, mode) form of the packed backward | 0 never
  *   "lists_nhwc"        1 (default) channels-last many-channel tensors take the channel-quad gather | 0 the NCHW gather
  * Returns DCB_OK, or DCB_E_MODE for an unknown name. There is no equivalent in the reference (its kernels are
  * re-specialised per shape by string templating, controlnet/softsplat.py:27-216).

@@ -245,14 +245,14 @@ __device__ __forceinline__ void ld_quad_ro(const __nv_bfloat16* p, float (&o)[4]
 }
 
 #ifndef DCB_LQ_CBLK
-#define DCB_LQ_CBLK 128       // channels per pass through the transpose tile (16.5 KB of shared memory)
+#define DCB_LQ_CBLK 64        // channels per pass through the transpose tile (8.25 KB of shared memory; measured: 64 beats 32 and 128 at C = 64)
 #endif
 #ifndef DCB_LQ_U
 #define DCB_LQ_U 4            // list entries whose loads are in flight together
 #endif
 
 // K7d for channels-last input. A CTA owns 32 consecutive targets of one row: 8 lanes share a target (4 targets per warp,
-// one pass per CTA), a lane owns up to 4 of the block's 32 channel quads (q = lane, lane + 8, ...: 128 contiguous bytes
+// one pass per CTA), a lane owns up to 2 of the block's 16 channel quads (q = lane, lane + 8, ...: 128 contiguous bytes
 // per group and load). The entries of a list are read once per chunk of U and reused for every quad; the normaliser is
 // summed in the same pass. Output: NCHW-contiguous, through the transpose tile.
 template <class T>

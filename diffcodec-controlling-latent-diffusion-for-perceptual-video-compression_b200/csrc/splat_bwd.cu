@@ -481,11 +481,12 @@ static int launch_bwd(BwdArgs& a, int dtype, cudaStream_t st) {
                     auto ab = [](long long q) { return q < 0 ? -q : q; };
                     return (ch - 1) * ab(v.sC) + (long long)(a.H - 1) * ab(v.sH) + (long long)(a.W - 1) * ab(v.sW) < (1ll << 31);
                 };
-                if (!fits(a.in, a.C) || !fits(a.flow, 2) || !fits(a.metric, 1) || (long long)a.tiles / a.tiles_x > 65535 || a.N > 65535)
-                    return set_error(DCB_E_LIMIT, "splat_bwd: tensor spans beyond 2^31 elements (or more than 65535 frames / tile rows) are not supported by the packed path");
+                if (!fits(a.in, a.C) || !fits(a.flow, 2) || !fits(a.metric, 1) || (long long)a.tiles / a.tiles_x > 65535)
+                    return set_error(DCB_E_LIMIT, "splat_bwd: tensor spans beyond 2^31 elements (or more than 524280 rows) are not supported by the packed path");
             }
             long long G = g_bwd_group_bytes / ((long long)a.HW * 16 > 0 ? (long long)a.HW * 16 : 1);
             if (G < 1) G = 1;
+            if (G > 65535) G = 65535;                           // gridDim.z of the source pass
             const int es = (int)sizeof(T), fs = (int)sizeof(TF);
             // the compile-time form: frames contiguous inside (NCHW), every gradient wanted (a metric gradient exists in the
             // linear / soft modes only)

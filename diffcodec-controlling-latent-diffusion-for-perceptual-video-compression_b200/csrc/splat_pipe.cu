@@ -682,9 +682,12 @@ __device__ __forceinline__ void epilogue_item(const PipeArgs& a, unsigned z, uns
 #ifndef DCB_EPI_WARPS
 #define DCB_EPI_WARPS 4
 #endif
+#ifndef DCB_EPI_MINCTAS
+#define DCB_EPI_MINCTAS (DCB_MINCTAS / DCB_EPI_WARPS)
+#endif
 constexpr int kEpiWarps = DCB_EPI_WARPS;
 template <class T, int MODE, int CA, int KIND>
-__global__ void __launch_bounds__(32 * kEpiWarps, (KIND ? kMinCtasRecipe : kMinCtas) / kEpiWarps) k_splat_epilogue(const __grid_constant__ PipeArgs a) {
+__global__ void __launch_bounds__(32 * kEpiWarps, KIND ? kMinCtasRecipe / kEpiWarps : DCB_EPI_MINCTAS) k_splat_epilogue(const __grid_constant__ PipeArgs a) {
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     asm volatile("griddepcontrol.wait;" ::: "memory");
     const unsigned chunk = blockIdx.x * kEpiWarps + (threadIdx.x >> 5);

@@ -569,3 +569,14 @@ def test_planar_single_launch_kernel(dcb, orc, shape, dtype, mode):
     assert_close(again.float().cpu(), ref, rel, "second single launch vs oracle")
     assert_close(after.float().cpu(), ref, rel, "two launches after the single-launch calls")
     assert_close(one.float(), two.float(), 2e-6 if dtype == torch.float32 else 1e-2, "single launch vs two launches")
+
+
+def test_more_frames_than_a_grid_dimension(dcb, orc):
+    """70001 frames of 2 x 3 pixels: the forward's and the packed backward's 3-d grids put frames on gridDim.z (<= 65535), so
+    both must cut the batch into several launches (softsplat.py accepts any N)."""
+    n, c, h, w = 70001, 2, 2, 3
+    tin, flow, metric, gout = make_inputs(5, n, c, h, w, flow_scale=0.8)
+    ref = oracle_run(orc, tin, flow, metric, gout, "soft")
+    got = cuda_run(dcb.softsplat, tin, flow, metric, gout, "soft")
+    for k in ("out", "gin", "gflow", "gmetric"):
+        assert_close(got[k], ref[k], 1e-5, k)

@@ -59,7 +59,7 @@ __device__ __forceinline__ float ld_global_ro(const __nv_bfloat16* p) {
 
 // dcb_set_option("lists_nhwc", 0): A/B switch, channels-last input through the NCHW gather (strided scalar loads)
 int g_lists_nhwc = 1;
-void lists_set_nhwc(long long v) { g_lists_nhwc = v != 0; }
+void lists_set_nhwc(long long v) { g_lists_nhwc = (int)v; }      // 0 off | 1 on | 8 on, always eight lanes per target (A/B)
 
 struct ListArgs {
     View in, flow, metric, mask;
@@ -72,7 +72,7 @@ struct ListArgs {
     int C, H, W;
     unsigned HW, gtotal;     // pixels per frame, pixels in this frame group
     unsigned tiles_x, tiles; // gather: 32 x 8 target tiles per row / per frame
-    unsigned row_tiles;      // channels-last gather: 32 x 1 target tiles per frame
+    unsigned q_tiles_x, row_tiles;   // channels-last gather: (256 / G) x 1 target tiles per row / per frame
     int frame0;              // first frame of the group
     int mode, eps;
     int nhwc;                // channels-last input whose channel quads are aligned: k_list_gather_nhwc
@@ -251,18 +251,19 @@ __device__ __forceinline__ void ld_quad_ro(const __nv_bfloat16* p, float (&o)[4]
 #define DCB_LQ_U 4            // list entries whose loads are in flight together
 #endif
 
-// K7d for channels-last input. A CTA owns 32 consecutive targets of one row: 8 lanes share a target (4 targets per warp,
-// one pass per CTA), a lane owns up to 2 of the block's 16 channel quads (q = lane, lane + 8, ...: 128 contiguous bytes
-// per group and load). The entries of a list are read once per chunk of U and reused for every quad; the normaliser is
-// summed in the same pass. Output: NCHW-contiguous, through the transpose tile.
-template <class T>
+// K7d for channels-last input. G lanes share a target (8, or 4 when whole 64-channel blocks make every lane's four quads
+// live): a CTA owns 256 / G consecutive targets of one row, one pass per CTA; a lane owns the channel quads q = lane,
+// lane + G, ... of the block (G x 16 contiguous bytes per group and load). The entries of a list are read once per chunk
+// of U and reused for every quad; the normaliser is summed in the same pass. Output: NCHW-contiguous, through the
+// transpose tile (row pitch chosen so that neither its writes nor its reads conflict).
+template <class T, int G>
 __global__ void __launch_bounds__(256) k_list_gather_nhwc(const ListArgs a) {
-    constexpr int CBLK = DCB_LQ_CBLK, U = DCB_LQ_U, G = 8, QPL = CBLK / 4 / G;
-    __shared__ float tile[CBLK][33];
+    constexpr int CBLK = DCB_LQ_CBLK, U = DCB_LQ_U, QPL = CBLK / 4 / G, TT = 256 / G, PITCH = TT + (G == 8 ? 1 : 2);
+    __shared__ float tile[CBLK][PITCH];
     pdl_wait();
     const unsigned tile_id = blockIdx.x % a.row_tiles, n = blockIdx.x / a.row_tiles;
-    const unsigned tx = tile_id % a.tiles_x, y = tile_id / a.tiles_x;
-    const unsigned x0 = tx * 32;
+    const unsigned tx = tile_id % a.q_tiles_x, y = tile_id / a.q_tiles_x;
+    const unsigned x0 = tx * TT;
     const int frame = a.frame0 + (int)n;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int ql = lane % G;
@@ -327,8 +328,10 @@ __global__ void __launch_bounds__(256) k_list_gather_nhwc(const ListArgs a) {
 #pragma unroll
                 for (int k = 0; k < 4; ++k) tile[4 * (ql + i * G) + k][tt] = scaled ? mul_rn(acc[i][k], scale) : acc[i][k];
         __syncthreads();
-        if (x0 + (unsigned)lane < (unsigned)a.W)
-            for (int c = warp; c < 4 * quads; c += 8) st_stream(obase + (size_t)(c0 + c) * a.HW + lane, tile[c][lane]);
+        for (int c = warp; c < 4 * quads; c += 8)
+#pragma unroll
+            for (int col = lane; col < TT; col += 32)
+                if (x0 + (unsigned)col < (unsigned)a.W) st_stream(obase + (size_t)(c0 + c) * a.HW + col, tile[c][col]);
         __syncthreads();
     }
 }
@@ -397,7 +400,14 @@ static int launch_lists(ListArgs& a, const ListLayout& L, char* ws, int N, bool 
         DCB_CHECK_CUDA(launch_pdl(k_list_alloc, blocks, 256, 0, st, a));
         DCB_CHECK_CUDA(launch_pdl(k_list_fill<T, TF>, blocks, 256, 0, st, a));
         if (a.nhwc) {
-            DCB_CHECK_CUDA(launch_pdl(k_list_gather_nhwc<T>, a.row_tiles * (unsigned)frames, 256, 0, st, a));
+            // four lanes per target when every lane's four quads are live (whole 64-channel blocks), else eight
+            // measured at C = 64 (profiles/r02/NOTES.md section 9): 8 / 4 / 2 lanes per target = 151 / 127 / 147 us (fp32)
+            const bool g4 = a.C % DCB_LQ_CBLK == 0 && g_lists_nhwc != 8;
+            const unsigned tt = g4 ? 64u : 32u;
+            a.q_tiles_x = ((unsigned)a.W + tt - 1) / tt;
+            a.row_tiles = a.q_tiles_x * (unsigned)a.H;
+            if (g4) DCB_CHECK_CUDA(launch_pdl(k_list_gather_nhwc<T, 4>, a.row_tiles * (unsigned)frames, 256, 0, st, a));
+            else DCB_CHECK_CUDA(launch_pdl(k_list_gather_nhwc<T, 8>, a.row_tiles * (unsigned)frames, 256, 0, st, a));
         } else {
             DCB_CHECK_CUDA(launch_pdl(k_list_gather<T>, a.tiles * (unsigned)frames, 256, 0, st, a));
         }
@@ -424,7 +434,7 @@ int splat_lists_impl(const DcbTensor* in, const DcbTensor* flow, const DcbTensor
     a.mode = mode; a.eps = eps;
     a.tiles_x = (unsigned)(a.W + 31) / 32;
     a.tiles = a.tiles_x * ((unsigned)(a.H + 7) / 8);
-    a.row_tiles = a.tiles_x * (unsigned)a.H;
+    a.q_tiles_x = a.tiles_x; a.row_tiles = a.tiles_x * (unsigned)a.H;
     {   // channels-last: unit channel stride, whole quads, every quad aligned to its vector load
         const long long es = elem_size(in->dtype);
         a.nhwc = (g_lists_nhwc && in->stride[1] == 1 && a.C % 4 == 0 && a.C >= 32 && ((uintptr_t)in->ptr % (uintptr_t)(4 * es)) == 0 &&

@@ -14,7 +14,7 @@ for dt in (torch.float32, torch.bfloat16):
     fl = (torch.nn.functional.interpolate(low, size=(256, 256), mode="bicubic") * 4).to(dt)
     cl = ti.to(memory_format=torch.channels_last)
     for name, x in (("NCHW", ti), ("channels_last", cl)):
-        for opt in ((1,) if name == "NCHW" else (1, 0)):
+        for opt in ((1,) if name == "NCHW" else (1, 8, 0)):
             d._lib.set_option("lists_nhwc", opt)
             with torch.no_grad():
                 for _ in range(5): d.softsplat(x, fl, me, "soft")

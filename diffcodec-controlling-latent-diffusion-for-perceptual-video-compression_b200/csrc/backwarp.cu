@@ -143,6 +143,7 @@ struct WarpRowsArgs {
     int fsN, fsC, fsH;           // flow strides; sW == 1
     int gsN, gsC, gsH;           // gt strides; sW == 1
     unsigned tiles_x, pf_dist;   // CTAs per tile row; prefetch distance = resident CTAs
+    unsigned pf_rows;            // ... in tile rows
     int C, H, W, HW, align;
 };
 
@@ -159,16 +160,18 @@ __global__ void __launch_bounds__(256, DCB_BW_MINCTAS) k_backwarp_rows(const War
     constexpr int PX = 2;
     // a CTA covers 8 rows x 64 columns: the two image rows a warp gathers from are the rows its
     // neighbours in the CTA gather from too, so they are served by this SM's L1
-    const unsigned tx = blockIdx.x % a.tiles_x, ty = blockIdx.x / a.tiles_x;
-    const unsigned n = blockIdx.y;
+    // grid = (tile columns, tile rows, frames): no integer division in front of the first load
+    const unsigned tx = blockIdx.x, ty = blockIdx.y;
+    const unsigned n = blockIdx.z;
     const int y = (int)(ty * 8 + (threadIdx.x >> 5));
     const int x = (int)((tx * 32 + (threadIdx.x & 31)) * PX);
 #if DCB_BW_PF
-    {   // L2 prefetch of the rows a CTA one wave ahead will stream: one line per lane
-        unsigned pb = blockIdx.x + a.pf_dist, pn = n;
-        if (pb >= gridDim.x) { pb -= gridDim.x; ++pn; }
-        if (pn < gridDim.y && pb < gridDim.x) {
-            const int px0 = (int)((pb % a.tiles_x) * 32 * PX), py = (int)((pb / a.tiles_x) * 8 + (threadIdx.x >> 5));
+    {   // L2 prefetch of the rows a CTA one wave ahead (pf_rows tile rows further down, wrapping into the next frame) will
+        // stream: one line per lane
+        unsigned pty = ty + a.pf_rows, pn = n;
+        if (pty >= gridDim.y) { pty -= gridDim.y; ++pn; }
+        if (pn < gridDim.z && pty < gridDim.y) {
+            const int px0 = (int)(tx * 32 * PX), py = (int)(pty * 8 + (threadIdx.x >> 5));
             const int lane = threadIdx.x & 31;
             const int plane = lane >> 1, pxl = px0 + (lane & 1) * 32;      // two lines of 32 elements per row segment
             if (py < a.H && pxl < a.W) {
@@ -316,6 +319,7 @@ static bool rows_supported(const DcbTensor* image, const DcbTensor* flow, const 
                            const DcbTensor* residual) {
     if (image->size[0] > 65535 || image->dtype == DCB_F64 || image->size[3] % 2 != 0 || max_offset31(image) < 0) return false;
     if (image->size[0] * image->size[1] * image->size[2] * image->size[3] >= (1ll << 31)) return false;
+    if (image->size[0] > 65535 || (image->size[2] + 7) / 8 > 65535) return false;      // frames on gridDim.z, tile rows on gridDim.y
     if (!rows_vec(flow) || (gt && (!rows_vec(gt) || gt->dtype != image->dtype))) return false;
     if (flow->dtype != image->dtype && !(image->dtype == DCB_BF16 && flow->dtype == DCB_F32)) return false;
     const uintptr_t m = (uintptr_t)(2 * elem_size(image->dtype) - 1);
@@ -335,7 +339,8 @@ static int launch_warp_rows(const DcbTensor* image, const DcbTensor* flow, const
     a.HW = a.H * a.W; a.align = align;
     a.tiles_x = (unsigned)(a.W / 2 + 31) / 32;
     a.pf_dist = (unsigned)(device_sm_count() * DCB_BW_MINCTAS);
-    const dim3 grid(a.tiles_x * (unsigned)((a.H + 7) / 8), (unsigned)image->size[0]);
+    a.pf_rows = a.pf_dist / a.tiles_x > 0 ? a.pf_dist / a.tiles_x : 1;
+    const dim3 grid(a.tiles_x, (unsigned)((a.H + 7) / 8), (unsigned)image->size[0]);
     const TapConst<float> kc = make_tap_const<float>(a.W, a.H);
     if (image->dtype == DCB_F32) k_backwarp_rows<float, float><<<grid, 256, 0, st>>>(a, kc);
     else if (flow->dtype == DCB_F32) k_backwarp_rows<__nv_bfloat16, float><<<grid, 256, 0, st>>>(a, kc);

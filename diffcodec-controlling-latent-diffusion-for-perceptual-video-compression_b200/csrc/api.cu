@@ -73,6 +73,7 @@ int resample_batch_impl(const DcbResampleJob* jobs, int n_jobs, cudaStream_t st)
 int convert_impl(const void* src, int src_dtype, void* dst, int dst_dtype, long long n, float scale, cudaStream_t st);
 extern int g_fwd_path;
 bool use_owner(int dtype, int mode, long long C, long long H, long long W);
+bool fwd_ws_is_scratch(long long N, long long C, long long H, long long W, int dtype, int mode);
 void owner_set_group_bytes(long long b);
 void pipe_set_group_bytes(long long b);
 void pipe_set_ring_slots(long long n);
@@ -167,9 +168,8 @@ int64_t dcb_splat_fwd_workspace_bytes(int64_t N, int64_t C, int64_t H, int64_t W
 }
 
 int32_t dcb_splat_fwd_workspace_is_scratch(int64_t N, int64_t C, int64_t H, int64_t W, int32_t dtype, int32_t mode, int32_t flags) {
-    (void)N;
     if (flags & DCB_FLAG_DETERMINISTIC) return 1;
-    return use_owner(dtype, mode, C, H, W) ? 1 : 0;
+    return fwd_ws_is_scratch(N, C, H, W, dtype, mode) ? 1 : 0;
 }
 
 int dcb_set_option(const char* name, int64_t value) {

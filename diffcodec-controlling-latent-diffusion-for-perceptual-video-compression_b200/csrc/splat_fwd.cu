@@ -190,6 +190,16 @@ bool use_owner(int dtype, int mode, long long C, long long H, long long W) {
     return owner_supported(C, mode, H, W);
 }
 
+// Is the forward's workspace plain scratch at these sizes (nothing in it has to be all-zero on entry or is left all-zero)?
+// True for the owner kernels and for the per-target list path: its lists are rebuilt by every call and only its counters are
+// zeroed (by the call itself), so sharing the kept-zero accumulator buffer would cost a memset of the whole list area
+// (40 B per pixel) behind every call. A strided view of these sizes that falls back to the planar accumulators zeroes them itself.
+bool fwd_ws_is_scratch(long long N, long long C, long long H, long long W, int dtype, int mode) {
+    if (use_owner(dtype, mode, C, H, W)) return true;
+    if (small_frames(dtype, mode, N, C, H, W) || use_pipe(dtype, mode, C) || dtype == DCB_F64) return false;
+    return lists_shape(dtype, mode, N, C, H, W);
+}
+
 long long splat_fwd_workspace(long long N, long long C, long long H, long long W, int dtype, int mode) {
     if (use_owner(dtype, mode, C, H, W)) return owner_workspace(N, H, W);
     if (small_frames(dtype, mode, N, C, H, W)) return cluster_workspace(N, C, H, W, mode);

@@ -105,8 +105,9 @@ int64_t dcb_splat_bwd_workspace_bytes(int64_t N, int64_t C, int64_t H, int64_t W
 
 /*
  * 1 when the forward splat of these sizes keeps NO accumulators in its workspace (target-tile-owner kernels:
- * the workspace only holds small per-strip landing boxes): the workspace is then plain scratch, DCB_FLAG_WS_CLEAN
- * buys nothing (if it is passed anyway the library zeroes what it wrote, to honour the flag's exit guarantee).
+ * the workspace only holds small per-strip landing boxes; many channels on large tensors: per-target lists that
+ * every call rebuilds): the workspace is then plain scratch, DCB_FLAG_WS_CLEAN buys nothing (if it is passed
+ * anyway the library zeroes what it wrote, to honour the flag's exit guarantee -- 40 bytes per pixel for the lists).
  * 0 when the workspace holds accumulators and the all-zero protocol of DCB_FLAG_WS_CLEAN saves a memset.
  */
 int32_t dcb_splat_fwd_workspace_is_scratch(int64_t N, int64_t C, int64_t H, int64_t W, int32_t elem_dtype,

@@ -57,7 +57,8 @@ def test_workspace_queries_need_no_gpu():
         assert lib.dcb_splat_fwd_workspace_bytes(64, 3, 1080, 1920, L.DCB_F32, L.MODE_SOFT, 0) == 64 * boxes
         assert lib.dcb_splat_fwd_workspace_bytes(4, 3, 135, 240, L.DCB_BF16, L.MODE_SOFT, 0) == 0
         assert lib.dcb_splat_fwd_workspace_is_scratch(1, 3, 1080, 1920, L.DCB_F32, L.MODE_SOFT, 0) == 1
-        assert lib.dcb_splat_fwd_workspace_is_scratch(8, 64, 256, 256, L.DCB_F32, L.MODE_SOFT, 0) == 0
+        assert lib.dcb_splat_fwd_workspace_is_scratch(8, 64, 256, 256, L.DCB_F32, L.MODE_SOFT, 0) == 1     # per-target lists: rebuilt by every call
+        assert lib.dcb_splat_fwd_workspace_is_scratch(2, 64, 32, 32, L.DCB_F32, L.MODE_SOFT, 0) == 0       # planar accumulators
         assert lib.dcb_occlusion_mask_workspace_bytes(2, 64, 64) == 0
     finally:
         L.set_option("fwd_path", 0)

@@ -580,3 +580,26 @@ def test_more_frames_than_a_grid_dimension(dcb, orc):
     got = cuda_run(dcb.softsplat, tin, flow, metric, gout, "soft")
     for k in ("out", "gin", "gflow", "gmetric"):
         assert_close(got[k], ref[k], 1e-5, k)
+
+
+@pytest.mark.parametrize("mode", ["soft", "sum"])
+def test_list_path_long_lists(dcb, orc, mode):
+    """A strongly compressive flow (every pixel moves 60 % of the way to the frame centre: ~25 sources per target there, none
+    elsewhere) on a tensor that takes the per-target list path: long and empty lists side by side (csrc/splat_lists.cu).
+    NCHW and channels_last gathers vs the oracle."""
+    n, c, h, w = 2, 64, 192, 200
+    tin, _, metric, _ = make_inputs(97, n, c, h, w)
+    ys, xs = torch.meshgrid(torch.arange(h, dtype=torch.float32), torch.arange(w, dtype=torch.float32), indexing="ij")
+    flow = torch.stack([-0.6 * (xs - w / 2 + 0.3), -0.6 * (ys - h / 2 - 0.2)], 0).unsqueeze(0).repeat(n, 1, 1, 1)
+    flow = flow + 0.05 * torch.randn(n, 2, h, w, generator=torch.Generator().manual_seed(3))
+    me_ref = metric if mode == "soft" else None
+    ref = orc.softsplat(tin, flow, me_ref, mode)
+    x, fl = tin.cuda(), flow.cuda()
+    me = metric.cuda() if me_ref is not None else None
+    before = dcb.launch_count()
+    a = dcb.softsplat(x, fl, me, mode)
+    assert dcb.launch_count() - before == 4          # count, alloc, fill, gather
+    b = dcb.softsplat(x.to(memory_format=torch.channels_last), fl, me, mode)
+    # long lists are summed in a different order than the oracle's: 25 terms of fp32
+    assert_close(a.cpu(), ref, 2e-5, "NCHW gather, long lists")
+    assert_close(b.cpu(), ref, 2e-5, "channels_last gather, long lists")

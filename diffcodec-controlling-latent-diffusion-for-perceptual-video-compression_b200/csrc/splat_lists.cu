@@ -167,8 +167,9 @@ __global__ void __launch_bounds__(256, DCB_LMINCTAS) k_list_gather(const ListArg
     pdl_wait();
     // a CTA owns a 32 x 8 tile of targets: the sources of vertically adjacent targets are the same
     // rows of `in`, so they are served by this SM's L1 instead of L2
-    const unsigned tile = blockIdx.x % a.tiles, n = blockIdx.x / a.tiles;
-    const unsigned tx = tile % a.tiles_x, ty = tile / a.tiles_x;
+    // grid = (tile columns, tile rows, frames of the group): no integer division in front of the first load
+    const unsigned n = blockIdx.z;
+    const unsigned tx = blockIdx.x, ty = blockIdx.y;
     const unsigned x = tx * 32 + (threadIdx.x & 31), y = ty * 8 + (threadIdx.x >> 5);
     if (x >= (unsigned)a.W || y >= (unsigned)a.H) return;
     const unsigned r = y * a.W + x, t = n * a.HW + r;
@@ -261,8 +262,9 @@ __global__ void __launch_bounds__(256) k_list_gather_nhwc(const ListArgs a) {
     constexpr int CBLK = DCB_LQ_CBLK, U = DCB_LQ_U, QPL = CBLK / 4 / G, TT = 256 / G, PITCH = TT + (G == 8 ? 1 : 2);
     __shared__ float tile[CBLK][PITCH];
     pdl_wait();
-    const unsigned tile_id = blockIdx.x % a.row_tiles, n = blockIdx.x / a.row_tiles;
-    const unsigned tx = tile_id % a.q_tiles_x, y = tile_id / a.q_tiles_x;
+    // grid = (tile columns, rows, frames of the group): no integer division in front of the first load
+    const unsigned n = blockIdx.z;
+    const unsigned tx = blockIdx.x, y = blockIdx.y;
     const unsigned x0 = tx * TT;
     const int frame = a.frame0 + (int)n;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -343,6 +345,7 @@ static long long lists_group_frames(long long N, long long H, long long W) {
     const long long per = 32 * H * W;                             // 4 entries of 8 B per pixel
     long long g = ((long long)DCB_LGROUP_MB << 20) / (per > 0 ? per : 1);
     if (g < 1) g = 1;
+    if (g > 65535) g = 65535;                                     // the gathers put the group's frames on gridDim.z
     return g > N ? (N < 1 ? 1 : N) : g;
 }
 
@@ -379,6 +382,7 @@ bool lists_supported(const DcbTensor* in, const DcbTensor* flow, const DcbTensor
 #endif
     if (N * C * H * W * elem_size(in->dtype) < ((long long)DCB_LMIN_MB << 20)) return false;
     if (N * H * W < 65536) return false;                          // one thread per pixel: few pixels cannot fill the machine
+    if (H > 65535) return false;                                  // rows on gridDim.y of the channels-last gather
     const long long G = lists_group_frames(N, H, W);
     if (4 * G * H * W >= (1ll << 31)) return false;
     if (in->stride[2] < 0 || in->stride[3] < 0) return false;
@@ -406,10 +410,11 @@ static int launch_lists(ListArgs& a, const ListLayout& L, char* ws, int N, bool 
             const unsigned tt = g4 ? 64u : 32u;
             a.q_tiles_x = ((unsigned)a.W + tt - 1) / tt;
             a.row_tiles = a.q_tiles_x * (unsigned)a.H;
-            if (g4) DCB_CHECK_CUDA(launch_pdl(k_list_gather_nhwc<T, 4>, a.row_tiles * (unsigned)frames, 256, 0, st, a));
-            else DCB_CHECK_CUDA(launch_pdl(k_list_gather_nhwc<T, 8>, a.row_tiles * (unsigned)frames, 256, 0, st, a));
+            const dim3 grid(a.q_tiles_x, (unsigned)a.H, (unsigned)frames);
+            if (g4) DCB_CHECK_CUDA(launch_pdl(k_list_gather_nhwc<T, 4>, grid, dim3(256), 0, st, a));
+            else DCB_CHECK_CUDA(launch_pdl(k_list_gather_nhwc<T, 8>, grid, dim3(256), 0, st, a));
         } else {
-            DCB_CHECK_CUDA(launch_pdl(k_list_gather<T>, a.tiles * (unsigned)frames, 256, 0, st, a));
+            DCB_CHECK_CUDA(launch_pdl(k_list_gather<T>, dim3(a.tiles_x, a.tiles / a.tiles_x, (unsigned)frames), dim3(256), 0, st, a));
         }
         count_launch(4);
         // a shared all-zero workspace is handed back all-zero: one memset behind the gather (zeroing

@@ -514,8 +514,11 @@ static int launch_bwd(BwdArgs& a, int dtype, cudaStream_t st) {
         }
     }
     // channel slices: fill ~148 SMs x 8 CTAs when pixels are scarce
+#ifndef DCB_BS_FILL
+#define DCB_BS_FILL 2048
+#endif
     int cs = 1;
-    while (cs < 32 && cs * 2 <= a.C && (long long)a.total * cs < 148LL * 2048) cs *= 2;
+    while (cs < 32 && cs * 2 <= a.C && (long long)a.total * cs < 148LL * DCB_BS_FILL) cs *= 2;
     if (a.mode != DCB_MODE_SUM) {
         int ct = 1;                                               // the target pass keeps 8 channels per slice in flight
         while (ct < 32 && ct * 2 * 8 <= a.C && (long long)a.total * ct < 148LL * 2048) ct *= 2;

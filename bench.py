@@ -446,6 +446,7 @@ def _uvg_sweep(torch, d, dev, rank, world, peak, gops_per_chunk=16):
     # deterministic mode on the first 8 GOPs of the sweep: an exact integer hash of the residual bits, independent of how many
     # ranks shared the work
     hashes = torch.zeros(8, dtype=torch.int64, device=dev)
+    first_res, first_gi = None, -1
     with d.deterministic(True):
         for gi, u in enumerate(d.enumerate_gops()[:8]):
             if gi % world != rank:
@@ -457,16 +458,36 @@ def _uvg_sweep(torch, d, dev, rank, world, peak, gops_per_chunk=16):
             f2 = -f1 + 0.5 * torch.nn.functional.interpolate(low2[:k], size=(H, W), mode="bicubic", align_corners=False)
             _, res = d.residual_conditioning(img[:k], f1, f2, gt[:k], "dataset")
             hashes[gi] = res.contiguous().view(torch.int32).to(torch.int64).sum()
+            if first_res is None:
+                first_res, first_gi = res.clone(), gi
     if world > 1:
         dist.all_reduce(hashes, op=dist.ReduceOp.SUM)                  # exact (integers); every GOP is owned by one rank
     det_hash = int(hashes.sum().item()) & ((1 << 62) - 1)
+    # north_star: "NCCL is used only to gather the output tensors": every rank's first deterministic GOP (3 residual frames,
+    # 74.6 MB) gathered to rank 0 over NCCL, timed, and checked bit for bit against the hash its owner computed
+    out_gather = {"backend": "none"}
+    if world > 1 and world <= 8:
+        bufs = d.gather_outputs(first_res, dst=0)                     # first use sets up NCCL's point-to-point channels: untimed
+        del bufs
+        torch.cuda.synchronize(); dist.barrier()
+        g1 = time.perf_counter()
+        bufs = d.gather_outputs(first_res, dst=0)
+        torch.cuda.synchronize()
+        og_ms = (time.perf_counter() - g1) * 1e3
+        ok = None
+        if rank == 0:
+            ok = all(int(b.contiguous().view(torch.int32).to(torch.int64).sum().item()) == int(hashes[r].item()) for r, b in enumerate(bufs))
+        out_gather = {"backend": "nccl", "tensors": world, "bytes_per_rank": first_res.numel() * first_res.element_size(), "ms": round(og_ms, 2),
+                      "gb_s_into_rank0": round((world - 1) * first_res.numel() * first_res.element_size() / og_ms / 1e6, 1),
+                      "bit_identical_to_owner_hash": ok}
+        del bufs
     return {"gops": 975, "gops_this_rank": len(units), "inter_frames": all_frames, "ms": round(ms, 2), "scaling": "strong",
             "frames_per_s": round(all_frames / ms * 1e3, 1), "mpixel_s": round(all_frames * H * W / ms / 1e3, 1),
             "alg_gbs_per_gpu": round(64 * all_frames * H * W / ms / 1e6 / world, 1),
             "frac_of_peak": round(64 * all_frames * H * W / ms / 1e6 / world / peak, 3),
             "digest": float(f"{digest:.9g}"), "checksum_gather": {"backend": "nccl" if world > 1 else "none", "ms": round(gather_ms, 2),
                                                                    "table": list(allsums.shape)},
-            "deterministic_hash_first_8_gops": det_hash}
+            "deterministic_hash_first_8_gops": det_hash, "output_gather": out_gather}
 
 
 def run_ours(args):

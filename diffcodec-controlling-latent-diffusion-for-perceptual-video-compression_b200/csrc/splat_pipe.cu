@@ -1,28 +1,34 @@
 // splat_pipe.cu -- the forward splat for C+1 <= 4 channels (frames, flows, SD latents) as a
 // software pipeline of plain, synchronisation-free kernels (sm_100a).
 //
-// Why (measured on B200, profiles/r01/): L2 reductions retire at most one 32-byte sector per
-// slice per clock (~360 G sectors/s), so the reference's 4 corner adds per pixel (~3 sectors/px on
-// realistic flow) cap a scatter at ~120 Gpx/s; fp32 accumulators that round-trip through HBM
+// Why (measured on B200, profiles/r01/, profiles/r02/): an L2 reduction occupies its slice for ~2.4 clocks per 32-byte
+// sector-op whether it carries one 16-byte cell or two (~150 G sector-ops/s over the chip), so the reference's 4 corner
+// adds per pixel (~3 sector-ops/px on realistic flow) cap a scatter at ~50 Gpx/s; fp32 accumulators that round-trip through HBM
 // triple the DRAM traffic (only ~1.5 frames of 1080p accumulators stay L2-resident next to the
 // streaming inputs). Two persistent-kernel variants (CTA-granular with TMA-staged tiles, and
 // warp-granular with global tickets) were built and measured first: their in-kernel dependency
 // tracking (gpu-scope fences, acquire polling, bar.sync) cost more than it saved
 // (profiles/r01/NOTES.md). What survived:
 //
-//  1. the KERNEL BOUNDARY is the only synchronisation: step k is one launch that normalises frame
-//     group k-1 and scatters frame group k, two independent jobs on two accumulator slots; the
-//     in-order stream gives "N(g) after all of S(g)" and "S(g+2) after all of N(g)" for free;
-//  2. the fp32 accumulators stay L2-RESIDENT: a ring of two slots, each one frame group (groups
-//     are sized to ~32 MB: one 1080p frame, or dozens of latents), is re-zeroed by the normalise
-//     pass that reads it, so there is no memset and no accumulator traffic to HBM;
+//  1. the KERNEL BOUNDARY is the only synchronisation: a frame group is scattered by one launch (k_splat_step) and
+//     normalised by the next (k_splat_epilogue), chained by programmatic dependent launch; the in-order stream gives
+//     "normalise(g) after all of scatter(g)" and "scatter(g+1) after all of normalise(g)" for free. (Round 1 ran
+//     normalise(g-1) and scatter(g) in ONE launch on a ring of two slots: dcb_set_option("pipe_ring_slots", 2).)
+//  2. the fp32 accumulators stay L2-RESIDENT: ONE slot of one frame group (a group is ~32 MB: one 1080p frame, or dozens
+//     of latents), re-zeroed by the normalise pass that reads it, so there is no memset and no accumulator traffic to
+//     HBM (measured: the scatter launch reads exactly the compulsory bytes, profiles/r02/ncu_step_slots.txt; two slots
+//     did not stay resident next to the streaming inputs and outputs);
 //  3. one 16-byte `red.global.add.v4.f32` per corner carries all C+1 channels, and corner pieces
 //     are merged IN REGISTERS before they reach L2: the east column of lane i is handed to lane
 //     i+1 by shuffle when their footprints abut, the south row of a pixel is carried to the next
 //     row of the same thread when they abut vertically (~1.2 reds per pixel instead of 4 on smooth
 //     flow; any flow stays correct -- an unmatched piece is simply issued alone);
-//  4. all loads of 8 rows are in flight before the first use; the pre-op (1 | m | exp(m), in*g)
-//     and the post-op (eps rule, divide, (1 - mask), cast, saved normaliser) never touch memory.
+//  4. all loads of 4 rows are in flight before the first use; the pre-op (1 | m | exp(m), in*g)
+//     and the post-op (eps rule, divide, (1 - mask), cast, saved normaliser) never touch memory;
+//  5. epilogues besides the normalise: the occlusion test of compute_mask, and the conditioning recipe's second pass
+//     (KIND = 1: a 2-channel rider scattered with the same footprints into float2 cells, one epilogue that normalises,
+//     tests occlusion, fuses and subtracts) -- two pixels per lane with 256-bit cell loads where the layout allows.
+//  What bounds it: the scatter launch's time is its reduction sector-ops x ~2.4 L2 slice clocks.
 //
 // Replaces controlnet/softsplat.py:240-270 (pre/post ops) + :281-345 (zero-init + softsplat_out).
 #include "dcb_common.cuh"

@@ -169,6 +169,32 @@ def test_residual_recipe_two_pass_pipeline(dcb, orc, variant, shape, group_frame
         L.release_workspaces()
 
 
+@pytest.mark.parametrize("shape", [(2, 3, 96, 120), (3, 3, 33, 47)])
+def test_residual_recipe_strided_views(dcb, orc, shape):
+    """The recipe on the views the reference's datasets hand over (dataset.py:224-230: the two flows are channel slices of ONE
+    4-channel tensor) and on a row-padded ground truth / a channels_last image: same values as the contiguous call."""
+    n, c, h, w = shape
+    L = dcb._lib
+    L.set_option("fwd_path", 1)          # the two-pass pipeline also for these small frames
+    L.release_workspaces()
+    try:
+        g = torch.Generator().manual_seed(29)
+        img = torch.rand(n, c, h, w, generator=g).cuda(); gt = torch.rand(n, c, h, w, generator=g).cuda()
+        f1, f2 = (t.cuda() for t in _flows(8, n, h, w, 2.0))
+        ref = dcb.residual_conditioning(img, f1, f2, gt, "dataset", return_masks=True)
+        both = torch.cat([f1, f2], dim=1)                                   # [N,4,H,W]: flow[:, :2] and flow[:, 2:]
+        gt_pad = torch.zeros(n, c, h, w + 3, device="cuda"); gt_pad[..., :w] = gt
+        img_cl = img.to(memory_format=torch.channels_last)
+        got = dcb.residual_conditioning(img_cl, both[:, :2], both[:, 2:], gt_pad[..., :w], "dataset", return_masks=True)
+        assert not both[:, 2:].is_contiguous() and not gt_pad[..., :w].is_contiguous()
+        assert torch.equal(got[2], ref[2]) and torch.equal(got[3], ref[3])          # masks
+        assert_close(got[0], ref[0], 2e-6, "fused, strided views")
+        assert_close(got[1], ref[1], 2e-6, "residual, strided views")
+    finally:
+        L.set_option("fwd_path", 0)
+        L.release_workspaces()
+
+
 def test_residual_dataset_wrappers(dcb, orc):
     import numpy as np
     rng = np.random.default_rng(0)

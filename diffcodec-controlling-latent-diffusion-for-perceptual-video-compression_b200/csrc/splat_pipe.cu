@@ -216,30 +216,37 @@ __device__ __forceinline__ void scatter_strip(const PipeArgs& a, int frame, int 
             const int off = y0 * W + x0;
             const bool vx0 = x0 >= 0, vx1 = x0 < W - 1, vy0 = y0 >= 0, vy1 = y0 < H - 1;
 
-            // ---- horizontal hand-over: my east column goes to lane + 1 if our footprints abut ----
-            // (the kernel is bound by L2 reduction sectors, not by issue slots: 12 shuffles per pixel
-            //  buy ~20 % fewer sectors on rough flow and ~45 % on smooth flow -- profiles/r01/NOTES.md)
+            // ---- horizontal hand-over: my east pieces go to lane + 1 wherever they fall on its west column ----
+            // footprints abut (lane + 1 sits one cell to the right, same row): NE -> its NW, SE -> its SW;
+            // one to the right and one row DOWN: my SE is its NW; one to the right and one row UP: my NE is its SW
+            // (bench flow: 53 % / 9 % / 9 % of the neighbour pairs). The shuffled values are the raw east pieces, and only
+            // west pieces are ever modified, so chains of hand-overs need no ordering.
+            // (the kernel is bound by L2 reduction sector-ops, not by issue slots: profiles/r02/NOTES.md)
             const int lkey = __shfl_up_sync(full, key, 1);
-            const bool take = lane > 0 && alive && lkey != kDead && lkey + 1 == key;
-            const bool given = (__shfl_down_sync(full, (int)take, 1) != 0) && lane < 31;
+            const bool nb = lane > 0 && alive && lkey != kDead;
+            const bool t_ab = nb && lkey + 1 == key, t_dn = nb && lkey + 1 + pitch == key, t_up = nb && lkey + 1 - pitch == key;
+            const int took = (t_ab ? 3 : 0) | (t_up ? 1 : 0) | (t_dn ? 2 : 0);          // bit 0: the left lane's NE, bit 1: its SE
+            const int right = __shfl_down_sync(full, took, 1);
+            const int gone = lane < 31 ? right : 0;                                       // which of my east pieces the right lane took
 #pragma unroll
             for (int c = 0; c < CA; ++c) {
                 const float en = __shfl_up_sync(full, ne[c], 1), es = __shfl_up_sync(full, se[c], 1);
-                nw[c] = take ? add_rn(nw[c], en) : nw[c];
-                sw[c] = take ? add_rn(sw[c], es) : sw[c];
+                nw[c] = t_ab ? add_rn(nw[c], en) : (t_dn ? add_rn(nw[c], es) : nw[c]);
+                sw[c] = t_ab ? add_rn(sw[c], es) : (t_up ? add_rn(sw[c], en) : sw[c]);
             }
             if (RIDER) {
 #pragma unroll
                 for (int c = 0; c < 2; ++c) {
                     const float en = __shfl_up_sync(full, ne2[c], 1), es = __shfl_up_sync(full, se2[c], 1);
-                    nw2[c] = take ? add_rn(nw2[c], en) : nw2[c];
-                    sw2[c] = take ? add_rn(sw2[c], es) : sw2[c];
+                    nw2[c] = t_ab ? add_rn(nw2[c], en) : (t_dn ? add_rn(nw2[c], es) : nw2[c]);
+                    sw2[c] = t_ab ? add_rn(sw2[c], es) : (t_up ? add_rn(sw2[c], en) : sw2[c]);
                 }
             }
-            const bool east = alive && !given && vx1;
-            red4_if(east && vy0, acc, off + 1, ne);
-            red4_if(east && vy1, acc, off + W + 1, se);
-            if (RIDER) { red2_if(east && vy0, acc2, off + 1, ne2); red2_if(east && vy1, acc2, off + W + 1, se2); }
+            const bool east = alive && vx1;
+            const bool e_n = east && vy0 && !(gone & 1), e_s = east && vy1 && !(gone & 2);
+            red4_if(e_n, acc, off + 1, ne);
+            red4_if(e_s, acc, off + W + 1, se);
+            if (RIDER) { red2_if(e_n, acc2, off + 1, ne2); red2_if(e_s, acc2, off + W + 1, se2); }
             // ---- vertical carry: the previous row's south piece joins my north piece if they abut ----
             const bool join = pend_key == key && alive;            // kDead never equals a live key
 #pragma unroll

@@ -216,6 +216,24 @@ __device__ __forceinline__ void scatter_strip(const PipeArgs& a, int frame, int 
             const int off = y0 * W + x0;
             const bool vx0 = x0 >= 0, vx1 = x0 < W - 1, vy0 = y0 >= 0, vy1 = y0 < H - 1;
 
+            // ---- vertical carry (before the hand-over, whose shuffles must see it): the previous row's south-west piece
+            // joins my NW piece if the footprints abut vertically, or my NE piece if I sit one row down and one cell LEFT ----
+            const bool join = pend_key == key && alive;            // kDead never equals a live key
+            const bool join_e = pend_key == key + 1 && alive;
+#pragma unroll
+            for (int c = 0; c < CA; ++c) {
+                nw[c] = join ? add_rn(nw[c], pend[c]) : nw[c];
+                ne[c] = join_e ? add_rn(ne[c], pend[c]) : ne[c];
+            }
+            red4_if(pend_ok && !join && !join_e, acc, pend_off, pend);
+            if (RIDER) {
+#pragma unroll
+                for (int c = 0; c < 2; ++c) {
+                    nw2[c] = join ? add_rn(nw2[c], pend2[c]) : nw2[c];
+                    ne2[c] = join_e ? add_rn(ne2[c], pend2[c]) : ne2[c];
+                }
+                red2_if(pend_ok && !join && !join_e, acc2, pend_off, pend2);
+            }
             // ---- horizontal hand-over: my east pieces go to lane + 1 wherever they fall on its west column ----
             // footprints abut (lane + 1 sits one cell to the right, same row): NE -> its NW, SE -> its SW;
             // one to the right and one row DOWN: my SE is its NW; one to the right and one row UP: my NE is its SW
@@ -247,16 +265,8 @@ __device__ __forceinline__ void scatter_strip(const PipeArgs& a, int frame, int 
             red4_if(e_n, acc, off + 1, ne);
             red4_if(e_s, acc, off + W + 1, se);
             if (RIDER) { red2_if(e_n, acc2, off + 1, ne2); red2_if(e_s, acc2, off + W + 1, se2); }
-            // ---- vertical carry: the previous row's south piece joins my north piece if they abut ----
-            const bool join = pend_key == key && alive;            // kDead never equals a live key
-#pragma unroll
-            for (int c = 0; c < CA; ++c) nw[c] = join ? add_rn(nw[c], pend[c]) : nw[c];
-            red4_if(pend_ok && !join, acc, pend_off, pend);
             red4_if(alive && vx0 && vy0, acc, off, nw);
             if (RIDER) {
-#pragma unroll
-                for (int c = 0; c < 2; ++c) nw2[c] = join ? add_rn(nw2[c], pend2[c]) : nw2[c];
-                red2_if(pend_ok && !join, acc2, pend_off, pend2);
                 red2_if(alive && vx0 && vy0, acc2, off, nw2);
                 pend2[0] = sw2[0]; pend2[1] = sw2[1];
             }

@@ -217,22 +217,27 @@ __device__ __forceinline__ void scatter_strip(const PipeArgs& a, int frame, int 
             const bool vx0 = x0 >= 0, vx1 = x0 < W - 1, vy0 = y0 >= 0, vy1 = y0 < H - 1;
 
             // ---- vertical carry (before the hand-over, whose shuffles must see it): the previous row's south-west piece
-            // joins my NW piece if the footprints abut vertically, or my NE piece if I sit one row down and one cell LEFT ----
+            // joins my NW piece if the footprints abut vertically, my NE piece if I sit one row down and one cell LEFT, my SW
+            // piece if my footprint is the same one again (bench flow: 54 % / 9 % / 9 % of the row steps) ----
             const bool join = pend_key == key && alive;            // kDead never equals a live key
             const bool join_e = pend_key == key + 1 && alive;
+            const bool join_s = pend_key == key + pitch && alive;   // the SAME footprint again: the piece stays my SW piece (carried on)
 #pragma unroll
             for (int c = 0; c < CA; ++c) {
                 nw[c] = join ? add_rn(nw[c], pend[c]) : nw[c];
                 ne[c] = join_e ? add_rn(ne[c], pend[c]) : ne[c];
+                sw[c] = join_s ? add_rn(sw[c], pend[c]) : sw[c];
             }
-            red4_if(pend_ok && !join && !join_e, acc, pend_off, pend);
+            const bool lone = pend_ok && !join && !join_e && !join_s;
+            red4_if(lone, acc, pend_off, pend);
             if (RIDER) {
 #pragma unroll
                 for (int c = 0; c < 2; ++c) {
                     nw2[c] = join ? add_rn(nw2[c], pend2[c]) : nw2[c];
                     ne2[c] = join_e ? add_rn(ne2[c], pend2[c]) : ne2[c];
+                    sw2[c] = join_s ? add_rn(sw2[c], pend2[c]) : sw2[c];
                 }
-                red2_if(pend_ok && !join && !join_e, acc2, pend_off, pend2);
+                red2_if(lone, acc2, pend_off, pend2);
             }
             // ---- horizontal hand-over: my east pieces go to lane + 1 wherever they fall on its west column ----
             // footprints abut (lane + 1 sits one cell to the right, same row): NE -> its NW, SE -> its SW;

@@ -143,6 +143,11 @@ __device__ __forceinline__ void scatter_strip(const PipeArgs& a, int frame, int 
     float pend2[2] = {0.f, 0.f};
     int pend_key = kDead, pend_off = 0;
     bool pend_ok = false;
+    // The diagonal joins / hand-overs below cost ~35 instructions per pixel and only pay where neighbouring footprints often
+    // fail to abut (rough flow: the launch is bound by reduction sector-ops). `rough_pass` (warp-uniform, per group of kRows
+    // rows) selects them when the flow of the group's first row jumps by more than a quarter pixel between at least
+    // kRoughLanes neighbouring lanes; smooth flow runs the plain form (abutting footprints only) and never pays for them.
+    constexpr int kRoughLanes = 5;
 
     const int xs = xin ? x : 0;
     const TF* fbase = (const TF*)a.flow.p + frame * a.flow.sN;
@@ -178,6 +183,11 @@ __device__ __forceinline__ void scatter_strip(const PipeArgs& a, int frame, int 
 #pragma unroll
                 for (int c = 0; c < C; ++c) iv[r][c] = ld_stream(ip + c * i_sC);
             }
+        }
+        bool rough_pass;
+        {
+            const float dfx = fabsf(flx[0] - __shfl_up_sync(full, flx[0], 1)), dfy = fabsf(fly[0] - __shfl_up_sync(full, fly[0], 1));
+            rough_pass = __popc(__ballot_sync(full, lane > 0 && (dfx > 0.25f || dfy > 0.25f))) >= kRoughLanes;
         }
 #pragma unroll
         for (int r = 0; r < kRows; ++r) {
@@ -216,64 +226,116 @@ __device__ __forceinline__ void scatter_strip(const PipeArgs& a, int frame, int 
             const int off = y0 * W + x0;
             const bool vx0 = x0 >= 0, vx1 = x0 < W - 1, vy0 = y0 >= 0, vy1 = y0 < H - 1;
 
-            // ---- vertical carry (before the hand-over, whose shuffles must see it): the previous row's south-west piece
-            // joins my NW piece if the footprints abut vertically, my NE piece if I sit one row down and one cell LEFT, my SW
-            // piece if my footprint is the same one again (bench flow: 54 % / 9 % / 9 % of the row steps) ----
-            const bool join = pend_key == key && alive;            // kDead never equals a live key
-            const bool join_e = pend_key == key + 1 && alive;
-            const bool join_s = pend_key == key + pitch && alive;   // the SAME footprint again: the piece stays my SW piece (carried on)
-#pragma unroll
-            for (int c = 0; c < CA; ++c) {
-                nw[c] = join ? add_rn(nw[c], pend[c]) : nw[c];
-                ne[c] = join_e ? add_rn(ne[c], pend[c]) : ne[c];
-                sw[c] = join_s ? add_rn(sw[c], pend[c]) : sw[c];
-            }
-            const bool lone = pend_ok && !join && !join_e && !join_s;
-            red4_if(lone, acc, pend_off, pend);
-            if (RIDER) {
-#pragma unroll
-                for (int c = 0; c < 2; ++c) {
-                    nw2[c] = join ? add_rn(nw2[c], pend2[c]) : nw2[c];
-                    ne2[c] = join_e ? add_rn(ne2[c], pend2[c]) : ne2[c];
-                    sw2[c] = join_s ? add_rn(sw2[c], pend2[c]) : sw2[c];
+            if (rough_pass) {
+                // ---- vertical carry (before the hand-over, whose shuffles must see it): the previous row's south-west piece
+                // joins my NW piece if the footprints abut vertically, my NE piece if I sit one row down and one cell LEFT, my SW
+                // piece if my footprint is the same one again (bench flow: 54 % / 9 % / 9 % of the row steps) ----
+                const bool join = pend_key == key && alive;            // kDead never equals a live key
+                const bool join_e = pend_key == key + 1 && alive;
+                const bool join_s = pend_key == key + pitch && alive;   // the SAME footprint again: the piece stays my SW piece (carried on)
+    #pragma unroll
+                for (int c = 0; c < CA; ++c) nw[c] = join ? add_rn(nw[c], pend[c]) : nw[c];
+                if (RIDER) {
+    #pragma unroll
+                    for (int c = 0; c < 2; ++c) nw2[c] = join ? add_rn(nw2[c], pend2[c]) : nw2[c];
                 }
-                red2_if(lone, acc2, pend_off, pend2);
-            }
-            // ---- horizontal hand-over: my east pieces go to lane + 1 wherever they fall on its west column ----
-            // footprints abut (lane + 1 sits one cell to the right, same row): NE -> its NW, SE -> its SW;
-            // one to the right and one row DOWN: my SE is its NW; one to the right and one row UP: my NE is its SW
-            // (bench flow: 53 % / 9 % / 9 % of the neighbour pairs). The shuffled values are the raw east pieces, and only
-            // west pieces are ever modified, so chains of hand-overs need no ordering.
-            // (the kernel is bound by L2 reduction sector-ops, not by issue slots: profiles/r02/NOTES.md)
-            const int lkey = __shfl_up_sync(full, key, 1);
-            const bool nb = lane > 0 && alive && lkey != kDead;
-            const bool t_ab = nb && lkey + 1 == key, t_dn = nb && lkey + 1 + pitch == key, t_up = nb && lkey + 1 - pitch == key;
-            const int took = (t_ab ? 3 : 0) | (t_up ? 1 : 0) | (t_dn ? 2 : 0);          // bit 0: the left lane's NE, bit 1: its SE
-            const int right = __shfl_down_sync(full, took, 1);
-            const int gone = lane < 31 ? right : 0;                                       // which of my east pieces the right lane took
-#pragma unroll
-            for (int c = 0; c < CA; ++c) {
-                const float en = __shfl_up_sync(full, ne[c], 1), es = __shfl_up_sync(full, se[c], 1);
-                nw[c] = t_ab ? add_rn(nw[c], en) : (t_dn ? add_rn(nw[c], es) : nw[c]);
-                sw[c] = t_ab ? add_rn(sw[c], es) : (t_up ? add_rn(sw[c], en) : sw[c]);
-            }
-            if (RIDER) {
-#pragma unroll
-                for (int c = 0; c < 2; ++c) {
-                    const float en = __shfl_up_sync(full, ne2[c], 1), es = __shfl_up_sync(full, se2[c], 1);
-                    nw2[c] = t_ab ? add_rn(nw2[c], en) : (t_dn ? add_rn(nw2[c], es) : nw2[c]);
-                    sw2[c] = t_ab ? add_rn(sw2[c], es) : (t_up ? add_rn(sw2[c], en) : sw2[c]);
+                // the two rarer joins sit behind a warp-uniform test: smooth flow (where they never fire) does not pay for them
+                if (__any_sync(full, join_e || join_s)) {
+    #pragma unroll
+                    for (int c = 0; c < CA; ++c) {
+                        ne[c] = join_e ? add_rn(ne[c], pend[c]) : ne[c];
+                        sw[c] = join_s ? add_rn(sw[c], pend[c]) : sw[c];
+                    }
+                    if (RIDER) {
+    #pragma unroll
+                        for (int c = 0; c < 2; ++c) {
+                            ne2[c] = join_e ? add_rn(ne2[c], pend2[c]) : ne2[c];
+                            sw2[c] = join_s ? add_rn(sw2[c], pend2[c]) : sw2[c];
+                        }
+                    }
                 }
-            }
-            const bool east = alive && vx1;
-            const bool e_n = east && vy0 && !(gone & 1), e_s = east && vy1 && !(gone & 2);
-            red4_if(e_n, acc, off + 1, ne);
-            red4_if(e_s, acc, off + W + 1, se);
-            if (RIDER) { red2_if(e_n, acc2, off + 1, ne2); red2_if(e_s, acc2, off + W + 1, se2); }
-            red4_if(alive && vx0 && vy0, acc, off, nw);
-            if (RIDER) {
-                red2_if(alive && vx0 && vy0, acc2, off, nw2);
-                pend2[0] = sw2[0]; pend2[1] = sw2[1];
+                const bool lone = pend_ok && !join && !join_e && !join_s;
+                red4_if(lone, acc, pend_off, pend);
+                if (RIDER) red2_if(lone, acc2, pend_off, pend2);
+                // ---- horizontal hand-over: my east pieces go to lane + 1 wherever they fall on its west column ----
+                // footprints abut (lane + 1 sits one cell to the right, same row): NE -> its NW, SE -> its SW;
+                // one to the right and one row DOWN: my SE is its NW; one to the right and one row UP: my NE is its SW
+                // (bench flow: 53 % / 9 % / 9 % of the neighbour pairs). The shuffled values are the east pieces after the vertical
+                // joins, and the hand-over only modifies west pieces, so chains of hand-overs need no ordering.
+                // (the kernel is bound by L2 reduction sector-ops, not by issue slots: profiles/r02/NOTES.md)
+                const int lkey = __shfl_up_sync(full, key, 1);
+                const bool nb = lane > 0 && alive && lkey != kDead;
+                const bool t_ab = nb && lkey + 1 == key, t_dn = nb && lkey + 1 + pitch == key, t_up = nb && lkey + 1 - pitch == key;
+                const int took = (t_ab ? 3 : 0) | (t_up ? 1 : 0) | (t_dn ? 2 : 0);          // bit 0: the left lane's NE, bit 1: its SE
+                const int right = __shfl_down_sync(full, took, 1);
+                const int gone = lane < 31 ? right : 0;                                       // which of my east pieces the right lane took
+                const bool diag = __any_sync(full, t_dn || t_up);
+    #pragma unroll
+                for (int c = 0; c < CA; ++c) {
+                    const float en = __shfl_up_sync(full, ne[c], 1), es = __shfl_up_sync(full, se[c], 1);
+                    nw[c] = t_ab ? add_rn(nw[c], en) : nw[c];
+                    sw[c] = t_ab ? add_rn(sw[c], es) : sw[c];
+                    if (diag) {
+                        nw[c] = t_dn ? add_rn(nw[c], es) : nw[c];
+                        sw[c] = t_up ? add_rn(sw[c], en) : sw[c];
+                    }
+                }
+                if (RIDER) {
+    #pragma unroll
+                    for (int c = 0; c < 2; ++c) {
+                        const float en = __shfl_up_sync(full, ne2[c], 1), es = __shfl_up_sync(full, se2[c], 1);
+                        nw2[c] = t_ab ? add_rn(nw2[c], en) : (t_dn ? add_rn(nw2[c], es) : nw2[c]);
+                        sw2[c] = t_ab ? add_rn(sw2[c], es) : (t_up ? add_rn(sw2[c], en) : sw2[c]);
+                    }
+                }
+                const bool east = alive && vx1;
+                const bool e_n = east && vy0 && !(gone & 1), e_s = east && vy1 && !(gone & 2);
+                red4_if(e_n, acc, off + 1, ne);
+                red4_if(e_s, acc, off + W + 1, se);
+                if (RIDER) { red2_if(e_n, acc2, off + 1, ne2); red2_if(e_s, acc2, off + W + 1, se2); }
+                red4_if(alive && vx0 && vy0, acc, off, nw);
+                if (RIDER) {
+                    red2_if(alive && vx0 && vy0, acc2, off, nw2);
+                    pend2[0] = sw2[0]; pend2[1] = sw2[1];
+                }
+            } else {
+                // ---- horizontal hand-over: my east column goes to lane + 1 if our footprints abut ----
+                // (the kernel is bound by L2 reduction sectors, not by issue slots: 12 shuffles per pixel
+                //  buy ~20 % fewer sectors on rough flow and ~45 % on smooth flow -- profiles/r01/NOTES.md)
+                const int lkey = __shfl_up_sync(full, key, 1);
+                const bool take = lane > 0 && alive && lkey != kDead && lkey + 1 == key;
+                const bool given = (__shfl_down_sync(full, (int)take, 1) != 0) && lane < 31;
+    #pragma unroll
+                for (int c = 0; c < CA; ++c) {
+                    const float en = __shfl_up_sync(full, ne[c], 1), es = __shfl_up_sync(full, se[c], 1);
+                    nw[c] = take ? add_rn(nw[c], en) : nw[c];
+                    sw[c] = take ? add_rn(sw[c], es) : sw[c];
+                }
+                if (RIDER) {
+    #pragma unroll
+                    for (int c = 0; c < 2; ++c) {
+                        const float en = __shfl_up_sync(full, ne2[c], 1), es = __shfl_up_sync(full, se2[c], 1);
+                        nw2[c] = take ? add_rn(nw2[c], en) : nw2[c];
+                        sw2[c] = take ? add_rn(sw2[c], es) : sw2[c];
+                    }
+                }
+                const bool east = alive && !given && vx1;
+                red4_if(east && vy0, acc, off + 1, ne);
+                red4_if(east && vy1, acc, off + W + 1, se);
+                if (RIDER) { red2_if(east && vy0, acc2, off + 1, ne2); red2_if(east && vy1, acc2, off + W + 1, se2); }
+                // ---- vertical carry: the previous row's south piece joins my north piece if they abut ----
+                const bool join = pend_key == key && alive;            // kDead never equals a live key
+    #pragma unroll
+                for (int c = 0; c < CA; ++c) nw[c] = join ? add_rn(nw[c], pend[c]) : nw[c];
+                red4_if(pend_ok && !join, acc, pend_off, pend);
+                red4_if(alive && vx0 && vy0, acc, off, nw);
+                if (RIDER) {
+    #pragma unroll
+                    for (int c = 0; c < 2; ++c) nw2[c] = join ? add_rn(nw2[c], pend2[c]) : nw2[c];
+                    red2_if(pend_ok && !join, acc2, pend_off, pend2);
+                    red2_if(alive && vx0 && vy0, acc2, off, nw2);
+                    pend2[0] = sw2[0]; pend2[1] = sw2[1];
+                }
             }
 #pragma unroll
             for (int c = 0; c < CA; ++c) pend[c] = sw[c];
